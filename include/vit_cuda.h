@@ -1,0 +1,160 @@
+/*
+ * vit_cuda.h -- C ABI of the B200 (sm_100a) ViT-B/16 inference engine.
+ *
+ * This is the drop-in boundary for the reference's GPU backend.  It replaces
+ *     void initialize_opencl(void);                                   ViT_opencl.h:21, ViT_opencl.c:74
+ *     void ViT_opencl(ImageData*, Network*, float **prb);             ViT_opencl.h:18, ViT_opencl.c:785
+ *     void Release_opencl(void);                                      ViT_opencl.h:22, ViT_opencl.c:103
+ * (sole caller: Main.c:19,57,86).  The reference-signature adaptor ViT_cuda() that a
+ * Main.c-style driver calls lives in vit_host.h; it is a thin plain-C wrapper over the
+ * three functions below.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types, no exceptions and no exit()
+ * across the boundary.  Every function returning int returns 0 on success or a negative
+ * VIT_E_* code; vit_cuda_last_error() then describes the failure.  There is no CPU
+ * fallback: without a usable sm_100 device every compute entry point fails.
+ *
+ * Threading: like the reference (global g_opencl, ViT_opencl.c:33) the engine is one
+ * process-wide singleton and is not re-entrant; calls must be serialised by the caller.
+ */
+#ifndef VIT_CUDA_H
+#define VIT_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same layout as the reference's `Network` (Network.h:18-21): one fp32 tensor in host
+ * memory, `size` = number of floats.  vit_host.h typedefs `Network` to this. */
+typedef struct vit_tensor {
+    float* data;
+    size_t size;
+} vit_tensor;
+
+enum {
+    VIT_OK            = 0,
+    VIT_E_ARG         = -1,  /* bad argument / tensor size mismatch / not initialised */
+    VIT_E_NODEVICE    = -2,  /* no CUDA device, or device is not sm_100 */
+    VIT_E_CUDA        = -3,  /* CUDA runtime/driver error (see last_error) */
+    VIT_E_NOMEM       = -4,
+    VIT_E_DEVICE_TRAP = -5   /* a kernel watchdog fired (pipeline dead-lock guard) */
+};
+
+/* GEMM-operand storage type.  Accumulation, residual stream, LayerNorm statistics,
+ * softmax and the classifier head are always fp32. */
+enum {
+    VIT_PREC_BF16 = 0,       /* default: BF16 operands, kind::f16 tcgen05, FP32 accumulate */
+    VIT_PREC_FP16 = 1        /* FP16 operands (same tensor-core rate, 3 more mantissa bits) */
+};
+
+#define VIT_NUM_TENSORS 152  /* torchvision vit_b_16 state_dict order, SURVEY.md App. A */
+#define VIT_NUM_CLASSES 1000
+
+/* Validate the 152 weight tensors (sizes for img_size 224 or 384), convert them once to
+ * the operand precision, replicate them on n_gpus devices (devices 0..n_gpus-1) and
+ * allocate per-device workspaces for up to max_batch_per_gpu images per pass.
+ * The host weight arrays are not referenced after return (the reference re-uploads them
+ * on every op, ViT_opencl.c:115-124). */
+int vit_cuda_init(const vit_tensor* networks, int n_tensors, int img_size,
+                  int max_batch_per_gpu, int n_gpus);
+
+/* As vit_cuda_init, with explicit CUDA device ordinals and operand precision.
+ * device_ids == NULL means 0..n_gpus-1. */
+int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size,
+                     int max_batch_per_gpu, int n_gpus, const int* device_ids, int precision);
+
+/* Forward n images.  images_nchw: host, contiguous [n][3][S][S] fp32 (pageable or pinned).
+ * logits_out: host [n][1000] fp32 pre-softmax logits.  top1_out: nullable, [n] argmax
+ * (lowest index wins ties).  Images are sharded contiguously over the GPUs; each shard is
+ * processed in passes of at most max_batch_per_gpu images with H2D / compute / D2H
+ * overlapped.  Synchronous: everything is on the host when the call returns. */
+int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out);
+
+/* Device-resident variant for one GPU slot (0 <= gpu_slot < n_gpus): d_images and d_logits
+ * are device pointers on that GPU, n <= max_batch_per_gpu.  Work is enqueued on the
+ * engine's stream for that slot and the call returns after it has completed. */
+int vit_cuda_forward_device(int gpu_slot, const float* d_images, int n, float* d_logits);
+
+/* Enqueue-only form of the above (no synchronisation), for timing with events, plus the
+ * matching synchronise.  vit_cuda_stream() returns the cudaStream_t of a slot as void*. */
+int   vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d_logits);
+int   vit_cuda_sync(int gpu_slot);
+void* vit_cuda_stream(int gpu_slot);
+
+/* Release all device memory, streams and pinned staging.  Safe to call when not
+ * initialised. */
+void vit_cuda_free(void);
+
+/* Thread-local, never NULL; valid until the next failing call on this thread. */
+const char* vit_cuda_last_error(void);
+
+/* Number of kernels the engine launched since init (all slots); used by bench.py to
+ * report gpu_launches. */
+long long vit_cuda_launch_count(void);
+
+/* Facts about the engine/device, for logs: fills up to n entries of
+ * {sm_count, cc_major, cc_minor, max_batch, tokens, precision, n_gpus, ws_bytes>>20}. */
+int vit_cuda_info(long long* out, int n);
+
+/* Device memory helpers so that a host program without a CUDA toolchain (plain C driver,
+ * ctypes) can stage device-resident inputs for vit_cuda_forward_device. */
+int vit_cuda_dev_alloc(int gpu_slot, size_t bytes, void** d_ptr);
+int vit_cuda_dev_free(int gpu_slot, void* d_ptr);
+int vit_cuda_dev_upload(int gpu_slot, void* d_dst, const void* h_src, size_t bytes);
+int vit_cuda_dev_download(int gpu_slot, void* h_dst, const void* d_src, size_t bytes);
+int vit_cuda_host_alloc_pinned(size_t bytes, void** h_ptr);
+int vit_cuda_host_free_pinned(void* h_ptr);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-operator entry points.  Each runs ONE kernel of the hot path on device 0 with host
+ * inputs/outputs (upload, launch, download); they exist so that every kernel can be checked
+ * against the oracle's restatement of the corresponding reference function.  They use the
+ * same kernels, tile shapes and epilogues as vit_cuda_forward.  `precision` is VIT_PREC_*.
+ * ------------------------------------------------------------------------------------------ */
+
+/* epilogue selectors for vit_cuda_op_linear */
+enum {
+    VIT_EPI_BIAS          = 0,  /* y = x W^T + b                 (in_proj, ViT_seq.c:134-147)  */
+    VIT_EPI_BIAS_GELU     = 1,  /* y = gelu(x W^T + b)           (mlp_0,   ViT_seq.c:260-264)  */
+    VIT_EPI_BIAS_RESIDUAL = 2   /* y = r + x W^T + b, fp32 out   (out_proj/mlp_3 + residual,
+                                                                  ViT_seq.c:219-227,286-288,266,297-299) */
+};
+
+/* x: [m][k] fp32 (rounded to the operand precision on upload), W: [n][k] fp32 (ditto),
+ * b: [n] fp32, residual: [m][n] fp32 or NULL, y: [m][n] fp32 (for the two operand-precision
+ * outputs the device result is widened back to fp32).  Replaces linear_layer,
+ * ViT_seq.c:240-250 / linear_forward_kernel, fc1_kernel, fc2_kernel in kernel.cl. */
+int vit_cuda_op_linear(const float* x, const float* W, const float* b, const float* residual,
+                       float* y, int m, int n, int k, int epilogue, int precision);
+
+/* LayerNorm rows of x [rows][768] (fp32) -> y [rows][768] (operand precision widened to
+ * fp32).  Replaces layer_norm, ViT_seq.c:103-121 / layer_norm_kernel, kernel.cl:6-80
+ * (with the oracle's eps 1e-6, which the OpenCL kernel drops). */
+int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float* y,
+                          int rows, int precision);
+
+/* Fused softmax(QK^T/8)V for `batch` images of `tokens` tokens, 12 heads of 64.
+ * qkv: [batch*tokens][2304] fp32 (Q|K|V, rounded to operand precision on upload),
+ * out: [batch*tokens][768] fp32.  Replaces ViT_seq.c:156-215 / the per-head
+ * MHA_gemm_kernel + softmax_reduction_kernel loop, ViT_opencl.c:546-564. */
+int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision);
+
+/* Patch embedding for `batch` images [batch][3][S][S]: conv_proj + class token + position
+ * embedding -> out [batch*tokens][768] fp32.  Replaces Conv2d/flatten_transpose/
+ * class_token/pos_emb, ViT_seq.c:25-101 / Conv2d_Kernel, kernel.cl:120-175. */
+int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w,
+                      const float* conv_b, const float* pos, float* out,
+                      int batch, int img_size, int precision);
+
+/* Final LayerNorm of the class rows + classifier: x [batch*tokens][768] fp32 ->
+ * logits [batch][1000] fp32 (all fp32 arithmetic).  Replaces ViT_seq.c:429-435. */
+int vit_cuda_op_head(const float* x, const float* ln_w, const float* ln_b,
+                     const float* head_w, const float* head_b, float* logits,
+                     int batch, int tokens);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIT_CUDA_H */

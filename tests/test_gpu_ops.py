@@ -1,0 +1,105 @@
+"""Kernel-level parity: every CUDA kernel of the hot path, called through the C ABI
+(vit_cuda_op_*), against the oracle's restatement of the reference function it replaces.
+Inputs are pre-rounded to the operand precision on the host so the comparison isolates the
+kernel (fp32 accumulation order + one output rounding)."""
+import numpy as np
+import pytest
+
+from conftest import round_operand
+
+pytestmark = pytest.mark.gpu
+
+PRECS = [0, 1]  # bf16, fp16
+OUT_RTOL = {0: 2.0 ** -8, 1: 2.0 ** -11}  # one rounding of the output to the operand type
+
+
+def _rand(shape, seed, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+def _close(got, ref, rtol, atol, what):
+    err = np.abs(got - ref)
+    bound = atol + rtol * np.abs(ref)
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {bad.sum()} / {bad.size} out of tolerance; max abs err {err.max():.3e} "
+                           f"at {np.unravel_index(err.argmax(), err.shape)}, ref there {ref.flat[err.argmax()]:.4f}, "
+                           f"got {got.flat[err.argmax()]:.4f}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("m,n,k", [(197, 2304, 768), (197, 768, 768), (128, 256, 64), (300, 768, 3072), (1000, 3072, 768)])
+def test_linear_bias(vit, oracle, prec, m, n, k):
+    x = round_operand(_rand((m, k), 1), prec)
+    W = round_operand(_rand((n, k), 2, 0.03), prec)
+    b = _rand((n,), 3, 0.1)
+    got = vit.op_linear(x, W, b, epilogue=vit.EPI_BIAS, precision=prec)
+    ref = oracle.linear(x, W, b)
+    _close(got, ref, OUT_RTOL[prec], 2e-4, f"linear+bias {m}x{n}x{k}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_linear_bias_gelu(vit, oracle, prec):
+    m, n, k = 197, 3072, 768
+    x = round_operand(_rand((m, k), 4), prec)
+    W = round_operand(_rand((n, k), 5, 0.05), prec)
+    b = _rand((n,), 6, 0.1)
+    got = vit.op_linear(x, W, b, epilogue=vit.EPI_BIAS_GELU, precision=prec)
+    ref = oracle.gelu(oracle.linear(x, W, b))
+    _close(got, ref, OUT_RTOL[prec], 3e-4, "linear+bias+gelu")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("m,n,k", [(197, 768, 768), (197, 768, 3072), (2 * 197, 768, 3072)])
+def test_linear_bias_residual(vit, oracle, prec, m, n, k):
+    x = round_operand(_rand((m, k), 7), prec)
+    W = round_operand(_rand((n, k), 8, 0.03), prec)
+    b = _rand((n,), 9, 0.1)
+    r = _rand((m, n), 10)
+    got = vit.op_linear(x, W, b, residual=r, epilogue=vit.EPI_BIAS_RESIDUAL, precision=prec)
+    ref = r + oracle.linear(x, W, b)
+    _close(got, ref, 1e-5, 3e-4, f"linear+bias+residual {m}x{n}x{k}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("rows", [1, 197, 1000])
+def test_layernorm(vit, oracle, prec, rows):
+    x = _rand((rows, 768), 11, 2.0) + 0.5
+    w = 1.0 + _rand((768,), 12, 0.1)
+    b = _rand((768,), 13, 0.1)
+    got = vit.op_layernorm(x, w, b, precision=prec)
+    ref = oracle.layer_norm(x, w, b)
+    _close(got, ref, OUT_RTOL[prec], 1e-4, f"layernorm rows={rows}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 256), (2, 130)])
+def test_attention(vit, oracle, prec, batch, tokens):
+    qkv = round_operand(_rand((batch * tokens, 2304), 14 + tokens), prec)
+    got = vit.op_attention(qkv, batch, tokens, precision=prec)
+    ref = np.empty((batch * tokens, 768), dtype=np.float32)
+    for i in range(batch):
+        blk = qkv[i * tokens:(i + 1) * tokens]
+        ref[i * tokens:(i + 1) * tokens] = oracle.attention_core(
+            np.ascontiguousarray(blk[:, :768]), np.ascontiguousarray(blk[:, 768:1536]), np.ascontiguousarray(blk[:, 1536:]))
+    # P is rounded to the operand type before P.V and the output once more
+    _close(got, ref, 4 * OUT_RTOL[prec], 6 * OUT_RTOL[prec], f"attention batch={batch} tokens={tokens}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_embed(vit, oracle, prec, weights224):
+    w = weights224
+    imgs = round_operand(vit.synth_images(3, 224, 21), prec)
+    conv_w = round_operand(w[1], prec)
+    got = vit.op_embed(imgs, w[0], conv_w, w[2], w[3], precision=prec)
+    ref = np.concatenate([oracle.embed(imgs[i], w[0], conv_w, w[2], w[3]) for i in range(3)])
+    _close(got, ref, 1e-5, 2e-5, "patch embedding")
+
+
+def test_head(vit, oracle, weights224):
+    w = weights224
+    batch, tokens = 5, 197
+    x = _rand((batch * tokens, 768), 31, 1.5)
+    got = vit.op_head(x, w[148], w[149], w[150], w[151], batch, tokens)
+    cls_rows = np.ascontiguousarray(x[::tokens])
+    ref = oracle.linear(oracle.layer_norm(cls_rows, w[148], w[149]), w[150], w[151])
+    _close(got, ref, 1e-5, 2e-5, "final LN + head")

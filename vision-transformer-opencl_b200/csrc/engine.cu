@@ -1,0 +1,763 @@
+// engine.cu -- the C ABI of include/vit_cuda.h: weight upload, workspaces, TMA descriptors,
+// the ViT-B/16 forward schedule (ViT_seq.c:337-439 / ViT_opencl.c:785-883 re-expressed as a
+// batch of token-flattened kernels) and the single-operator test entry points.
+//
+// There is deliberately no CPU fallback: every entry point fails with VIT_E_NODEVICE unless a
+// compute-capability-10.x device is present.
+#include "../../include/vit_cuda.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "attention_sm100.cuh"
+#include "gemm_sm100.cuh"
+#include "kernels_misc.cuh"
+
+namespace {
+
+using namespace vit;
+
+constexpr int kHeads = 12, kHidden = 3072, kDepth = 12, kClasses = VIT_NUM_CLASSES, kPatch = 16;
+
+thread_local char t_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                               \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return set_err(e__ == cudaErrorMemoryAllocation ? VIT_E_NOMEM : VIT_E_CUDA,            \
+                           "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));  \
+    } while (0)
+#define VIT_TRY(expr)          \
+    do {                       \
+        int r__ = (expr);      \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------ driver API
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+int load_driver() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return 0;
+}
+
+// 2-D row-major [rows][cols] tensor of 16-bit elements, box {box_cols, box_rows}, 128B swizzle.
+int make_tmap(CUtensorMap* m, int prec, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+              uint32_t box_rows) {
+    VIT_TRY(load_driver());
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(m, prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu box=%ux%u", (int)r,
+                       (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ launches
+constexpr int kGemmBN = 256, kGemmStages = 4, kGemmEpiWG = 2;
+constexpr int kGemmThreads = (GEMM_NON_EPI_WARPS + 4 * kGemmEpiWG) * 32;
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(VIT_E_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+template <typename T, int EPI>
+int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count, cudaStream_t st) {
+    using L = GemmSmem<kGemmBN, kGemmStages>;
+    auto kern = gemm_sm100_kernel<T, kGemmBN, kGemmStages, kGemmEpiWG, EPI>;
+    static bool configured = false;  // per instantiation; attribute is per device but identical on all
+    static int configured_dev_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured || !(configured_dev_mask & (1 << dev))) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+        configured = true;
+        configured_dev_mask |= 1 << dev;
+    }
+    if (p.N % kGemmBN || p.K % GEMM_BK || p.N > GEMM_MAX_N || p.M <= 0)
+        return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64, N<=3072)", p.M, p.N, p.K);
+    const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / kGemmBN);
+    const int grid = std::min(tiles, sm_count);
+    kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, p);
+    return check_launch("gemm");
+}
+
+template <int EPI>
+int launch_gemm(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
+                cudaStream_t st) {
+    return prec == VIT_PREC_FP16 ? launch_gemm_t<__half, EPI>(ta, tb, p, sm_count, st)
+                                 : launch_gemm_t<__nv_bfloat16, EPI>(ta, tb, p, sm_count, st);
+}
+
+template <typename T>
+int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
+    auto kern = attention_sm100_kernel<T>;
+    const int smem = attn_smem_bytes(p.kpad);
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<p.batch * kHeads, ATTN_THREADS, smem, st>>>(tq, tkv, p);
+    return check_launch("attention");
+}
+int launch_attention(int prec, const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
+    if (p.tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", p.tokens);
+    return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tq, tkv, p, st)
+                                 : launch_attention_t<__nv_bfloat16>(tq, tkv, p, st);
+}
+
+int launch_layernorm(int prec, const float* x, const float* w, const float* b, void* y, int rows, cudaStream_t st) {
+    const int grid = (rows + 7) / 8;
+    if (prec == VIT_PREC_FP16) layernorm_kernel<__half><<<grid, 256, 0, st>>>(x, w, b, static_cast<__half*>(y), rows);
+    else layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, w, b, static_cast<__nv_bfloat16*>(y), rows);
+    return check_launch("layernorm");
+}
+
+int launch_patchify(int prec, const float* img, void* patches, int batch, int S, int sm_count, cudaStream_t st) {
+    const size_t total4 = static_cast<size_t>(batch) * 3 * S * S / 4;
+    const int grid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(sm_count) * 16));
+    if (prec == VIT_PREC_FP16) patchify_kernel<__half><<<grid, 256, 0, st>>>(img, static_cast<__half*>(patches), batch, S);
+    else patchify_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, static_cast<__nv_bfloat16*>(patches), batch, S);
+    return check_launch("patchify");
+}
+
+int launch_convert_from_f32(int prec, const float* src, void* dst, size_t n, cudaStream_t st) {
+    const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+    if (prec == VIT_PREC_FP16) convert_from_f32_kernel<__half><<<grid, 256, 0, st>>>(src, static_cast<__half*>(dst), n);
+    else convert_from_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    return check_launch("convert");
+}
+int launch_convert_to_f32(int prec, const void* src, float* dst, size_t n, cudaStream_t st) {
+    const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+    if (prec == VIT_PREC_FP16) convert_to_f32_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
+    else convert_to_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst, n);
+    return check_launch("convert");
+}
+
+// ------------------------------------------------------------------------------------ device check
+int check_device(int dev, int* sm_count) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return set_err(VIT_E_NODEVICE, "no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (dev < 0 || dev >= count) return set_err(VIT_E_NODEVICE, "device %d requested, %d present", dev, count);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return set_err(VIT_E_NODEVICE, "device %d (%s) is sm_%d%d; this engine is built for sm_100a only", dev, prop.name,
+                       prop.major, prop.minor);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return 0;
+}
+
+int watchdog_or_cuda_error(cudaError_t e, const char* what) {
+    unsigned int flag = 0;
+    // After a trap the context is dead and this read fails too; report the trap from the error code.
+    if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction || e == cudaErrorAssert)
+        return set_err(VIT_E_DEVICE_TRAP, "%s: device trap (%s) -- kernel watchdog or fault", what, cudaGetErrorString(e));
+    (void)flag;
+    return set_err(VIT_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------ engine state
+struct LayerW {
+    float *ln1_w, *ln1_b, *qkv_b, *out_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;  // fp32
+    void *qkv_w, *out_w, *fc1_w, *fc2_w;                                    // operand precision
+    CUtensorMap tm_qkv_w, tm_out_w, tm_fc1_w, tm_fc2_w;
+};
+
+struct DeviceCtx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    std::vector<void*> allocs;
+    // weights
+    float *cls = nullptr, *conv_b = nullptr, *pos = nullptr, *lnf_w = nullptr, *lnf_b = nullptr, *head_w = nullptr,
+          *head_b = nullptr;
+    void* conv_w = nullptr;
+    CUtensorMap tm_conv_w;
+    LayerW layer[kDepth];
+    // workspace (capacity = max_batch images)
+    float* images[2] = {nullptr, nullptr};
+    void *patches = nullptr, *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr;
+    float *x = nullptr, *cls_ln = nullptr, *logits = nullptr;
+    CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_q, tm_kv;
+    size_t ws_bytes = 0;
+};
+
+struct Engine {
+    bool up = false;
+    int img = 0, grid = 0, patches = 0, tokens = 0, max_batch = 0, prec = 0;
+    std::vector<DeviceCtx> ctx;
+};
+Engine g_eng;
+
+int dev_alloc(DeviceCtx& c, void** p, size_t bytes, bool zero) {
+    CU_TRY(cudaMalloc(p, bytes));
+    c.allocs.push_back(*p);
+    c.ws_bytes += bytes;
+    if (zero) CU_TRY(cudaMemsetAsync(*p, 0, bytes, c.stream));
+    return 0;
+}
+
+int upload_f32(DeviceCtx& c, float** dst, const vit_tensor& t) {
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(dst), t.size * sizeof(float), false));
+    CU_TRY(cudaMemcpyAsync(*dst, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    return 0;
+}
+
+int upload_operand(DeviceCtx& c, void** dst, const vit_tensor& t, float* scratch, int prec) {
+    VIT_TRY(dev_alloc(c, dst, t.size * 2, false));
+    CU_TRY(cudaMemcpyAsync(scratch, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    return launch_convert_from_f32(prec, scratch, *dst, t.size, c.stream);
+}
+
+void destroy_ctx(DeviceCtx& c) {
+    if (c.device < 0) return;
+    cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    for (void* p : c.allocs) cudaFree(p);
+    c.allocs.clear();
+    for (int i = 0; i < 2; ++i) {
+        if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
+        if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
+    }
+    if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    c = DeviceCtx();
+}
+
+int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
+    c.device = device;
+    VIT_TRY(check_device(device, &c.sm_count));
+    CU_TRY(cudaSetDevice(device));
+    CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+    }
+    const int prec = e.prec;
+    // ---- weights: fp32 small tensors verbatim, GEMM operands converted once
+    float* scratch = nullptr;
+    CU_TRY(cudaMalloc(&scratch, static_cast<size_t>(kHidden) * kDim * sizeof(float)));
+    int rc = 0;
+    do {
+        if ((rc = upload_f32(c, &c.cls, w[0]))) break;
+        if ((rc = upload_operand(c, &c.conv_w, w[1], scratch, prec))) break;
+        if ((rc = upload_f32(c, &c.conv_b, w[2]))) break;
+        if ((rc = upload_f32(c, &c.pos, w[3]))) break;
+        for (int l = 0; l < kDepth && !rc; ++l) {
+            const vit_tensor* lw = w + 4 + 12 * l;
+            LayerW& L = c.layer[l];
+            if ((rc = upload_f32(c, &L.ln1_w, lw[0]))) break;
+            if ((rc = upload_f32(c, &L.ln1_b, lw[1]))) break;
+            if ((rc = upload_operand(c, &L.qkv_w, lw[2], scratch, prec))) break;
+            if ((rc = upload_f32(c, &L.qkv_b, lw[3]))) break;
+            if ((rc = upload_operand(c, &L.out_w, lw[4], scratch, prec))) break;
+            if ((rc = upload_f32(c, &L.out_b, lw[5]))) break;
+            if ((rc = upload_f32(c, &L.ln2_w, lw[6]))) break;
+            if ((rc = upload_f32(c, &L.ln2_b, lw[7]))) break;
+            if ((rc = upload_operand(c, &L.fc1_w, lw[8], scratch, prec))) break;
+            if ((rc = upload_f32(c, &L.fc1_b, lw[9]))) break;
+            if ((rc = upload_operand(c, &L.fc2_w, lw[10], scratch, prec))) break;
+            if ((rc = upload_f32(c, &L.fc2_b, lw[11]))) break;
+            if ((rc = make_tmap(&L.tm_qkv_w, prec, L.qkv_w, kDim, 3 * kDim, GEMM_BK, kGemmBN))) break;
+            if ((rc = make_tmap(&L.tm_out_w, prec, L.out_w, kDim, kDim, GEMM_BK, kGemmBN))) break;
+            if ((rc = make_tmap(&L.tm_fc1_w, prec, L.fc1_w, kDim, kHidden, GEMM_BK, kGemmBN))) break;
+            if ((rc = make_tmap(&L.tm_fc2_w, prec, L.fc2_w, kHidden, kDim, GEMM_BK, kGemmBN))) break;
+        }
+        if (rc) break;
+        if ((rc = upload_f32(c, &c.lnf_w, w[148]))) break;
+        if ((rc = upload_f32(c, &c.lnf_b, w[149]))) break;
+        if ((rc = upload_f32(c, &c.head_w, w[150]))) break;
+        if ((rc = upload_f32(c, &c.head_b, w[151]))) break;
+        if ((rc = make_tmap(&c.tm_conv_w, prec, c.conv_w, kDim, kDim, GEMM_BK, kGemmBN))) break;
+    } while (0);
+    cudaError_t se = cudaStreamSynchronize(c.stream);
+    cudaFree(scratch);
+    if (rc) return rc;
+    if (se != cudaSuccess) return watchdog_or_cuda_error(se, "weight upload");
+
+    // ---- workspaces.  Zero-filled once: attention may read (and multiply by P == 0) rows
+    // past the last image of a pass, which must therefore always hold finite values.
+    const size_t B = e.max_batch, rows = B * e.tokens, prow = B * e.patches;
+    const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
+    for (int i = 0; i < 2; ++i) VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.images[i]), B * img_elems * 4, false));
+    VIT_TRY(dev_alloc(c, &c.patches, prow * kDim * 2, true));
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.x), rows * kDim * 4, true));
+    VIT_TRY(dev_alloc(c, &c.xn, rows * kDim * 2, true));
+    VIT_TRY(dev_alloc(c, &c.qkv, rows * 3 * kDim * 2, true));
+    VIT_TRY(dev_alloc(c, &c.ao, rows * kDim * 2, true));
+    VIT_TRY(dev_alloc(c, &c.hid, rows * kHidden * 2, true));
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.cls_ln), B * kDim * 4, true));
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.logits), B * kClasses * 4, true));
+    VIT_TRY(make_tmap(&c.tm_patches, prec, c.patches, kDim, prow, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_xn, prec, c.xn, kDim, rows, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_ao, prec, c.ao, kDim, rows, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));
+    if (e.tokens <= 256) {
+        const int kpad = (e.tokens + 15) / 16 * 16;
+        VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, 256));
+        VIT_TRY(make_tmap(&c.tm_kv, prec, c.qkv, 3 * kDim, rows, ATTN_DH, kpad));
+    }
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+// Enqueue the whole forward for nb images already resident in d_images (fp32 NCHW) on c.stream.
+int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
+    cudaStream_t st = c.stream;
+    const int prec = e.prec;
+    const int rows = nb * e.tokens;
+    // conv_proj: patch rows -> GEMM with (+bias, +pos_embedding, row remap) epilogue; class rows aside
+    VIT_TRY(launch_patchify(prec, d_images, c.patches, nb, e.img, c.sm_count, st));
+    cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(c.x, c.cls, c.pos, nb, e.tokens);
+    VIT_TRY(check_launch("cls_rows"));
+    {
+        GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
+        VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
+    }
+    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f};
+    for (int l = 0; l < kDepth; ++l) {
+        const LayerW& L = c.layer[l];
+        VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
+        {
+            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0};
+            VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
+        }
+        VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, st));
+        {
+            GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x, 0, 0};
+            VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
+        }
+        VIT_TRY(launch_layernorm(prec, c.x, L.ln2_w, L.ln2_b, c.xn, rows, st));
+        {
+            GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr, 0, 0};
+            VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
+        }
+        {
+            GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x, 0, 0};
+            VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
+        }
+    }
+    head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
+    VIT_TRY(check_launch("head_ln"));
+    head_gemm_kernel<<<dim3((kClasses + 63) / 64, (nb + 63) / 64), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
+                                                                                kClasses);
+    return check_launch("head_gemm");
+}
+
+size_t tensor_numel(int idx, int img) {
+    const size_t g = img / kPatch, tokens = g * g + 1;
+    switch (idx) {
+        case 0: case 2: case 148: case 149: return kDim;
+        case 1: return static_cast<size_t>(kDim) * 3 * kPatch * kPatch;
+        case 3: return tokens * kDim;
+        case 150: return static_cast<size_t>(kClasses) * kDim;
+        case 151: return kClasses;
+    }
+    switch ((idx - 4) % 12) {
+        case 2: return static_cast<size_t>(3) * kDim * kDim;
+        case 3: return 3 * kDim;
+        case 4: return static_cast<size_t>(kDim) * kDim;
+        case 8: case 10: return static_cast<size_t>(kHidden) * kDim;
+        case 9: return kHidden;
+        default: return kDim;
+    }
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+const char* vit_cuda_last_error(void) { return t_err; }
+long long vit_cuda_launch_count(void) { return g_launches.load(); }
+
+void vit_cuda_free(void) {
+    for (auto& c : g_eng.ctx) destroy_ctx(c);
+    g_eng.ctx.clear();
+    g_eng.up = false;
+}
+
+int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size, int max_batch_per_gpu, int n_gpus,
+                     const int* device_ids, int precision) {
+    if (g_eng.up) vit_cuda_free();
+    if (!networks || n_tensors != VIT_NUM_TENSORS) return set_err(VIT_E_ARG, "expected %d weight tensors, got %d", VIT_NUM_TENSORS, n_tensors);
+    if (img_size <= 0 || img_size % kPatch || img_size > 1024) return set_err(VIT_E_ARG, "img_size %d must be a positive multiple of 16", img_size);
+    if (max_batch_per_gpu <= 0 || n_gpus <= 0) return set_err(VIT_E_ARG, "max_batch_per_gpu and n_gpus must be positive");
+    if (precision != VIT_PREC_BF16 && precision != VIT_PREC_FP16) return set_err(VIT_E_ARG, "unknown precision %d", precision);
+    for (int i = 0; i < n_tensors; ++i)
+        if (!networks[i].data || networks[i].size != tensor_numel(i, img_size))
+            return set_err(VIT_E_ARG, "weight tensor %d: have %zu floats%s, need %zu for img_size %d", i, networks[i].size,
+                           networks[i].data ? "" : " (missing)", tensor_numel(i, img_size), img_size);
+    Engine& e = g_eng;
+    e.img = img_size;
+    e.grid = img_size / kPatch;
+    e.patches = e.grid * e.grid;
+    e.tokens = e.patches + 1;
+    e.max_batch = max_batch_per_gpu;
+    e.prec = precision;
+    e.ctx.assign(n_gpus, DeviceCtx());
+    for (int g = 0; g < n_gpus; ++g) {
+        const int rc = init_ctx(e.ctx[g], device_ids ? device_ids[g] : g, networks, e);
+        if (rc) {
+            char keep[sizeof(t_err)];
+            memcpy(keep, t_err, sizeof(keep));
+            vit_cuda_free();
+            memcpy(t_err, keep, sizeof(keep));
+            return rc;
+        }
+    }
+    e.up = true;
+    return 0;
+}
+
+int vit_cuda_init(const vit_tensor* networks, int n_tensors, int img_size, int max_batch_per_gpu, int n_gpus) {
+    return vit_cuda_init_ex(networks, n_tensors, img_size, max_batch_per_gpu, n_gpus, nullptr, VIT_PREC_BF16);
+}
+
+int vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d_logits) {
+    Engine& e = g_eng;
+    if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
+    if (gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
+    if (n <= 0 || n > e.max_batch) return set_err(VIT_E_ARG, "n=%d outside (0, max_batch=%d]", n, e.max_batch);
+    if (e.tokens > 256) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    DeviceCtx& c = e.ctx[gpu_slot];
+    CU_TRY(cudaSetDevice(c.device));
+    return enqueue_forward(c, e, d_images, n, d_logits);
+}
+
+int vit_cuda_sync(int gpu_slot) {
+    Engine& e = g_eng;
+    if (!e.up || gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
+    CU_TRY(cudaSetDevice(e.ctx[gpu_slot].device));
+    const cudaError_t se = cudaStreamSynchronize(e.ctx[gpu_slot].stream);
+    if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
+    return 0;
+}
+
+void* vit_cuda_stream(int gpu_slot) {
+    if (!g_eng.up || gpu_slot < 0 || gpu_slot >= (int)g_eng.ctx.size()) return nullptr;
+    return g_eng.ctx[gpu_slot].stream;
+}
+
+int vit_cuda_forward_device(int gpu_slot, const float* d_images, int n, float* d_logits) {
+    VIT_TRY(vit_cuda_enqueue_device(gpu_slot, d_images, n, d_logits));
+    return vit_cuda_sync(gpu_slot);
+}
+
+int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out) {
+    Engine& e = g_eng;
+    if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
+    if (!images_nchw || !logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (n == 0) return 0;
+    if (e.tokens > 256) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    const int G = static_cast<int>(e.ctx.size());
+    const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
+    const int per_gpu = (n + G - 1) / G;  // contiguous shards
+    int max_passes = 0;
+    for (int g = 0; g < G; ++g) {
+        const int lo = std::min(n, g * per_gpu), hi = std::min(n, lo + per_gpu);
+        max_passes = std::max(max_passes, (hi - lo + e.max_batch - 1) / e.max_batch);
+    }
+    // pass-major issue order so that all GPUs are fed before any host-side wait
+    for (int pass = 0; pass < max_passes; ++pass) {
+        for (int g = 0; g < G; ++g) {
+            DeviceCtx& c = e.ctx[g];
+            const int lo = std::min(n, g * per_gpu), hi = std::min(n, lo + per_gpu);
+            const int first = lo + pass * e.max_batch;
+            if (first >= hi) continue;
+            const int nb = std::min(e.max_batch, hi - first);
+            const int buf = pass & 1;
+            CU_TRY(cudaSetDevice(c.device));
+            // H2D of this pass overlaps the previous pass's compute (other image buffer)
+            if (pass >= 2) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_done[buf], 0));
+            CU_TRY(cudaMemcpyAsync(c.images[buf], images_nchw + static_cast<size_t>(first) * img_elems,
+                                   static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+            CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
+            CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
+            VIT_TRY(enqueue_forward(c, e, c.images[buf], nb, c.logits));
+            CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
+            CU_TRY(cudaMemcpyAsync(logits_out + static_cast<size_t>(first) * kClasses, c.logits,
+                                   static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        DeviceCtx& c = e.ctx[g];
+        CU_TRY(cudaSetDevice(c.device));
+        const cudaError_t se = cudaStreamSynchronize(c.stream);
+        if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
+    }
+    if (top1_out)
+        for (int i = 0; i < n; ++i) {
+            const float* row = logits_out + static_cast<size_t>(i) * kClasses;
+            int best = 0;
+            for (int j = 1; j < kClasses; ++j)
+                if (row[j] > row[best]) best = j;
+            top1_out[i] = best;
+        }
+    return 0;
+}
+
+int vit_cuda_info(long long* out, int n) {
+    if (!g_eng.up || !out) return set_err(VIT_E_ARG, "engine not initialised");
+    const DeviceCtx& c = g_eng.ctx[0];
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, c.device));
+    const long long v[8] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
+                            (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20)};
+    for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ memory helpers
+static int slot_device(int gpu_slot, int* dev) {
+    if (g_eng.up) {
+        if (gpu_slot < 0 || gpu_slot >= (int)g_eng.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
+        *dev = g_eng.ctx[gpu_slot].device;
+    } else {
+        *dev = gpu_slot;
+        VIT_TRY(check_device(gpu_slot, nullptr));
+    }
+    return 0;
+}
+int vit_cuda_dev_alloc(int gpu_slot, size_t bytes, void** d_ptr) {
+    int dev;
+    VIT_TRY(slot_device(gpu_slot, &dev));
+    CU_TRY(cudaSetDevice(dev));
+    CU_TRY(cudaMalloc(d_ptr, bytes));
+    return 0;
+}
+int vit_cuda_dev_free(int gpu_slot, void* d_ptr) {
+    int dev;
+    VIT_TRY(slot_device(gpu_slot, &dev));
+    CU_TRY(cudaSetDevice(dev));
+    CU_TRY(cudaFree(d_ptr));
+    return 0;
+}
+int vit_cuda_dev_upload(int gpu_slot, void* d_dst, const void* h_src, size_t bytes) {
+    int dev;
+    VIT_TRY(slot_device(gpu_slot, &dev));
+    CU_TRY(cudaSetDevice(dev));
+    CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int vit_cuda_dev_download(int gpu_slot, void* h_dst, const void* d_src, size_t bytes) {
+    int dev;
+    VIT_TRY(slot_device(gpu_slot, &dev));
+    CU_TRY(cudaSetDevice(dev));
+    CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int vit_cuda_host_alloc_pinned(size_t bytes, void** h_ptr) {
+    VIT_TRY(check_device(0, nullptr));
+    CU_TRY(cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable));
+    return 0;
+}
+int vit_cuda_host_free_pinned(void* h_ptr) {
+    CU_TRY(cudaFreeHost(h_ptr));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ single-op entry points
+namespace {
+struct Scratch {  // RAII device buffers for the op tests
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    int alloc(void** p, size_t bytes, bool zero = false) {
+        CU_TRY(cudaMalloc(p, bytes));
+        ptrs.push_back(*p);
+        if (zero) CU_TRY(cudaMemset(*p, 0, bytes));
+        return 0;
+    }
+    int upload_f32(float** p, const float* h, size_t n) {
+        VIT_TRY(alloc(reinterpret_cast<void**>(p), n * 4));
+        CU_TRY(cudaMemcpy(*p, h, n * 4, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    // fp32 host -> operand precision device (rows padded with zeros up to pad_elems)
+    int upload_operand(void** p, const float* h, size_t n, int prec, size_t pad_elems = 0) {
+        float* tmp = nullptr;
+        VIT_TRY(upload_f32(&tmp, h, n));
+        VIT_TRY(alloc(p, std::max(n, pad_elems) * 2, true));
+        VIT_TRY(launch_convert_from_f32(prec, tmp, *p, n, nullptr));
+        CU_TRY(cudaDeviceSynchronize());
+        return 0;
+    }
+    int download_operand(float* h, const void* d, size_t n, int prec) {
+        float* tmp = nullptr;
+        VIT_TRY(alloc(reinterpret_cast<void**>(&tmp), n * 4));
+        VIT_TRY(launch_convert_to_f32(prec, d, tmp, n, nullptr));
+        CU_TRY(cudaMemcpy(h, tmp, n * 4, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+};
+int op_begin(int* sm_count) {
+    VIT_TRY(check_device(0, sm_count));
+    CU_TRY(cudaSetDevice(0));
+    return 0;
+}
+int op_end(const char* what) {
+    const cudaError_t se = cudaDeviceSynchronize();
+    if (se != cudaSuccess) return watchdog_or_cuda_error(se, what);
+    return 0;
+}
+}  // namespace
+
+int vit_cuda_op_linear(const float* x, const float* W, const float* b, const float* residual, float* y, int m, int n,
+                       int k, int epilogue, int precision) {
+    int sms = 0;
+    VIT_TRY(op_begin(&sms));
+    if (!x || !W || !b || !y || m <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (epilogue == VIT_EPI_BIAS_RESIDUAL && !residual) return set_err(VIT_E_ARG, "residual epilogue needs a residual");
+    Scratch s;
+    void *dx, *dw;
+    float* db;
+    VIT_TRY(s.upload_operand(&dx, x, (size_t)m * k, precision));
+    VIT_TRY(s.upload_operand(&dw, W, (size_t)n * k, precision));
+    VIT_TRY(s.upload_f32(&db, b, n));
+    CUtensorMap ta, tb;
+    VIT_TRY(make_tmap(&ta, precision, dx, k, m, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&tb, precision, dw, k, n, GEMM_BK, kGemmBN));
+    if (epilogue == VIT_EPI_BIAS_RESIDUAL) {
+        float* dy;
+        VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * n));
+        GemmParams p{m, n, k, db, dy, dy, 0, 0};
+        VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(precision, ta, tb, p, sms, nullptr));
+        VIT_TRY(op_end("op_linear"));
+        CU_TRY(cudaMemcpy(y, dy, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
+    } else {
+        void* dy;
+        VIT_TRY(s.alloc(&dy, (size_t)m * n * 2, true));
+        GemmParams p{m, n, k, db, dy, nullptr, 0, 0};
+        if (epilogue == VIT_EPI_BIAS_GELU) VIT_TRY(launch_gemm<EPI_BIAS_GELU>(precision, ta, tb, p, sms, nullptr));
+        else if (epilogue == VIT_EPI_BIAS) VIT_TRY(launch_gemm<EPI_BIAS>(precision, ta, tb, p, sms, nullptr));
+        else return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
+        VIT_TRY(op_end("op_linear"));
+        VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
+    }
+    return op_end("op_linear");
+}
+
+int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int precision) {
+    VIT_TRY(op_begin(nullptr));
+    if (!x || !w || !b || !y || rows <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    Scratch s;
+    float *dx, *dw, *db;
+    void* dy;
+    VIT_TRY(s.upload_f32(&dx, x, (size_t)rows * kDim));
+    VIT_TRY(s.upload_f32(&dw, w, kDim));
+    VIT_TRY(s.upload_f32(&db, b, kDim));
+    VIT_TRY(s.alloc(&dy, (size_t)rows * kDim * 2));
+    VIT_TRY(launch_layernorm(precision, dx, dw, db, dy, rows, nullptr));
+    VIT_TRY(op_end("op_layernorm"));
+    VIT_TRY(s.download_operand(y, dy, (size_t)rows * kDim, precision));
+    return op_end("op_layernorm");
+}
+
+int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision) {
+    VIT_TRY(op_begin(nullptr));
+    if (!qkv || !out || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", tokens);
+    Scratch s;
+    const size_t rows = (size_t)batch * tokens;
+    const int kpad = (tokens + 15) / 16 * 16;
+    void *dqkv, *dout;
+    VIT_TRY(s.upload_operand(&dqkv, qkv, rows * 3 * kDim, precision));
+    VIT_TRY(s.alloc(&dout, rows * kDim * 2, true));
+    CUtensorMap tq, tkv;
+    VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, 256));
+    VIT_TRY(make_tmap(&tkv, precision, dqkv, 3 * kDim, rows, ATTN_DH, kpad));
+    AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f};
+    VIT_TRY(launch_attention(precision, tq, tkv, p, nullptr));
+    VIT_TRY(op_end("op_attention"));
+    VIT_TRY(s.download_operand(out, dout, rows * kDim, precision));
+    return op_end("op_attention");
+}
+
+int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w, const float* conv_b, const float* pos,
+                      float* out, int batch, int img_size, int precision) {
+    int sms = 0;
+    VIT_TRY(op_begin(&sms));
+    if (!images || !cls || !conv_w || !conv_b || !pos || !out || batch <= 0 || img_size % kPatch) return set_err(VIT_E_ARG, "bad arguments");
+    Scratch s;
+    const int g = img_size / kPatch, patches = g * g, tokens = patches + 1;
+    const size_t img_elems = (size_t)3 * img_size * img_size;
+    float *dimg, *dcls, *dcb, *dpos, *dx;
+    void *dw, *dpatch;
+    VIT_TRY(s.upload_f32(&dimg, images, batch * img_elems));
+    VIT_TRY(s.upload_f32(&dcls, cls, kDim));
+    VIT_TRY(s.upload_f32(&dcb, conv_b, kDim));
+    VIT_TRY(s.upload_f32(&dpos, pos, (size_t)tokens * kDim));
+    VIT_TRY(s.upload_operand(&dw, conv_w, (size_t)kDim * kDim, precision));
+    VIT_TRY(s.alloc(&dpatch, (size_t)batch * patches * kDim * 2, true));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dx), (size_t)batch * tokens * kDim * 4, true));
+    CUtensorMap ta, tb;
+    VIT_TRY(make_tmap(&ta, precision, dpatch, kDim, (uint64_t)batch * patches, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&tb, precision, dw, kDim, kDim, GEMM_BK, kGemmBN));
+    VIT_TRY(launch_patchify(precision, dimg, dpatch, batch, img_size, sms, nullptr));
+    cls_rows_kernel<<<(batch * kDim + 255) / 256, 256>>>(dx, dcls, dpos, batch, tokens);
+    VIT_TRY(check_launch("cls_rows"));
+    GemmParams p{batch * patches, kDim, kDim, dcb, dx, dpos, patches, tokens};
+    VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(precision, ta, tb, p, sms, nullptr));
+    VIT_TRY(op_end("op_embed"));
+    CU_TRY(cudaMemcpy(out, dx, (size_t)batch * tokens * kDim * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int vit_cuda_op_head(const float* x, const float* ln_w, const float* ln_b, const float* head_w, const float* head_b,
+                     float* logits, int batch, int tokens) {
+    VIT_TRY(op_begin(nullptr));
+    if (!x || !ln_w || !ln_b || !head_w || !head_b || !logits || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    Scratch s;
+    float *dx, *dlw, *dlb, *dhw, *dhb, *dcls, *dlog;
+    VIT_TRY(s.upload_f32(&dx, x, (size_t)batch * tokens * kDim));
+    VIT_TRY(s.upload_f32(&dlw, ln_w, kDim));
+    VIT_TRY(s.upload_f32(&dlb, ln_b, kDim));
+    VIT_TRY(s.upload_f32(&dhw, head_w, (size_t)kClasses * kDim));
+    VIT_TRY(s.upload_f32(&dhb, head_b, kClasses));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dcls), (size_t)batch * kDim * 4));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dlog), (size_t)batch * kClasses * 4));
+    head_ln_kernel<<<(batch + 7) / 8, 256>>>(dx, dlw, dlb, dcls, batch, tokens);
+    VIT_TRY(check_launch("head_ln"));
+    head_gemm_kernel<<<dim3((kClasses + 63) / 64, (batch + 63) / 64), 256>>>(dcls, dhw, dhb, dlog, batch, kClasses);
+    VIT_TRY(check_launch("head_gemm"));
+    VIT_TRY(op_end("op_head"));
+    CU_TRY(cudaMemcpy(logits, dlog, (size_t)batch * kClasses * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// kernels_misc.cuh -- the HBM-bound kernels around the GEMMs: LayerNorm, patch extraction,
+// class-token rows, the fp32 classifier head and operand conversion.
+#pragma once
+
+#include "ptx.cuh"
+
+namespace vit {
+
+constexpr int kDim = 768;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over 768 features, one warp per token row (layer_norm, ViT_seq.c:103-121; replaces
+// layer_norm_kernel, kernel.cl:6-80).  fp32 in, eps = 1e-6 as in the CPU reference (the OpenCL
+// kernel drops it), statistics in fp32 with a centred second pass over the registers, output
+// in the GEMM operand precision.  Each lane owns 6 float4 (128-bit loads, fully coalesced).
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, T* __restrict__ y, int rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * kDim);
+    float4 v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = __ldcs(xr + lane + 32 * i);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / kDim);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float inv_std = rsqrtf(warp_sum(q) * (1.0f / kDim) + 1e-6f);
+    const float4* wr = reinterpret_cast<const float4*>(w);
+    const float4* br = reinterpret_cast<const float4*>(b);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * kDim);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float4 g = __ldg(wr + lane + 32 * i), be = __ldg(br + lane + 32 * i);
+        uint2 o;
+        o.x = pack2<T>(fmaf(v[i].x * inv_std, g.x, be.x), fmaf(v[i].y * inv_std, g.y, be.y));
+        o.y = pack2<T>(fmaf(v[i].z * inv_std, g.z, be.z), fmaf(v[i].w * inv_std, g.w, be.w));
+        yr[lane + 32 * i] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch extraction + cast: images [B][3][S][S] fp32 -> patches [B*G*G][768] in operand precision,
+// K order (ic, kh, kw) = the flattened conv_proj.weight row order (Conv2d, ViT_seq.c:33-41), patch
+// index oh*G+ow (flatten_transpose, ViT_seq.c:57-65).  One thread per float4 of the image, reads
+// fully coalesced, writes 8-byte pieces.
+template <typename T>
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, T* __restrict__ patches,
+                                                       int batch, int S) {
+    const int G = S / 16;
+    const size_t per_img4 = static_cast<size_t>(3) * S * S / 4;
+    const size_t total = per_img4 * batch;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t bimg = i / per_img4;
+        size_t rem = i - bimg * per_img4;           // float4 index inside the image
+        const int x4 = static_cast<int>(rem % (S / 4));
+        rem /= (S / 4);
+        const int yy = static_cast<int>(rem % S);
+        const int c = static_cast<int>(rem / S);
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(img) + i);
+        const int x = x4 * 4;
+        const int ph = yy >> 4, kh = yy & 15, pw = x >> 4, kw = x & 15;
+        const size_t prow = bimg * (G * G) + ph * G + pw;
+        uint2 o;
+        o.x = pack2<T>(v.x, v.y);
+        o.y = pack2<T>(v.z, v.w);
+        *reinterpret_cast<uint2*>(patches + prow * kDim + c * 256 + kh * 16 + kw) = o;
+    }
+}
+
+// Class-token rows: X[b*tokens][:] = class_token + pos_embedding[0]  (class_token + pos_emb,
+// ViT_seq.c:72-101).  The patch rows are written by the conv_proj GEMM epilogue.
+__global__ void cls_rows_kernel(float* __restrict__ X, const float* __restrict__ cls, const float* __restrict__ pos,
+                                int batch, int tokens) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch * kDim) return;
+    const int b = i / kDim, d = i - b * kDim;
+    X[static_cast<size_t>(b) * tokens * kDim + d] = cls[d] + pos[d];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final LayerNorm on the class rows only (the reference normalises all rows and keeps row 0,
+// ViT_seq.c:429-433), fp32 out.  One warp per image.
+__global__ void __launch_bounds__(256) head_ln_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float* __restrict__ out,
+                                                      int batch, int tokens) {
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (img >= batch) return;
+    const int lane = threadIdx.x & 31;
+    const float4* xr = reinterpret_cast<const float4*>(X + static_cast<size_t>(img) * tokens * kDim);
+    float4 v[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / kDim);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float inv_std = rsqrtf(warp_sum(q) * (1.0f / kDim) + 1e-6f);
+    float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(img) * kDim);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float4 g = reinterpret_cast<const float4*>(w)[lane + 32 * i];
+        const float4 be = reinterpret_cast<const float4*>(b)[lane + 32 * i];
+        o[lane + 32 * i] = make_float4(fmaf(v[i].x * inv_std, g.x, be.x), fmaf(v[i].y * inv_std, g.y, be.y),
+                                       fmaf(v[i].z * inv_std, g.z, be.z), fmaf(v[i].w * inv_std, g.w, be.w));
+    }
+}
+
+// Classifier head in fp32 on the CUDA cores: logits[b][c] = bias[c] + sum_k xn[b][k] * W[c][k]
+// (linear_layer with tokens = 1, ViT_seq.c:435).  0.002 % of the model's FLOPs; fp32 keeps the
+// logits free of operand rounding.  64x64 output tile, 4x4 per thread, K chunks of 16.
+__global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ xn, const float* __restrict__ W,
+                                                        const float* __restrict__ bias, float* __restrict__ logits,
+                                                        int batch, int classes) {
+    __shared__ float sA[16][64 + 4];
+    __shared__ float sW[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int b0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < kDim; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, k = i & 15;
+            sA[k][r] = (b0 + r < batch) ? xn[static_cast<size_t>(b0 + r) * kDim + k0 + k] : 0.f;
+            sW[k][r] = (c0 + r < classes) ? W[static_cast<size_t>(c0 + r) * kDim + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; w[i] = sW[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = b0 + ty * 4 + i, c = c0 + tx * 4 + j;
+            if (b < batch && c < classes) logits[static_cast<size_t>(b) * classes + c] = acc[i][j] + bias[c];
+        }
+}
+
+// fp32 -> operand precision (weights at init, test inputs), and back (test outputs).
+template <typename T>
+__global__ void convert_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = from_float<T>(src[i]);
+}
+template <typename T>
+__global__ void convert_to_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = to_float<T>(src[i]);
+}
+
+}  // namespace vit

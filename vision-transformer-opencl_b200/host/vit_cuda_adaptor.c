@@ -1,0 +1,96 @@
+/*
+ * vit_cuda_adaptor.c -- the reference's three-call GPU backend surface re-expressed over the
+ * CUDA engine:  initialize_opencl / ViT_opencl / Release_opencl  (ViT_opencl.h:18-22, called
+ * from Main.c:19,57,86)  ->  initialize_cuda / ViT_cuda / Release_cuda.  Plain C.
+ */
+#include "vit_host.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static vit_host_config g_cfg = {1, 256, VIT_PREC_BF16};
+static int g_cfg_from_env_done = 0;
+static int g_engine_up = 0;
+static int g_engine_img = 0;
+static const Network* g_engine_weights = NULL;
+static int g_status = 0;
+
+void vit_host_set_config(const vit_host_config* cfg) {
+    if (!cfg) return;
+    g_cfg = *cfg;
+    if (g_cfg.n_gpus < 1) g_cfg.n_gpus = 1;
+    if (g_cfg.max_batch_per_gpu < 1) g_cfg.max_batch_per_gpu = 256;
+    g_cfg_from_env_done = 1;
+}
+
+static void config_from_env(void) {
+    if (g_cfg_from_env_done) return;
+    g_cfg_from_env_done = 1;
+    const char* s;
+    if ((s = getenv("VIT_GPUS")) && atoi(s) > 0) g_cfg.n_gpus = atoi(s);
+    if ((s = getenv("VIT_MAX_BATCH")) && atoi(s) > 0) g_cfg.max_batch_per_gpu = atoi(s);
+    if ((s = getenv("VIT_PRECISION")) && strcmp(s, "fp16") == 0) g_cfg.precision = VIT_PREC_FP16;
+}
+
+int initialize_cuda(void) {
+    config_from_env();
+    g_status = 0;
+    return 0;
+}
+
+int ViT_cuda_status(void) { return g_status; }
+
+void Release_cuda(void) {
+    vit_cuda_free();
+    g_engine_up = 0;
+    g_engine_weights = NULL;
+}
+
+static void fail(float** prb, int n, const char* what) {
+    fprintf(stderr, "ViT_cuda: %s: %s\n", what, vit_cuda_last_error());
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < VIT_NUM_CLASSES; ++j) prb[i][j] = NAN;
+}
+
+void ViT_cuda(ImageData* image, Network* networks, float** prb) {
+    config_from_env();
+    const int n = image[0].n;
+    const int img = image[0].h;
+    const size_t per = (size_t)image[0].c * image[0].h * image[0].w;
+    g_status = VIT_E_ARG;
+    if (n <= 0 || image[0].c != 3 || image[0].h != image[0].w) {
+        fprintf(stderr, "ViT_cuda: unsupported image batch %d x %d x %d x %d\n", n, image[0].c, image[0].h, image[0].w);
+        return;
+    }
+    /* the reference hands the weights over on every call; upload them once per weight set */
+    if (!g_engine_up || g_engine_img != img || g_engine_weights != networks) {
+        if (g_engine_up) vit_cuda_free();
+        g_engine_up = 0;
+        g_status = vit_cuda_init_ex(networks, VIT_NUM_TENSORS, img, g_cfg.max_batch_per_gpu, g_cfg.n_gpus, NULL, g_cfg.precision);
+        if (g_status != 0) {
+            fail(prb, n, "init");
+            return;
+        }
+        g_engine_up = 1;
+        g_engine_img = img;
+        g_engine_weights = networks;
+    }
+    /* image[i].data are separate allocations (Network.c:80): gather into pinned staging */
+    float* staging = NULL;
+    float* logits = NULL;
+    int pinned = vit_cuda_host_alloc_pinned(((size_t)n * per + (size_t)n * VIT_NUM_CLASSES) * sizeof(float), (void**)&staging) == 0;
+    if (!pinned) staging = (float*)malloc(((size_t)n * per + (size_t)n * VIT_NUM_CLASSES) * sizeof(float));
+    if (!staging) {
+        g_status = VIT_E_NOMEM;
+        return;
+    }
+    logits = staging + (size_t)n * per;
+    for (int i = 0; i < n; ++i) memcpy(staging + (size_t)i * per, image[i].data, per * sizeof(float));
+    g_status = vit_cuda_forward(staging, n, logits, NULL);
+    if (g_status != 0) fail(prb, n, "forward");
+    else
+        for (int i = 0; i < n; ++i) vit_softmax(logits + (size_t)i * VIT_NUM_CLASSES, prb[i], VIT_NUM_CLASSES);
+    if (pinned) vit_cuda_host_free_pinned(staging); else free(staging);
+}
