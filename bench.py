@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- ViT-B/16 224x224 images/sec on B200 (BASELINE.json metric), device-resident and
+end-to-end through the C ABI, with the dominant kernel's roofline and the CPU reference beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16|fp16]
+    python bench.py --impl reference ...      # the reference's own ViT_seq on the host cores
+
+A "step" is one forward pass of the hot path over one batch of B synthetic images per GPU
+(default 1024 = BASELINE.json configs[2]; for N > 1 this is configs[3], 8192 images over 8 GPUs,
+weights replicated, no collective on the data path).  Under torchrun (N > 1) every rank owns one
+GPU; torch.distributed is used only for the barrier and the max-over-ranks reduction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "vision-transformer-opencl_b200"))
+
+import numpy as np
+
+FLOP_PER_IMAGE_224 = 35_127_656_448  # matmul-only, 2 FLOP/MAC, un-padded 197 tokens
+# per-launch algorithmic FLOPs of one GEMM over `rows` token rows
+GEMM_FLOP_PER_ROW = {"qkv_gemm": 2 * 768 * 2304, "out_gemm": 2 * 768 * 768, "fc1_gemm": 2 * 768 * 3072, "fc2_gemm": 2 * 3072 * 768}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref = its ViT_seq.c compiled unmodified) on
+    the host cores: one image per thread, all threads busy, each step a bounded sample."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py as O
+    import vit_b200 as V
+    cores = os.cpu_count() or 1
+    if args.cpu_threads:
+        cores = args.cpu_threads
+    w = V.synth_weights(224, 42)
+    kind = "reference" if O.ref_available() else "port"
+    n = cores  # images per step, one per thread
+    imgs = V.synth_images(n, 224, 7)
+
+    def step():
+        if kind == "reference":
+            ths = [threading.Thread(target=O.ref_vit_seq, args=(w, imgs[i:i + 1])) for i in range(n)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        else:
+            O.forward(w, imgs, 224, n_threads=cores)
+
+    devnull = os.open(os.devnull, os.O_WRONLY)  # ViT_seq prints a timing line per image
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 1)
+    value = n * args.steps / dt
+    sample = f"{n} images per step ({'reference ViT_seq(), one image per thread' if kind == 'reference' else 'oracle port, OpenMP'}), same synthetic batch (seed 7) truncated"
+    print(json.dumps({
+        "impl": "reference", "metric": "ViT-B/16 224x224 inference throughput", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 224x224 synthetic batch, CPU ViT_seq", "images_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def cpu_baseline(seconds_hint=20):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py as O
+    import vit_b200 as V
+    cores = os.cpu_count() or 1
+    w = V.synth_weights(224, 42)
+    imgs = V.synth_images(cores, 224, 7)
+    kind = "reference" if O.ref_available() else "port"
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    t0 = time.perf_counter()
+    try:
+        if kind == "reference":
+            ths = [threading.Thread(target=O.ref_vit_seq, args=(w, imgs[i:i + 1])) for i in range(cores)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        else:
+            O.forward(w, imgs, 224, n_threads=cores)
+    finally:
+        os.dup2(saved, 1)
+    dt = time.perf_counter() - t0
+    return {"value": cores / dt, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{cores} images of the same synthetic batch (seed 7), one image per host thread through "
+                      f"{'the reference ViT_seq() compiled from its own source (oracle/_ref)' if kind == 'reference' else 'the oracle port'}, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import vit_b200 as V
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    prec = V.PREC_FP16 if args.precision == "fp16" else V.PREC_BF16
+    B = args.batch
+    peaks = load_peaks()
+    weights = V.synth_weights(224, 42)
+    eng = V.Engine(weights, 224, max_batch=B, n_gpus=1, device_ids=[local_rank], precision=prec)
+    info = eng.info()
+
+    # synthetic batch (seed 7), distinct images per rank; pinned host copy for the end-to-end leg
+    h_imgs, h_imgs_ptr = V.pinned_empty((B, 3, 224, 224))
+    V.synth_images(B, 224, 7, first_index=rank * B, out=h_imgs)
+    h_logits, h_logits_ptr = V.pinned_empty((B, 1000))
+    d_imgs = V.dev_alloc(0, h_imgs.nbytes)
+    d_logits = V.dev_alloc(0, h_logits.nbytes)
+    V.dev_upload(0, d_imgs, h_imgs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (inputs in HBM, 617 MB per batch >> 126 MB L2)
+    for _ in range(max(args.warmup, 3)):
+        eng.enqueue_device(d_imgs, B, d_logits)
+    eng.sync()
+    eng.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = V.launch_count()
+    if rank == 0:
+        sampler.start()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.enqueue_device(d_imgs, B, d_logits)
+    ms_total = eng.timer_stop()
+    eng.sync()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = V.launch_count() - launches0
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = n_gpus * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through vit_cuda_forward: pinned host images in, host logits out, every step
+    for _ in range(2):
+        eng.forward_raw(h_imgs_ptr, B, h_logits_ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.forward_raw(h_imgs_ptr, B, h_logits_ptr)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_gpus * B * args.steps / e2e_s
+    top1 = h_logits.argmax(1)
+
+    # ---- batch-1 latency (BASELINE.json configs[1]), device resident and host-to-host
+    lat = None
+    if rank == 0 and not args.no_latency:
+        dev_ms, host_ms = [], []
+        for i in range(20 + 200):
+            eng.timer_start()
+            eng.enqueue_device(d_imgs, 1, d_logits)
+            ms = eng.timer_stop()
+            if i >= 20:
+                dev_ms.append(ms)
+        for i in range(20 + 200):
+            t1 = time.perf_counter()
+            eng.forward_raw(h_imgs_ptr, 1, h_logits_ptr)
+            if i >= 20:
+                host_ms.append((time.perf_counter() - t1) * 1e3)
+        lat = {"device_ms_median": float(np.median(dev_ms)), "device_ms_p99": float(np.percentile(dev_ms, 99)),
+               "host_to_host_ms_median": float(np.median(host_ms)), "host_to_host_ms_p99": float(np.percentile(host_ms, 99)), "runs": 200}
+
+    if rank == 0:
+        rows = B * 197
+        step_ms_by_cat = {k: v["ms"] / args.steps for k, v in prof.items()}
+        dom = max(GEMM_FLOP_PER_ROW, key=lambda k: step_ms_by_cat[k])  # dominant kernel of the step
+        dom_ms = prof[dom]["ms"] / max(prof[dom]["launches"], 1)
+        dom_tflops = GEMM_FLOP_PER_ROW[dom] * rows / (dom_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]  # kernel timed inside a long step
+        out = {
+            "metric": "ViT-B/16 224x224 inference throughput", "value": value, "unit": "images/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"ViT-B/16 224x224 synthetic batch {B} per GPU ({n_gpus * B} total), 197 tokens, 12 layers, random-init weights (seed 42), fp32 residual stream",
+                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "l2": "inputs (617 MB/batch) and activations larger than the 126 MB L2"},
+            "model_tflops": FLOP_PER_IMAGE_224 * value / 1e12,
+            "model_frac_of_peak": {"burst": FLOP_PER_IMAGE_224 * value / n_gpus / 1e12 / peaks["bf16_tflops"],
+                                   "sustained": FLOP_PER_IMAGE_224 * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
+            "roofline": {"kernel": f"gemm_sm100_kernel ({dom})", "bound": "tensor", "achieved": dom_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": dom_tflops / peak, "traffic": None, "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
+                         "ms_per_launch": dom_ms, "launches": prof[dom]["launches"]},
+            "step_breakdown_ms": step_ms_by_cat,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h_imgs.nbytes), "d2h_bytes_per_step": int(h_logits.nbytes),
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks, "engine": info, "top1_checksum": int(top1.sum()),
+        }
+        if lat:
+            out["batch1_latency"] = lat
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+
+    V.dev_free(0, d_imgs)
+    V.dev_free(0, d_logits)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    _, _, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29531", __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,29 @@ long long vit_cuda_launch_count(void);
  * {sm_count, cc_major, cc_minor, max_batch, tokens, precision, n_gpus, ws_bytes>>20}. */
 int vit_cuda_info(long long* out, int n);
 
+/* CUDA-event stopwatch on a slot's stream: start records an event, stop records a second one,
+ * waits for it and returns the elapsed device time in milliseconds. */
+int vit_cuda_timer_start(int gpu_slot);
+int vit_cuda_timer_stop(int gpu_slot, float* ms);
+
+/* Per-kernel-category device timing.  While enabled, every launch of the forward is bracketed
+ * by an event pair on the slot's stream; vit_cuda_profile_read synchronises, returns the summed
+ * milliseconds and launch count per category (VIT_PROF_*) since the last read, and resets. */
+enum {
+    VIT_PROF_PATCHIFY = 0,   /* patch extraction + class rows */
+    VIT_PROF_EMBED_GEMM,     /* conv_proj GEMM */
+    VIT_PROF_LAYERNORM,      /* ln_1 + ln_2 */
+    VIT_PROF_QKV_GEMM,       /* in_proj */
+    VIT_PROF_ATTENTION,      /* fused softmax(QK^T)V */
+    VIT_PROF_OUT_GEMM,       /* out_proj + residual */
+    VIT_PROF_FC1_GEMM,       /* mlp_0 + GELU */
+    VIT_PROF_FC2_GEMM,       /* mlp_3 + residual */
+    VIT_PROF_HEAD,           /* final LN + classifier */
+    VIT_PROF_NCAT
+};
+int vit_cuda_profile_enable(int on);
+int vit_cuda_profile_read(int gpu_slot, double* total_ms, long long* launches, int ncat);
+
 /* Device memory helpers so that a host program without a CUDA toolchain (plain C driver,
  * ctypes) can stage device-resident inputs for vit_cuda_forward_device. */
 int vit_cuda_dev_alloc(int gpu_slot, size_t bytes, void** d_ptr);

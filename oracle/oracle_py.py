@@ -73,6 +73,7 @@ def forward(weights, images: np.ndarray, img_size: int = 224, n_threads: int = 0
 
 
 def linear(x, W, b):
+    assert x.ndim == 2 and W.ndim == 2 and W.shape[1] == x.shape[1] and b.size == W.shape[0]
     y = np.empty((x.shape[0], W.shape[0]), dtype=np.float32)
     lib.oracle_linear(_p(x), _p(y), x.shape[0], x.shape[1], W.shape[0], _p(W), _p(b))
     return y

@@ -47,25 +47,29 @@ int oracle_max_threads(void) {
 
 ORACLE_CLONES
 static void linear_block(const float* x, float* y, int t0, int tn, int in_f, int out_f,
-                         const float* Wt /* [in_f][out_pad] */, int out_pad, const float* b) {
-    for (int o0 = 0; o0 < out_f; o0 += LIN_OB) {
+                         const float* Wt /* [in_f][out_pad] */, int out_pad,
+                         const float* bp /* [out_pad], zero padded */) {
+    /* rows past the end of a ragged last block alias the last valid row; their results
+     * are computed and dropped, so no load is ever conditional */
+    const float* xr[LIN_TB];
+    for (int tt = 0; tt < LIN_TB; ++tt) xr[tt] = x + (size_t)(t0 + (tt < tn ? tt : tn - 1)) * in_f;
+    for (int o0 = 0; o0 < out_pad; o0 += LIN_OB) {
         float acc[LIN_TB][LIN_OB];
         for (int tt = 0; tt < LIN_TB; ++tt)
-            for (int j = 0; j < LIN_OB; ++j)
-                acc[tt][j] = (o0 + j < out_f) ? b[o0 + j] : 0.0f;
+            for (int j = 0; j < LIN_OB; ++j) acc[tt][j] = bp[o0 + j];
         for (int i = 0; i < in_f; ++i) {
             const float* wrow = Wt + (size_t)i * out_pad + o0;
             for (int tt = 0; tt < LIN_TB; ++tt) {
-                const float xv = (tt < tn) ? x[(size_t)(t0 + tt) * in_f + i] : 0.0f;
+                const float xv = xr[tt][i];
                 for (int j = 0; j < LIN_OB; ++j) {
                     float p = xv * wrow[j];
                     acc[tt][j] = acc[tt][j] + p;
                 }
             }
         }
+        const int jn = out_f - o0 < LIN_OB ? out_f - o0 : LIN_OB;
         for (int tt = 0; tt < tn; ++tt)
-            for (int j = 0; j < LIN_OB && o0 + j < out_f; ++j)
-                y[(size_t)(t0 + tt) * out_f + o0 + j] = acc[tt][j];
+            for (int j = 0; j < jn; ++j) y[(size_t)(t0 + tt) * out_f + o0 + j] = acc[tt][j];
     }
 }
 
@@ -86,7 +90,9 @@ void oracle_linear(const float* x, float* y, int tokens, int in_f, int out_f,
         return;
     }
     const int out_pad = (out_f + LIN_OB - 1) / LIN_OB * LIN_OB;
-    float* Wt = (float*)calloc((size_t)in_f * out_pad, sizeof(float));
+    float* Wt = (float*)calloc((size_t)in_f * out_pad + out_pad, sizeof(float));
+    float* bp = Wt + (size_t)in_f * out_pad;
+    memcpy(bp, b, sizeof(float) * out_f);
     for (int o = 0; o < out_f; ++o)
         for (int i = 0; i < in_f; ++i) Wt[(size_t)i * out_pad + o] = W[(size_t)o * in_f + i];
     const int nblk = (tokens + LIN_TB - 1) / LIN_TB;
@@ -94,7 +100,7 @@ void oracle_linear(const float* x, float* y, int tokens, int in_f, int out_f,
     for (int blk = 0; blk < nblk; ++blk) {
         int t0 = blk * LIN_TB;
         int tn = tokens - t0 < LIN_TB ? tokens - t0 : LIN_TB;
-        linear_block(x, y, t0, tn, in_f, out_f, Wt, out_pad, b);
+        linear_block(x, y, t0, tn, in_f, out_f, Wt, out_pad, bp);
     }
     free(Wt);
 }

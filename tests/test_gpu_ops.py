@@ -101,5 +101,5 @@ def test_head(vit, oracle, weights224):
     x = _rand((batch * tokens, 768), 31, 1.5)
     got = vit.op_head(x, w[148], w[149], w[150], w[151], batch, tokens)
     cls_rows = np.ascontiguousarray(x[::tokens])
-    ref = oracle.linear(oracle.layer_norm(cls_rows, w[148], w[149]), w[150], w[151])
+    ref = oracle.linear(oracle.layer_norm(cls_rows, w[148], w[149]), w[150].reshape(1000, 768), w[151])
     _close(got, ref, 1e-5, 2e-5, "final LN + head")

@@ -107,7 +107,7 @@ def case_head():
     w = V.synth_weights(224, 42)
     x = rand((5 * 197, 768), 31, 1.5)
     got = V.op_head(x, w[148], w[149], w[150], w[151], 5, 197)
-    ref = O.linear(O.layer_norm(np.ascontiguousarray(x[::197]), w[148], w[149]), w[150], w[151])
+    ref = O.linear(O.layer_norm(np.ascontiguousarray(x[::197]), w[148], w[149]), w[150].reshape(1000, 768), w[151])
     stats("head", got, ref)
 
 

@@ -190,6 +190,10 @@ int watchdog_or_cuda_error(cudaError_t e, const char* what) {
 }
 
 // ------------------------------------------------------------------------------------ engine state
+struct timerEvents_t {
+    cudaEvent_t start = nullptr, stop = nullptr;
+};
+
 struct LayerW {
     float *ln1_w, *ln1_b, *qkv_b, *out_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;  // fp32
     void *qkv_w, *out_w, *fc1_w, *fc2_w;                                    // operand precision
@@ -214,10 +218,15 @@ struct DeviceCtx {
     float *x = nullptr, *cls_ln = nullptr, *logits = nullptr;
     CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_q, tm_kv;
     size_t ws_bytes = 0;
+    // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
+    size_t prof_used[VIT_PROF_NCAT] = {};
+    timerEvents_t timer;
 };
 
 struct Engine {
     bool up = false;
+    bool profiling = false;
     int img = 0, grid = 0, patches = 0, tokens = 0, max_batch = 0, prec = 0;
     std::vector<DeviceCtx> ctx;
 };
@@ -253,6 +262,13 @@ void destroy_ctx(DeviceCtx& c) {
         if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
         if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
     }
+    for (auto& v : c.prof_events)
+        for (auto& pr : v) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+    if (c.timer.start) cudaEventDestroy(c.timer.start);
+    if (c.timer.stop) cudaEventDestroy(c.timer.stop);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     c = DeviceCtx();
@@ -336,42 +352,84 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
     return 0;
 }
 
+// RAII marker: when profiling is on, brackets one launch with an event pair of its category.
+struct ProfScope {
+    DeviceCtx& c;
+    int cat;
+    bool on;
+    ProfScope(DeviceCtx& c_, bool on_, int cat_) : c(c_), cat(cat_), on(on_) {
+        if (!on) return;
+        auto& v = c.prof_events[cat];
+        if (c.prof_used[cat] == v.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            v.emplace_back(a, b);
+        }
+        cudaEventRecord(v[c.prof_used[cat]].first, c.stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(c.prof_events[cat][c.prof_used[cat]].second, c.stream);
+        ++c.prof_used[cat];
+    }
+};
+
 // Enqueue the whole forward for nb images already resident in d_images (fp32 NCHW) on c.stream.
 int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
     cudaStream_t st = c.stream;
     const int prec = e.prec;
     const int rows = nb * e.tokens;
     // conv_proj: patch rows -> GEMM with (+bias, +pos_embedding, row remap) epilogue; class rows aside
-    VIT_TRY(launch_patchify(prec, d_images, c.patches, nb, e.img, c.sm_count, st));
-    cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(c.x, c.cls, c.pos, nb, e.tokens);
-    VIT_TRY(check_launch("cls_rows"));
+    const bool pf = e.profiling;
     {
+        ProfScope ps(c, pf, VIT_PROF_PATCHIFY);
+        VIT_TRY(launch_patchify(prec, d_images, c.patches, nb, e.img, c.sm_count, st));
+        cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(c.x, c.cls, c.pos, nb, e.tokens);
+        VIT_TRY(check_launch("cls_rows"));
+    }
+    {
+        ProfScope ps(c, pf, VIT_PROF_EMBED_GEMM);
         GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
         VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
     }
     AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f};
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
-        VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
         {
+            ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
+            VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
+        }
+        {
+            ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
             GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0};
             VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
         }
-        VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, st));
         {
+            ProfScope ps(c, pf, VIT_PROF_ATTENTION);
+            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, st));
+        }
+        {
+            ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
             GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x, 0, 0};
             VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
         }
-        VIT_TRY(launch_layernorm(prec, c.x, L.ln2_w, L.ln2_b, c.xn, rows, st));
         {
+            ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
+            VIT_TRY(launch_layernorm(prec, c.x, L.ln2_w, L.ln2_b, c.xn, rows, st));
+        }
+        {
+            ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
             GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr, 0, 0};
             VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
         }
         {
+            ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
             GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x, 0, 0};
             VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
         }
     }
+    ProfScope ps(c, pf, VIT_PROF_HEAD);
     head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
     VIT_TRY(check_launch("head_ln"));
     head_gemm_kernel<<<dim3((kClasses + 63) / 64, (nb + 63) / 64), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
@@ -488,19 +546,18 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
     const int G = static_cast<int>(e.ctx.size());
     const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
     const int per_gpu = (n + G - 1) / G;  // contiguous shards
-    int max_passes = 0;
-    for (int g = 0; g < G; ++g) {
-        const int lo = std::min(n, g * per_gpu), hi = std::min(n, lo + per_gpu);
-        max_passes = std::max(max_passes, (hi - lo + e.max_batch - 1) / e.max_batch);
-    }
+    // Pass size: a shard is cut into >= 4 passes when it is large enough, so that the H2D copy of
+    // pass i+1 (copy stream, second image buffer) hides under the compute of pass i.
+    const int pass_size = std::min(e.max_batch, std::max(32, (per_gpu + 3) / 4));
+    const int max_passes = (per_gpu + pass_size - 1) / pass_size;
     // pass-major issue order so that all GPUs are fed before any host-side wait
     for (int pass = 0; pass < max_passes; ++pass) {
         for (int g = 0; g < G; ++g) {
             DeviceCtx& c = e.ctx[g];
             const int lo = std::min(n, g * per_gpu), hi = std::min(n, lo + per_gpu);
-            const int first = lo + pass * e.max_batch;
+            const int first = lo + pass * pass_size;
             if (first >= hi) continue;
-            const int nb = std::min(e.max_batch, hi - first);
+            const int nb = std::min(pass_size, hi - first);
             const int buf = pass & 1;
             CU_TRY(cudaSetDevice(c.device));
             // H2D of this pass overlaps the previous pass's compute (other image buffer)
@@ -540,6 +597,56 @@ int vit_cuda_info(long long* out, int n) {
     const long long v[8] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
                             (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20)};
     for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------ timing helpers
+int vit_cuda_timer_start(int gpu_slot) {
+    if (!g_eng.up || gpu_slot < 0 || gpu_slot >= (int)g_eng.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
+    DeviceCtx& c = g_eng.ctx[gpu_slot];
+    CU_TRY(cudaSetDevice(c.device));
+    if (!c.timer.start) {
+        CU_TRY(cudaEventCreate(&c.timer.start));
+        CU_TRY(cudaEventCreate(&c.timer.stop));
+    }
+    CU_TRY(cudaEventRecord(c.timer.start, c.stream));
+    return 0;
+}
+int vit_cuda_timer_stop(int gpu_slot, float* ms) {
+    if (!g_eng.up || gpu_slot < 0 || gpu_slot >= (int)g_eng.ctx.size() || !ms) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
+    DeviceCtx& c = g_eng.ctx[gpu_slot];
+    if (!c.timer.start) return set_err(VIT_E_ARG, "timer not started");
+    CU_TRY(cudaSetDevice(c.device));
+    CU_TRY(cudaEventRecord(c.timer.stop, c.stream));
+    const cudaError_t se = cudaEventSynchronize(c.timer.stop);
+    if (se != cudaSuccess) return watchdog_or_cuda_error(se, "timer_stop");
+    CU_TRY(cudaEventElapsedTime(ms, c.timer.start, c.timer.stop));
+    return 0;
+}
+int vit_cuda_profile_enable(int on) {
+    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
+    g_eng.profiling = on != 0;
+    for (auto& c : g_eng.ctx)
+        for (auto& u : c.prof_used) u = 0;
+    return 0;
+}
+int vit_cuda_profile_read(int gpu_slot, double* total_ms, long long* launches, int ncat) {
+    if (!g_eng.up || gpu_slot < 0 || gpu_slot >= (int)g_eng.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
+    DeviceCtx& c = g_eng.ctx[gpu_slot];
+    CU_TRY(cudaSetDevice(c.device));
+    const cudaError_t se = cudaStreamSynchronize(c.stream);
+    if (se != cudaSuccess) return watchdog_or_cuda_error(se, "profile_read");
+    for (int k = 0; k < ncat && k < VIT_PROF_NCAT; ++k) {
+        double acc = 0;
+        for (size_t i = 0; i < c.prof_used[k]; ++i) {
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, c.prof_events[k][i].first, c.prof_events[k][i].second));
+            acc += ms;
+        }
+        total_ms[k] = acc;
+        launches[k] = (long long)c.prof_used[k];
+        c.prof_used[k] = 0;
+    }
     return 0;
 }
 

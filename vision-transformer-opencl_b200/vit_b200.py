@@ -18,6 +18,7 @@ NUM_TENSORS = 152
 NUM_CLASSES = 1000
 PREC_BF16, PREC_FP16 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+PROF_CATEGORIES = ["patchify", "embed_gemm", "layernorm", "qkv_gemm", "attention", "out_gemm", "fc1_gemm", "fc2_gemm", "head"]
 
 
 class VitCudaError(RuntimeError):
@@ -62,6 +63,10 @@ _sig("vit_cuda_free", None)
 _sig("vit_cuda_last_error", C.c_char_p)
 _sig("vit_cuda_launch_count", C.c_longlong)
 _sig("vit_cuda_info", C.c_int, C.POINTER(C.c_longlong), C.c_int)
+_sig("vit_cuda_timer_start", C.c_int, C.c_int)
+_sig("vit_cuda_timer_stop", C.c_int, C.c_int, _f32p)
+_sig("vit_cuda_profile_enable", C.c_int, C.c_int)
+_sig("vit_cuda_profile_read", C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int)
 _sig("vit_cuda_dev_alloc", C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p))
 _sig("vit_cuda_dev_free", C.c_int, C.c_int, C.c_void_p)
 _sig("vit_cuda_dev_upload", C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -181,6 +186,30 @@ class Engine:
     def forward_raw(self, images_ptr: int, n: int, logits_ptr: int):
         _check(lib.vit_cuda_forward(images_ptr, n, logits_ptr, None))
 
+    # ---- device-resident path + timing (bench.py)
+    def enqueue_device(self, d_images: int, n: int, d_logits: int, slot: int = 0):
+        _check(lib.vit_cuda_enqueue_device(slot, d_images, n, d_logits))
+
+    def sync(self, slot: int = 0):
+        _check(lib.vit_cuda_sync(slot))
+
+    def timer_start(self, slot: int = 0):
+        _check(lib.vit_cuda_timer_start(slot))
+
+    def timer_stop(self, slot: int = 0) -> float:
+        ms = C.c_float()
+        _check(lib.vit_cuda_timer_stop(slot, C.byref(ms)))
+        return float(ms.value)
+
+    def profile_enable(self, on: bool):
+        _check(lib.vit_cuda_profile_enable(1 if on else 0))
+
+    def profile_read(self, slot: int = 0) -> dict:
+        ms = (C.c_double * len(PROF_CATEGORIES))()
+        cnt = (C.c_longlong * len(PROF_CATEGORIES))()
+        _check(lib.vit_cuda_profile_read(slot, ms, cnt, len(PROF_CATEGORIES)))
+        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(PROF_CATEGORIES)}
+
     def info(self) -> dict:
         v = (C.c_longlong * 8)()
         _check(lib.vit_cuda_info(v, 8))
@@ -269,3 +298,7 @@ def softmax_rows(logits: np.ndarray) -> np.ndarray:
     for i in range(logits.shape[0]):
         lib.vit_softmax(fptr(logits[i]), fptr(out[i]), logits.shape[1])
     return out
+
+
+def launch_count() -> int:
+    return int(lib.vit_cuda_launch_count())
