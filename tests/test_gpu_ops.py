@@ -72,7 +72,7 @@ def test_layernorm(vit, oracle, prec, rows):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 256), (2, 130)])
+@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 256), (2, 130), (40, 197), (70, 100)])
 def test_attention(vit, oracle, prec, batch, tokens):
     qkv = round_operand(_rand((batch * tokens, 2304), 14 + tokens), prec)
     got = vit.op_attention(qkv, batch, tokens, precision=prec)

@@ -147,6 +147,8 @@ CASES = {
     "attention_197": lambda: case_attention(2, 197, 0),
     "attention_197_fp16": lambda: case_attention(2, 197, 1),
     "attention_256": lambda: case_attention(1, 256, 0),
+    "attention_many": lambda: case_attention(40, 197, 0),
+    "attention_many_small": lambda: case_attention(70, 100, 0),
     "embed": lambda: case_embed(0),
     "head": case_head,
     "model_bf16": lambda: case_model(8, 0, 8),

@@ -200,4 +200,251 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     }
 }
 
+// =============================================================================================
+// Persistent, software-pipelined variant (the one the engine uses).
+//
+// One CTA per SM loops over (image, head) items.  Per item the two 128-row query tiles own one
+// 256-column TMEM region each:   S_t fp32 [0,kpad)  ->  P_t (operand precision, packed two per
+// column, written back in place by the softmax threads) [0,kpad/2)  ->  O_t fp32 [128,192).
+// P never touches shared memory: the second MMA takes its A operand from TMEM.  Shared memory
+// holds only the double-buffered Q/K/V tiles of the current and the next item, so the TMA loads
+// of item i+1 run under the softmax of item i, and while one warpgroup is in its softmax the
+// tensor core works for the other one.
+//
+//   warp 8  TMA producer          warp 9  MMA issuer + TMEM owner
+//   warps 0-3 / 4-7  softmax + output warpgroups for query tile 0 / 1
+constexpr int ATTN2_THREADS = 320;
+__host__ __device__ inline int attn2_stage_bytes(int kpad) { return 2 * ATTN_Q_TILE_BYTES + 2 * attn_kv_bytes(kpad); }
+__host__ inline int attn2_smem_bytes(int kpad) { return 2 * attn2_stage_bytes(kpad) + 256 + 1024; }
+
+template <typename T>
+__global__ void __launch_bounds__(ATTN2_THREADS, 1)
+attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                                  const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kv_bytes = attn_kv_bytes(p.kpad);
+    const int stage_bytes = attn2_stage_bytes(p.kpad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+    uint64_t* kv_full = bars;        // [2 stages] Q,K,V of an item landed (tx)
+    uint64_t* stage_free = bars + 2; // [2 stages] every MMA reading the stage has completed
+    uint64_t* s_full = bars + 4;     // [2 tiles]  S_t in TMEM
+    uint64_t* p_full = bars + 6;     // [2 tiles]  P_t written back (128 arrivals)
+    uint64_t* o_full = bars + 8;     // [2 tiles]  O_t in TMEM
+    uint64_t* o_free = bars + 10;    // [2 tiles]  O_t drained, region reusable (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = p.batch * 12;
+    const int nqt = p.tokens > 128 ? 2 : 1;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&stage_free[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_free[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int s = it & 1;
+                const int img = item / 12, head = item - img * 12;
+                const int row0 = img * p.tokens;
+                uint8_t* sQ = smem + s * stage_bytes;
+                uint8_t* sK = sQ + 2 * ATTN_Q_TILE_BYTES;
+                uint8_t* sV = sK + kv_bytes;
+                mbar_wait(&stage_free[s], ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
+                tma_load_2d(sQ, &tmap_q, &kv_full[s], head * ATTN_DH, row0);
+                tma_load_2d(sK, &tmap_kv, &kv_full[s], ATTN_DIM + head * ATTN_DH, row0);
+                tma_load_2d(sV, &tmap_kv, &kv_full[s], 2 * ATTN_DIM + head * ATTN_DH, row0);
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
+            const uint32_t idesc_o = make_idesc<T>(128, ATTN_DH, 0, 1);
+            const int ksteps = p.kpad / 16;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int s = it & 1;
+                const uint32_t q_addr = smem_u32(smem + s * stage_bytes);
+                const uint32_t k_addr = q_addr + 2 * ATTN_Q_TILE_BYTES;
+                const uint32_t v_addr = k_addr + kv_bytes;
+                mbar_wait(&kv_full[s], (it >> 1) & 1);
+                tc_fence_after();
+                for (int t = 0; t < nqt; ++t) {
+                    mbar_wait(&o_free[t], (it & 1) ^ 1);  // previous item's O_t drained
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < ATTN_DH / 16; ++k)
+                        umma_f16(tmem_base + t * 256, desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
+                                 desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
+                    umma_commit(&s_full[t]);
+                }
+                for (int t = 0; t < nqt; ++t) {
+                    mbar_wait(&p_full[t], it & 1);
+                    tc_fence_after();
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma_f16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + ks * 8, desc_mnmajor_sw128(v_addr, ks),
+                                    idesc_o, ks != 0);
+                    umma_commit(&o_full[t]);
+                }
+                umma_commit(&stage_free[s]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax / output warpgroups
+        const int t = warp >> 2;
+        const int quarter = warp & 3;
+        const int qrow = t * 128 + quarter * 32 + lane;
+        const bool warp_active = t < nqt && (t * 128 + quarter * 32) < p.tokens;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+        const int nch = p.kpad / 16;
+        int it = 0;
+        // A warp whose rows are all padding still walks the barriers in lockstep (an mbarrier cannot
+        // take arrivals for a future phase); a whole unused warpgroup (tokens <= 128) does nothing.
+        for (int item = blockIdx.x; t < nqt && item < n_items; item += gridDim.x, ++it) {
+            const int img = item / 12, head = item - img * 12;
+            float inv_sum = 0.f;
+            mbar_wait(&s_full[t], it & 1);
+            tc_fence_after();
+            if (warp_active) {
+                // Both passes walk the S row in steps of 32 columns: two x16 TMEM loads per round
+                // trip, the next step's loads in flight while the current one is processed.
+                const int nsteps = (nch + 1) >> 1;
+                uint32_t ra[32], rb[32];
+                auto load_step = [&](uint32_t* buf, int st) {
+                    tmem_ld_x16p(taddr + st * 32, buf);
+                    if (2 * st + 1 < nch) tmem_ld_x16p(taddr + st * 32 + 16, buf + 16);
+                };
+                // pass 1: row maximum over the valid keys
+                float mx = -INFINITY;
+                auto max_step = [&](const uint32_t* v, int st) {
+                    const int base = st * 32;
+                    if (base + 32 <= p.tokens) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (base + j < p.tokens) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                };
+                load_step(ra, 0);
+                for (int st = 0; st < nsteps; st += 2) {
+                    tmem_ld_wait();
+                    if (st + 1 < nsteps) load_step(rb, st + 1);
+                    max_step(ra, st);
+                    if (st + 1 < nsteps) {
+                        tmem_ld_wait();
+                        if (st + 2 < nsteps) load_step(ra, st + 2);
+                        max_step(rb, st + 1);
+                    }
+                }
+                // pass 2: p = exp2((s - max) * scale*log2e), row sum, P written back in place
+                // (P columns [16 st, 16 st + 16) never overlap S columns not yet read)
+                const float moff = -mx * p.scale_log2;
+                float sum = 0.f;
+                auto exp_step = [&](const uint32_t* v, int st) {
+                    const int base = st * 32;
+                    uint32_t packed[16];
+                    if (base + 32 <= p.tokens) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
+                            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
+                            sum += e0 + e1;
+                            packed[j] = pack2<T>(e0, e1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c0 = base + 2 * j;
+                            float e0 = 0.f, e1 = 0.f;
+                            if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
+                            if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
+                            sum += e0 + e1;
+                            packed[j] = pack2<T>(e0, e1);
+                        }
+                    }
+                    tmem_st_x8p(taddr + st * 16, packed);
+                    if (2 * st + 1 < nch) tmem_st_x8p(taddr + st * 16 + 8, packed + 8);
+                };
+                load_step(ra, 0);
+                for (int st = 0; st < nsteps; st += 2) {
+                    tmem_ld_wait();
+                    if (st + 1 < nsteps) load_step(rb, st + 1);
+                    exp_step(ra, st);
+                    if (st + 1 < nsteps) {
+                        tmem_ld_wait();
+                        if (st + 2 < nsteps) load_step(ra, st + 2);
+                        exp_step(rb, st + 1);
+                    }
+                }
+                inv_sum = 1.0f / sum;
+                tmem_st_wait();
+                tc_fence_before();
+            }
+            mbar_arrive(&p_full[t]);
+            mbar_wait(&o_full[t], it & 1);
+            tc_fence_after();
+            if (warp_active) {
+                uint32_t r0[32], r1[32];
+                tmem_ld_x32(taddr + 128, r0);
+                tmem_ld_x32(taddr + 160, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_free[t]);
+                if (qrow < p.tokens) {
+                    T* orow = static_cast<T*>(p.out) + (static_cast<size_t>(img) * p.tokens + qrow) * ATTN_DIM + head * ATTN_DH;
+                    uint4* dst = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            w[q] = pack2<T>(__uint_as_float(r0[8 * j + 2 * q]) * inv_sum, __uint_as_float(r0[8 * j + 2 * q + 1]) * inv_sum);
+                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            w[q] = pack2<T>(__uint_as_float(r1[8 * j + 2 * q]) * inv_sum, __uint_as_float(r1[8 * j + 2 * q + 1]) * inv_sum);
+                        dst[4 + j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            } else {
+                mbar_arrive(&o_free[t]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 }  // namespace vit

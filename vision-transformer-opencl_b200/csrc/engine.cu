@@ -93,8 +93,38 @@ int check_launch(const char* what) {
     return 0;
 }
 
+constexpr int kPairStages = 6;
+int gemm_impl() {  // VIT_GEMM_IMPL=1 selects the single-CTA 128x256 kernel (A/B testing)
+    static int impl = -1;
+    if (impl < 0) {
+        const char* s = getenv("VIT_GEMM_IMPL");
+        impl = (s && atoi(s) == 1) ? 1 : 2;
+    }
+    return impl;
+}
+
+template <typename T, int EPI>
+int launch_gemm_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count, cudaStream_t st) {
+    using L = GemmPairSmem<kPairStages>;
+    auto kern = gemm_sm100_pair_kernel<T, kPairStages, kGemmEpiWG, EPI>;
+    static int configured_dev_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured_dev_mask & (1 << dev))) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+        configured_dev_mask |= 1 << dev;
+    }
+    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+    const int grid = 2 * std::min(tiles, sm_count / 2);
+    kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, p);
+    return check_launch("gemm_pair");
+}
+
 template <typename T, int EPI>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count, cudaStream_t st) {
+    if (p.N % kGemmBN || p.K % GEMM_BK || p.N > GEMM_MAX_N || p.M <= 0)
+        return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64, N<=3072)", p.M, p.N, p.K);
+    if (gemm_impl() == 2) return launch_gemm_pair_t<T, EPI>(ta, tb, p, sm_count, st);
     using L = GemmSmem<kGemmBN, kGemmStages>;
     auto kern = gemm_sm100_kernel<T, kGemmBN, kGemmStages, kGemmEpiWG, EPI>;
     static bool configured = false;  // per instantiation; attribute is per device but identical on all
@@ -121,18 +151,35 @@ int launch_gemm(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
                                  : launch_gemm_t<__nv_bfloat16, EPI>(ta, tb, p, sm_count, st);
 }
 
+int attention_impl() {  // VIT_ATTN_IMPL=1 selects the simple one-CTA-per-head kernel (A/B testing)
+    static int impl = -1;
+    if (impl < 0) {
+        const char* s = getenv("VIT_ATTN_IMPL");
+        impl = (s && atoi(s) == 1) ? 1 : 2;
+    }
+    return impl;
+}
+
 template <typename T>
-int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
+int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, int sm_count, cudaStream_t st) {
+    if (attention_impl() == 2) {
+        auto kern2 = attention_sm100_persistent_kernel<T>;
+        const int smem2 = attn2_smem_bytes(p.kpad);
+        CU_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        kern2<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem2, st>>>(tq, tkv, p);
+        return check_launch("attention");
+    }
     auto kern = attention_sm100_kernel<T>;
     const int smem = attn_smem_bytes(p.kpad);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<p.batch * kHeads, ATTN_THREADS, smem, st>>>(tq, tkv, p);
     return check_launch("attention");
 }
-int launch_attention(int prec, const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
+int launch_attention(int prec, const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, int sm_count,
+                     cudaStream_t st) {
     if (p.tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", p.tokens);
-    return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tq, tkv, p, st)
-                                 : launch_attention_t<__nv_bfloat16>(tq, tkv, p, st);
+    return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tq, tkv, p, sm_count, st)
+                                 : launch_attention_t<__nv_bfloat16>(tq, tkv, p, sm_count, st);
 }
 
 int launch_layernorm(int prec, const float* x, const float* w, const float* b, void* y, int rows, cudaStream_t st) {
@@ -181,11 +228,9 @@ int check_device(int dev, int* sm_count) {
 }
 
 int watchdog_or_cuda_error(cudaError_t e, const char* what) {
-    unsigned int flag = 0;
-    // After a trap the context is dead and this read fails too; report the trap from the error code.
+    // After a trap the context is dead (the watchdog flag cannot be read back); report it from the error code.
     if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction || e == cudaErrorAssert)
         return set_err(VIT_E_DEVICE_TRAP, "%s: device trap (%s) -- kernel watchdog or fault", what, cudaGetErrorString(e));
-    (void)flag;
     return set_err(VIT_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
@@ -309,17 +354,17 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
             if ((rc = upload_f32(c, &L.fc1_b, lw[9]))) break;
             if ((rc = upload_operand(c, &L.fc2_w, lw[10], scratch, prec))) break;
             if ((rc = upload_f32(c, &L.fc2_b, lw[11]))) break;
-            if ((rc = make_tmap(&L.tm_qkv_w, prec, L.qkv_w, kDim, 3 * kDim, GEMM_BK, kGemmBN))) break;
-            if ((rc = make_tmap(&L.tm_out_w, prec, L.out_w, kDim, kDim, GEMM_BK, kGemmBN))) break;
-            if ((rc = make_tmap(&L.tm_fc1_w, prec, L.fc1_w, kDim, kHidden, GEMM_BK, kGemmBN))) break;
-            if ((rc = make_tmap(&L.tm_fc2_w, prec, L.fc2_w, kHidden, kDim, GEMM_BK, kGemmBN))) break;
+            if ((rc = make_tmap(&L.tm_qkv_w, prec, L.qkv_w, kDim, 3 * kDim, GEMM_BK, 128))) break;
+            if ((rc = make_tmap(&L.tm_out_w, prec, L.out_w, kDim, kDim, GEMM_BK, 128))) break;
+            if ((rc = make_tmap(&L.tm_fc1_w, prec, L.fc1_w, kDim, kHidden, GEMM_BK, 128))) break;
+            if ((rc = make_tmap(&L.tm_fc2_w, prec, L.fc2_w, kHidden, kDim, GEMM_BK, 128))) break;
         }
         if (rc) break;
         if ((rc = upload_f32(c, &c.lnf_w, w[148]))) break;
         if ((rc = upload_f32(c, &c.lnf_b, w[149]))) break;
         if ((rc = upload_f32(c, &c.head_w, w[150]))) break;
         if ((rc = upload_f32(c, &c.head_b, w[151]))) break;
-        if ((rc = make_tmap(&c.tm_conv_w, prec, c.conv_w, kDim, kDim, GEMM_BK, kGemmBN))) break;
+        if ((rc = make_tmap(&c.tm_conv_w, prec, c.conv_w, kDim, kDim, GEMM_BK, 128))) break;
     } while (0);
     cudaError_t se = cudaStreamSynchronize(c.stream);
     cudaFree(scratch);
@@ -407,7 +452,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         }
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
-            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, st));
+            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, c.sm_count, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
@@ -662,28 +707,28 @@ static int slot_device(int gpu_slot, int* dev) {
     return 0;
 }
 int vit_cuda_dev_alloc(int gpu_slot, size_t bytes, void** d_ptr) {
-    int dev;
+    int dev = 0;
     VIT_TRY(slot_device(gpu_slot, &dev));
     CU_TRY(cudaSetDevice(dev));
     CU_TRY(cudaMalloc(d_ptr, bytes));
     return 0;
 }
 int vit_cuda_dev_free(int gpu_slot, void* d_ptr) {
-    int dev;
+    int dev = 0;
     VIT_TRY(slot_device(gpu_slot, &dev));
     CU_TRY(cudaSetDevice(dev));
     CU_TRY(cudaFree(d_ptr));
     return 0;
 }
 int vit_cuda_dev_upload(int gpu_slot, void* d_dst, const void* h_src, size_t bytes) {
-    int dev;
+    int dev = 0;
     VIT_TRY(slot_device(gpu_slot, &dev));
     CU_TRY(cudaSetDevice(dev));
     CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
     return 0;
 }
 int vit_cuda_dev_download(int gpu_slot, void* h_dst, const void* d_src, size_t bytes) {
-    int dev;
+    int dev = 0;
     VIT_TRY(slot_device(gpu_slot, &dev));
     CU_TRY(cudaSetDevice(dev));
     CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
@@ -758,7 +803,7 @@ int vit_cuda_op_linear(const float* x, const float* W, const float* b, const flo
     VIT_TRY(s.upload_f32(&db, b, n));
     CUtensorMap ta, tb;
     VIT_TRY(make_tmap(&ta, precision, dx, k, m, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&tb, precision, dw, k, n, GEMM_BK, kGemmBN));
+    VIT_TRY(make_tmap(&tb, precision, dw, k, n, GEMM_BK, 128));
     if (epilogue == VIT_EPI_BIAS_RESIDUAL) {
         float* dy;
         VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * n));
@@ -796,7 +841,8 @@ int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float*
 }
 
 int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision) {
-    VIT_TRY(op_begin(nullptr));
+    int sms = 0;
+    VIT_TRY(op_begin(&sms));
     if (!qkv || !out || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
     if (tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", tokens);
     Scratch s;
@@ -809,7 +855,7 @@ int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, i
     VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, 256));
     VIT_TRY(make_tmap(&tkv, precision, dqkv, 3 * kDim, rows, ATTN_DH, kpad));
     AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f};
-    VIT_TRY(launch_attention(precision, tq, tkv, p, nullptr));
+    VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr));
     VIT_TRY(op_end("op_attention"));
     VIT_TRY(s.download_operand(out, dout, rows * kDim, precision));
     return op_end("op_attention");
@@ -834,7 +880,7 @@ int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w
     VIT_TRY(s.alloc(reinterpret_cast<void**>(&dx), (size_t)batch * tokens * kDim * 4, true));
     CUtensorMap ta, tb;
     VIT_TRY(make_tmap(&ta, precision, dpatch, kDim, (uint64_t)batch * patches, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&tb, precision, dw, kDim, kDim, GEMM_BK, kGemmBN));
+    VIT_TRY(make_tmap(&tb, precision, dw, kDim, kDim, GEMM_BK, 128));
     VIT_TRY(launch_patchify(precision, dimg, dpatch, batch, img_size, sms, nullptr));
     cls_rows_kernel<<<(batch * kDim + 255) / 256, 256>>>(dx, dcls, dpos, batch, tokens);
     VIT_TRY(check_launch("cls_rows"));

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__((GEMM_NON_EPI_WARPS + 4 * EPI_WG) * 32, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
     using L = GemmSmem<BN, STAGES>;
-    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+    static_assert(BN % 128 == 0 && BN <= 256, "BN");
     static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
     constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     constexpr int COLS_PER_WG = BN / EPI_WG;
@@ -112,7 +112,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-                    tma_load_2d(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+#pragma unroll
+                    for (int h = 0; h < BN / 128; ++h)  // W maps use 128-row boxes (shared with the pair kernel)
+                        tma_load_2d(sa + L::A_BYTES + h * 128 * GEMM_BK * 2, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0 + h * 128);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -228,6 +230,211 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// =============================================================================================
+// CTA-pair variant (the one the engine uses): two CTAs of a cluster cooperate on a 256 x 256
+// output tile with tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA loads only its own 128 rows
+// of A and its own 128 of the 256 W rows per K block (32 KB per stage instead of 48 KB), which
+// cuts the L2 -> SM operand traffic per FLOP by a third -- the limiter of the single-CTA kernel
+// (ncu: L2 throughput bound at ~50 % tensor-pipe utilisation).  Accumulators: 128 lanes x 256
+// columns per CTA, two stages.  The leader CTA issues all MMAs; completion is multicast to both
+// CTAs' barriers; the peer's epilogue releases accumulator stages by remote mbarrier arrives.
+template <int STAGES>
+struct GemmPairSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 128 rows of A
+    static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // this CTA's half of the 256 W rows
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BIAS_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = BIAS_OFF + GEMM_MAX_N * 4;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <typename T, int STAGES, int EPI_WG, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GEMM_NON_EPI_WARPS + 4 * EPI_WG) * 32, 1)
+gemm_sm100_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const GemmParams p) {
+    using L = GemmPairSmem<STAGES>;
+    constexpr int BN = 256;
+    constexpr int COLS_PER_WG = BN / EPI_WG;
+    constexpr int EPI_THREADS = EPI_WG * 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int tiles_n = p.N / BN;
+    const int tiles_m = (p.M + 255) / 256;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = p.K / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * EPI_THREADS / 32);  // one arrival per epilogue warp of both CTAs (used in the leader)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA credit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / tiles_n) * 256 + rank * 128;
+                const int n0 = (tile % tiles_n) * BN + rank * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                    tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+                    tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc<T>(256, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
+                                      (kb | k) != 0);
+                    umma_commit_pair(&empty_bar[stage], 0x3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tfull_bar[acc], 0x3);
+                if ((acc ^= 1) == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= GEMM_NON_EPI_WARPS) {
+        // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int ew = warp - GEMM_NON_EPI_WARPS;
+        const int quarter = warp & 3;
+        const int wg = ew >> 2;
+        const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m0 = (tile / tiles_n) * 256 + rank * 128;
+            const int n0 = (tile % tiles_n) * BN + wg * COLS_PER_WG;
+            const int row = m0 + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * COLS_PER_WG;
+
+            size_t out_row = static_cast<size_t>(row);
+            const float* res_row = nullptr;
+            if constexpr (EPI == EPI_BIAS_RESIDUAL) {
+                res_row = p.residual + static_cast<size_t>(row) * p.N;
+            } else if constexpr (EPI == EPI_PATCH_EMBED) {
+                const int img = row / p.patches;
+                const int pp = row - img * p.patches;
+                out_row = static_cast<size_t>(img) * p.tokens + 1 + pp;
+                res_row = p.residual + static_cast<size_t>(1 + pp) * p.N;
+            }
+#pragma unroll 1
+            for (int c = 0; c < COLS_PER_WG / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (c == COLS_PER_WG / 32 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                }
+                const int col = n0 + c * 32;
+                const float* sb = s_bias + col;
+                if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v0 = __uint_as_float(r[2 * j]) + sb[2 * j];
+                        float v1 = __uint_as_float(r[2 * j + 1]) + sb[2 * j + 1];
+                        if constexpr (EPI == EPI_BIAS_GELU) {
+                            v0 = gelu_erf(v0);
+                            v1 = gelu_erf(v1);
+                        }
+                        packed[j] = pack2<T>(v0, v1);
+                    }
+                    if (row_ok) {
+                        uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + out_row * p.N + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                } else {
+                    if (row_ok) {
+                        const float4* rs = reinterpret_cast<const float4*>(res_row + col);
+                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.N + col);
+                        float4 rv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rv[j] = rs[j];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o;
+                            o.x = rv[j].x + (__uint_as_float(r[4 * j + 0]) + sb[4 * j + 0]);
+                            o.y = rv[j].y + (__uint_as_float(r[4 * j + 1]) + sb[4 * j + 1]);
+                            o.z = rv[j].z + (__uint_as_float(r[4 * j + 2]) + sb[4 * j + 2]);
+                            o.w = rv[j].w + (__uint_as_float(r[4 * j + 3]) + sb[4 * j + 3]);
+                            dst[j] = o;
+                        }
+                    }
+                }
+            }
+            if ((acc ^= 1) == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer may still multicast into / read from this CTA's smem until here
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair<512>(tmem_base);
     }
 }
 
