@@ -64,22 +64,31 @@ int load_driver() {
     return 0;
 }
 
-// 2-D row-major [rows][cols] tensor of 16-bit elements, box {box_cols, box_rows}, 128B swizzle.
-int make_tmap(CUtensorMap* m, int prec, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
-              uint32_t box_rows) {
+// 2-D row-major [rows][cols] tensor, box {box_cols, box_rows}, 128B swizzle (box_cols * elem = 128 B).
+int make_tmap_raw(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t cols, uint64_t rows,
+                  uint32_t box_cols, uint32_t box_rows) {
     VIT_TRY(load_driver());
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint64_t strides[1] = {cols * elem_bytes};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = g_encode(m, prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                                2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = g_encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu box=%ux%u", (int)r,
                        (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
     return 0;
+}
+// operand-precision (16-bit) tensor
+int make_tmap(CUtensorMap* m, int prec, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+              uint32_t box_rows) {
+    return make_tmap_raw(m, prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base,
+                         cols, rows, box_cols, box_rows);
+}
+// fp32 tensor (residual stream): 32 columns = 128 bytes per box row
+int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+    return make_tmap_raw(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, cols, rows, 32, box_rows);
 }
 
 // ------------------------------------------------------------------------------------ launches
@@ -118,6 +127,34 @@ int launch_gemm_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     const int grid = 2 * std::min(tiles, sm_count / 2);
     kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, p);
     return check_launch("gemm_pair");
+}
+
+constexpr int kStagedStages = 5, kStagedSlots = 4;
+template <typename T, int EPI>
+int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
+                         int sm_count, cudaStream_t st) {
+    using L = GemmStagedSmem<kStagedStages, kStagedSlots>;
+    auto kern = gemm_sm100_staged_kernel<T, kStagedStages, kStagedSlots, EPI>;
+    static int configured_dev_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured_dev_mask & (1 << dev))) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+        configured_dev_mask |= 1 << dev;
+    }
+    if (p.N % kGemmBN || p.K % GEMM_BK || p.M <= 0)
+        return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64)", p.M, p.N, p.K);
+    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+    const int grid = 2 * std::min(tiles, sm_count / 2);
+    kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, tout, p);
+    return check_launch("gemm_staged");
+}
+// tout: store map of the output (for the residual epilogue also the load map of the residual, in place)
+template <int EPI>
+int launch_gemm_staged(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
+                       int sm_count, cudaStream_t st) {
+    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI>(ta, tb, tout, p, sm_count, st)
+                                 : launch_gemm_staged_t<__nv_bfloat16, EPI>(ta, tb, tout, p, sm_count, st);
 }
 
 template <typename T, int EPI>
@@ -261,7 +298,10 @@ struct DeviceCtx {
     float* images[2] = {nullptr, nullptr};
     void *patches = nullptr, *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr;
     float *x = nullptr, *cls_ln = nullptr, *logits = nullptr;
-    CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_q, tm_kv;
+    // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
+    // use, so TMA zero-fills loads and clips stores past the last image
+    int maps_nb = -1;
+    CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_x, tm_q, tm_kv;
     size_t ws_bytes = 0;
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
@@ -384,16 +424,26 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
     VIT_TRY(dev_alloc(c, &c.hid, rows * kHidden * 2, true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.cls_ln), B * kDim * 4, true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.logits), B * kClasses * 4, true));
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
+    if (c.maps_nb == nb) return 0;
+    const int prec = e.prec;
+    const uint64_t rows = static_cast<uint64_t>(nb) * e.tokens, prow = static_cast<uint64_t>(nb) * e.patches;
     VIT_TRY(make_tmap(&c.tm_patches, prec, c.patches, kDim, prow, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&c.tm_xn, prec, c.xn, kDim, rows, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&c.tm_ao, prec, c.ao, kDim, rows, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));     // mlp_0 store + mlp_3 A load
+    VIT_TRY(make_tmap(&c.tm_qkv_st, prec, c.qkv, 3 * kDim, rows, GEMM_BK, GEMM_BM)); // in_proj store
+    VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
     if (e.tokens <= 256) {
         const int kpad = (e.tokens + 15) / 16 * 16;
         VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, 256));
         VIT_TRY(make_tmap(&c.tm_kv, prec, c.qkv, 3 * kDim, rows, ATTN_DH, kpad));
     }
-    CU_TRY(cudaStreamSynchronize(c.stream));
+    c.maps_nb = nb;
     return 0;
 }
 
@@ -425,6 +475,8 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     cudaStream_t st = c.stream;
     const int prec = e.prec;
     const int rows = nb * e.tokens;
+    VIT_TRY(ensure_maps(c, e, nb));
+    const bool staged = gemm_impl() == 2;
     // conv_proj: patch rows -> GEMM with (+bias, +pos_embedding, row remap) epilogue; class rows aside
     const bool pf = e.profiling;
     {
@@ -448,7 +500,8 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         {
             ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
             GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0};
-            VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, p, c.sm_count, st));
+            else VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
@@ -457,7 +510,8 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         {
             ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
             GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x, 0, 0};
-            VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, p, c.sm_count, st));
+            else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
@@ -466,12 +520,14 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         {
             ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
             GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr, 0, 0};
-            VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, c.tm_hid, p, c.sm_count, st));
+            else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
             GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x, 0, 0};
-            VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, p, c.sm_count, st));
+            else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
         }
     }
     ProfScope ps(c, pf, VIT_PROF_HEAD);
@@ -804,20 +860,29 @@ int vit_cuda_op_linear(const float* x, const float* W, const float* b, const flo
     CUtensorMap ta, tb;
     VIT_TRY(make_tmap(&ta, precision, dx, k, m, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&tb, precision, dw, k, n, GEMM_BK, 128));
+    const bool staged = gemm_impl() == 2;
+    CUtensorMap tout;
     if (epilogue == VIT_EPI_BIAS_RESIDUAL) {
         float* dy;
         VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * n));
         GemmParams p{m, n, k, db, dy, dy, 0, 0};
-        VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(precision, ta, tb, p, sms, nullptr));
+        VIT_TRY(make_tmap_f32(&tout, dy, n, m, GEMM_BM));
+        if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(precision, ta, tb, tout, p, sms, nullptr));
+        else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(precision, ta, tb, p, sms, nullptr));
         VIT_TRY(op_end("op_linear"));
         CU_TRY(cudaMemcpy(y, dy, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
     } else {
         void* dy;
         VIT_TRY(s.alloc(&dy, (size_t)m * n * 2, true));
         GemmParams p{m, n, k, db, dy, nullptr, 0, 0};
-        if (epilogue == VIT_EPI_BIAS_GELU) VIT_TRY(launch_gemm<EPI_BIAS_GELU>(precision, ta, tb, p, sms, nullptr));
-        else if (epilogue == VIT_EPI_BIAS) VIT_TRY(launch_gemm<EPI_BIAS>(precision, ta, tb, p, sms, nullptr));
-        else return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
+        VIT_TRY(make_tmap(&tout, precision, dy, n, m, GEMM_BK, GEMM_BM));
+        if (epilogue == VIT_EPI_BIAS_GELU) {
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(precision, ta, tb, tout, p, sms, nullptr));
+            else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(precision, ta, tb, p, sms, nullptr));
+        } else if (epilogue == VIT_EPI_BIAS) {
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(precision, ta, tb, tout, p, sms, nullptr));
+            else VIT_TRY(launch_gemm<EPI_BIAS>(precision, ta, tb, p, sms, nullptr));
+        } else return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
         VIT_TRY(op_end("op_linear"));
         VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
     }

@@ -438,4 +438,256 @@ gemm_sm100_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
+// =============================================================================================
+// CTA-pair GEMM with a staged epilogue (the kernel the engine uses for in_proj, out_proj, mlp_0
+// and mlp_3).  Main loop as in gemm_sm100_pair_kernel.  The epilogue no longer touches global
+// memory from registers (one thread per row => 32 different cache lines per warp instruction,
+// a latency-bound trickle, ncu profiles/r1_*): the 8 epilogue warps walk the 128 x 256 accumulator
+// in column chunks that are exactly one 128-byte-per-row, 128B-swizzled shared-memory slot
+// (64 operand-precision columns, or 32 fp32 columns), and
+//   * results leave through TMA bulk stores issued by one thread per chunk;
+//   * for the residual epilogue the fp32 residual chunk is TMA-loaded into the slot ahead of time
+//     by a dedicated loader warp, updated in place, and stored back -- so both directions of the
+//     residual stream move as full 128-byte rows, asynchronously, under the next tile's MMAs.
+// Slots form a ring shared by loader, epilogue warps and the storing thread.
+constexpr int GEMM_SLOT_BYTES = 128 * 128;
+
+template <int STAGES, int SLOTS>
+struct GemmStagedSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = 128 * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SLOT_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BIAS_OFF = SLOT_OFF + SLOTS * GEMM_SLOT_BYTES;
+    static constexpr int BAR_OFF = BIAS_OFF + 2 * 256 * 4;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * SLOTS;
+    static constexpr int DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16;  // base must be 1024-aligned (checked)
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <typename T, int STAGES, int SLOTS, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+    using L = GemmStagedSmem<STAGES, SLOTS>;
+    static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESIDUAL, "staged epilogues");
+    constexpr bool kResidual = EPI == EPI_BIAS_RESIDUAL;
+    constexpr int BN = 256;
+    constexpr int CHUNK_COLS = kResidual ? 32 : 64;      // one 128-byte row segment per chunk
+    constexpr int NCHUNK = BN / CHUNK_COLS;
+    constexpr int COLS_PER_WARP = CHUNK_COLS / 2;        // two warps share a TMEM lane quarter
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* res_full = tempty_bar + 2;     // [SLOTS] residual chunk landed in the slot
+    uint64_t* slot_free = res_full + SLOTS;  // [SLOTS] the store out of the slot has drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_free + SLOTS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int tiles_n = p.N / BN;
+    const int tiles_m = (p.M + 255) / 256;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = p.K / GEMM_BK;
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzle atoms need 1 KB alignment
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        tma_prefetch_desc(&tmap_out);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 16);  // one arrival per epilogue warp of both CTAs (used in the leader)
+        }
+        for (int s = 0; s < SLOTS; ++s) {
+            mbar_init(&res_full[s], 1);
+            mbar_init(&slot_free[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ operand producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / tiles_n) * 256 + rank * 128;
+                const int n0 = (tile % tiles_n) * BN + rank * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                    tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+                    tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = make_idesc<T>(256, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
+                                      (kb | k) != 0);
+                    umma_commit_pair(&empty_bar[stage], 0x3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tfull_bar[acc], 0x3);
+                if ((acc ^= 1) == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------ residual loader (EPI_BIAS_RESIDUAL)
+        if (kResidual && lane == 0) {
+            uint32_t k = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / tiles_n) * 256 + rank * 128;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int c = 0; c < NCHUNK; ++c, ++k) {
+                    const uint32_t slot = k % SLOTS, ph = (k / SLOTS) & 1;
+                    mbar_wait(&slot_free[slot], ph ^ 1);
+                    mbar_arrive_expect_tx(&res_full[slot], GEMM_SLOT_BYTES);
+                    tma_load_2d(smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, &tmap_out, &res_full[slot], n0 + c * CHUNK_COLS, m0);
+                }
+            }
+        }
+    } else if (warp >= GEMM_NON_EPI_WARPS) {
+        // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int ew = warp - GEMM_NON_EPI_WARPS;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;                 // which half of the chunk's columns
+        const int etid = threadIdx.x - GEMM_NON_EPI_WARPS * 32;
+        const bool storer = etid == 0;
+        const int row = quarter * 32 + lane;      // row inside the CTA's 128-row block
+        const uint32_t row_off = row * 128, sw = row & 7;
+        const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t k = 0;  // running chunk counter (ring position)
+        int tile_par = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, tile_par ^= 1) {
+            const int m0 = (tile / tiles_n) * 256 + rank * 128;
+            const int n0 = (tile % tiles_n) * BN;
+            float* sb = s_bias + tile_par * 256;
+            sb[etid] = p.bias[n0 + etid];         // visible after the first chunk barrier below... used before: sync now
+            epi_bar_sync();
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c, ++k) {
+                const uint32_t slot = k % SLOTS;
+                uint8_t* srow = smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES + row_off;
+                const float* bcol = sb + c * CHUNK_COLS + half * COLS_PER_WARP;
+                if constexpr (kResidual) {
+                    uint32_t r[16];
+                    tmem_ld_x16p(taddr + c * CHUNK_COLS, r);
+                    tmem_ld_wait();
+                    if (c == NCHUNK - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                    }
+                    mbar_wait(&res_full[slot], (k / SLOTS) & 1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4* q = reinterpret_cast<float4*>(srow + (((half * 4 + j) ^ sw) << 4));
+                        float4 v = *q;
+                        v.x += __uint_as_float(r[4 * j + 0]) + bcol[4 * j + 0];
+                        v.y += __uint_as_float(r[4 * j + 1]) + bcol[4 * j + 1];
+                        v.z += __uint_as_float(r[4 * j + 2]) + bcol[4 * j + 2];
+                        v.w += __uint_as_float(r[4 * j + 3]) + bcol[4 * j + 3];
+                        *q = v;
+                    }
+                } else {
+                    uint32_t r[32];
+                    tmem_ld_x32(taddr + c * CHUNK_COLS, r);
+                    tmem_ld_wait();
+                    if (c == NCHUNK - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+                    }
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v0 = __uint_as_float(r[2 * j]) + bcol[2 * j];
+                        float v1 = __uint_as_float(r[2 * j + 1]) + bcol[2 * j + 1];
+                        if constexpr (EPI == EPI_BIAS_GELU) {
+                            v0 = gelu_erf(v0);
+                            v1 = gelu_erf(v1);
+                        }
+                        packed[j] = pack2<T>(v0, v1);
+                    }
+                    // the slot's previous store (chunk k - SLOTS) has drained: the storer checked before
+                    // the barrier that ended chunk k - 1
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ sw) << 4)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+                fence_proxy_async_smem();
+                if (!kResidual && storer) tma_store_wait_read<SLOTS - 2>();  // frees the slot of chunk k + 1
+                epi_bar_sync();
+                if (storer) {
+                    tma_store_2d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, m0);
+                    tma_store_commit();
+                    if constexpr (kResidual) {
+                        if (k >= 1) {  // the previous chunk's store has finished reading its slot: hand it to the loader
+                            tma_store_wait_read<1>();
+                            mbar_arrive(&slot_free[(k - 1) % SLOTS]);
+                        }
+                    }
+                }
+            }
+            if ((acc ^= 1) == 0) acc_phase ^= 1;
+        }
+        if (storer) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair<512>(tmem_base);
+    }
+}
+
 }  // namespace vit
