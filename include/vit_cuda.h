@@ -72,6 +72,11 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size,
  * overlapped.  Synchronous: everything is on the host when the call returns. */
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out);
 
+/* The contiguous shard [*lo, *hi) of n images that GPU slot g of n_gpus processes in
+ * vit_cuda_forward: ceil(n / n_gpus) images per slot, the last ones possibly fewer or none.
+ * Pure host arithmetic (usable without a device); returns VIT_E_ARG on bad arguments. */
+int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi);
+
 /* Device-resident variant for one GPU slot (0 <= gpu_slot < n_gpus): d_images and d_logits
  * are device pointers on that GPU, n <= max_batch_per_gpu.  Work is enqueued on the
  * engine's stream for that slot and the call returns after it has completed. */

@@ -1,0 +1,107 @@
+"""Host-side C code (no GPU): loaders, result writer, comparator rule, tensor table, synthetic
+asset generator."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+REF_NET = Path("/root/reference/Network")
+
+
+def test_tensor_table_matches_state_dict_layout(vit):
+    sizes = [vit.tensor_numel(i) for i in range(152)]
+    assert sum(sizes) == 86_567_656  # ViT-B/16 parameter count
+    assert vit.tensor_numel(3, 384) == 577 * 768 and vit.tensor_numel(3) == 197 * 768
+    assert vit.tensor_name(0) == "class_token" and vit.tensor_name(151) == "heads_head_bias"
+    assert vit.tensor_name(4 + 12 * 7 + 8) == "encoder_layers_encoder_layer_7_mlp_0_weight"
+    assert vit.tensor_numel(-1) == 0 and vit.tensor_numel(152) == 0
+
+
+@pytest.mark.skipif(not REF_NET.exists(), reason="reference Network/ directory not mounted")
+def test_tensor_table_matches_shipped_weight_files(vit):
+    """Every Weight_<idx>_<name>.bin the reference ships has the name and size our table predicts."""
+    files = sorted(REF_NET.glob("Weight_*.bin"))
+    assert len(files) >= 100
+    for f in files:
+        idx = int(f.name.split("_")[1])
+        assert f.name == f"Weight_{idx}_{vit.tensor_name(idx)}.bin"
+        assert f.stat().st_size == 4 * vit.tensor_numel(idx)
+
+
+@pytest.mark.skipif(not REF_NET.exists(), reason="reference Network/ directory not mounted")
+def test_load_shipped_weights_reports_the_missing_ones(vit, capfd):
+    net = (vit.Tensor * 152)()
+    n = vit.lib.load_weights(str(REF_NET).encode(), net, 152)
+    assert n == len(list(REF_NET.glob("Weight_*.bin"))) == 116
+    rc = vit.lib.vit_validate_weights(net, 152, 224)
+    assert rc == -(6 + 1)  # first absent tensor: layer-0 in_proj_weight
+    assert "missing" in capfd.readouterr().err
+    w = np.ctypeslib.as_array(net[1].data, (net[1].size,))
+    # values are rounded to 6 decimals in fp32 (Network.c:185-187): re-rounding is the identity
+    assert np.array_equal(np.float32(np.round(w * np.float32(1e6))) / np.float32(1e6), w)
+    vit.lib.free_weights(net, 152)
+
+
+def test_load_weights_errors(vit, tmp_path, capfd):
+    net = (vit.Tensor * 152)()
+    assert vit.lib.load_weights(str(tmp_path / "nope").encode(), net, 152) == -1
+    (tmp_path / "Weight_abc_x.bin").write_bytes(b"\0" * 8)      # unparsable index: ignored
+    (tmp_path / "Weight_999_x.bin").write_bytes(b"\0" * 8)      # out of range: ignored
+    (tmp_path / "Weight_5_x.txt").write_bytes(b"\0" * 8)        # wrong extension: ignored
+    (tmp_path / "Weight_7_empty.bin").write_bytes(b"")          # empty: ignored
+    assert vit.lib.load_weights(str(tmp_path).encode(), net, 152) == 0
+    assert vit.lib.load_image_data(str(tmp_path / "nope.bin").encode()) is None or not vit.lib.load_image_data(str(tmp_path / "nope.bin").encode())
+    (tmp_path / "short.bin").write_bytes(np.array([2, 3, 4, 4], dtype=np.int32).tobytes() + b"\0" * 10)
+    assert not vit.lib.load_image_data(str(tmp_path / "short.bin").encode())
+    capfd.readouterr()
+
+
+def test_result_file_format_and_comparator_rule(vit, tmp_path):
+    """Main.c:71 line format; comparator.c:43-74 rule with the line count as an argument."""
+    probs = np.full((3, 1000), 1e-4, dtype=np.float32)
+    probs[0, 65], probs[1, 795], probs[2, 0] = 0.919345, 0.824735, 0.5
+    rows = (C.POINTER(C.c_float) * 3)(*[vit.fptr(probs[i]) for i in range(3)])
+    res = tmp_path / "res.txt"
+    assert vit.lib.write_results(str(res).encode(), rows, 3) == 0
+    assert res.read_text() == "[0] label: 65 / prob: 0.919345\n[1] label: 795 / prob: 0.824735\n[2] label: 0 / prob: 0.500000\n"
+    ans = tmp_path / "ans.txt"
+    cmp = lambda n: vit.lib.comparator_files(str(res).encode(), str(ans).encode(), n)
+    ans.write_text("[0] label: 65 / prob: 0.925000\n[1] label: 795 / prob: 0.824735\n[2] label: 0 / prob: 0.5\n")
+    assert cmp(3) == 0                                   # |dprob| = 0.0057 <= 0.01
+    ans.write_text("[0] label: 65 / prob: 0.930000\n[1] label: 794 / prob: 0.824735\n[2] label: 1 / prob: 0.6\n")
+    assert cmp(3) == 4                                   # prob; label; label + prob
+    assert cmp(1) == 1
+    ans.write_text("[0] label: 65 / prob: 0.919345\n")
+    assert cmp(3) == 1                                   # short file: +1 and stop
+    ans.write_text("garbage\n[1] label: 795 / prob: 0.824735\n")
+    assert cmp(2) == 1                                   # unparsable line: +1, continue
+    assert vit.lib.comparator_files(b"/nonexistent", str(ans).encode(), 1) == 1
+
+
+def test_softmax_and_argmax(vit):
+    x = np.array([1.0, 3.0, 3.0, -2.0], dtype=np.float32)
+    p = np.empty_like(x)
+    vit.lib.vit_softmax(vit.fptr(x), vit.fptr(p), 4)
+    e = np.exp(x - 3.0)
+    assert np.allclose(p, e / e.sum(), rtol=1e-6)
+    assert vit.lib.vit_argmax(vit.fptr(x), 4) == 1       # lowest index wins ties
+
+
+def test_synthetic_assets_are_deterministic(vit):
+    a = vit.synth_weights(224, 42)
+    b = vit.synth_weights(224, 42)
+    c = vit.synth_weights(224, 43)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert not np.array_equal(a[6], c[6])
+    # fixed values: the generator is integer hashing + exact float arithmetic, identical everywhere
+    assert a[6][:3].tolist() == [float(np.float32(v)) for v in (0.027973, -0.034692, 0.005305)]
+    assert abs(float(a[6].std()) - 0.03) < 1e-3 and abs(float(a[4].mean()) - 1.0) < 1e-2
+    i1 = vit.synth_images(4, 224, 7)
+    i2 = vit.synth_images(2, 224, 7, first_index=2)
+    assert np.array_equal(i1[2:], i2)                    # image i depends only on (seed, i): shardable
+    assert i1.min() >= -2.12 and i1.max() <= 2.64
+    w384 = vit.synth_weights(384, 42)
+    assert w384[3].size == 577 * 768 and np.array_equal(w384[6], a[6])
+    net = vit.as_network(a)
+    assert vit.lib.vit_validate_weights(net, 152, 224) == 0

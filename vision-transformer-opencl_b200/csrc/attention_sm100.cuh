@@ -214,6 +214,24 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 //   warp 8  TMA producer          warp 9  MMA issuer + TMEM owner
 //   warps 0-3 / 4-7  softmax + output warpgroups for query tile 0 / 1
 constexpr int ATTN2_THREADS = 320;
+// TMEM column plan (512 columns).  With kpad <= 224 (ViT-B/16 at 224^2: kpad = 208):
+//   S_0/P_0 [0,kpad)   S_1/P_1 [kpad,2 kpad)   O_1 inside its S region at +128   O_0 [2 kpad, 2 kpad+64)
+// so S_0 of the next item can be issued without waiting for O_0 to be drained.  Otherwise
+//   S_0 [0,256)  S_1 [256,512)  O_t inside its own S region at +128.
+struct AttnTmemPlan {
+    uint32_t s1, o0, o1;  // column of S_1, O_0, O_1 (S_0 is at column 0)
+    bool spare;
+    __device__ __forceinline__ uint32_t s_col(int t) const { return t ? s1 : 0u; }
+    __device__ __forceinline__ uint32_t o_col(int t) const { return t ? o1 : o0; }
+};
+__device__ __forceinline__ AttnTmemPlan attn2_tmem_plan(int kpad) {
+    AttnTmemPlan pl;
+    pl.spare = 2 * kpad + 64 <= 512;
+    pl.s1 = pl.spare ? kpad : 256;
+    pl.o1 = pl.s1 + 128;
+    pl.o0 = pl.spare ? 2 * kpad : 128;
+    return pl;
+}
 __host__ __device__ inline int attn2_stage_bytes(int kpad) { return 2 * ATTN_Q_TILE_BYTES + 2 * attn_kv_bytes(kpad); }
 __host__ inline int attn2_smem_bytes(int kpad) { return 2 * attn2_stage_bytes(kpad) + 256 + 1024; }
 
@@ -238,6 +256,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
     const int lane = threadIdx.x & 31;
     const int n_items = p.batch * 12;
     const int nqt = p.tokens > 128 ? 2 : 1;
+    const AttnTmemPlan plan = attn2_tmem_plan(p.kpad);
 
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -282,32 +301,55 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
             const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
             const uint32_t idesc_o = make_idesc<T>(128, ATTN_DH, 0, 1);
             const int ksteps = p.kpad / 16;
+            auto issue_s = [&](int t, int stage) {  // S_t = Q_t K^T of the item staged in `stage`
+                const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+                const uint32_t k_addr = q_addr + 2 * ATTN_Q_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < ATTN_DH / 16; ++k)
+                    umma_f16(tmem_base + plan.s_col(t), desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
+                             desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
+                umma_commit(&s_full[t]);
+            };
+            auto issue_pv = [&](int t, int stage) {  // O_t = P_t V, P_t read from TMEM
+                const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * ATTN_Q_TILE_BYTES + kv_bytes;
+                for (int ks = 0; ks < ksteps; ++ks)
+                    umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8, desc_mnmajor_sw128(v_addr, ks),
+                                idesc_o, ks != 0);
+                umma_commit(&o_full[t]);
+            };
+            // Issue order per item i:  PV_0(i), S_0(i+1), PV_1(i), S_1(i+1).  O_0 lives outside the S
+            // regions (spare columns), so S_0 of the next item does not wait for the output drain of
+            // this one; the tensor pipe executes in issue order, which protects P_0(i) from S_0(i+1).
             int it = 0;
+            if (blockIdx.x < n_items) {
+                mbar_wait(&kv_full[0], 0);
+                tc_fence_after();
+                for (int t = 0; t < nqt; ++t) issue_s(t, 0);
+            }
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int s = it & 1;
-                const uint32_t q_addr = smem_u32(smem + s * stage_bytes);
-                const uint32_t k_addr = q_addr + 2 * ATTN_Q_TILE_BYTES;
-                const uint32_t v_addr = k_addr + kv_bytes;
-                mbar_wait(&kv_full[s], (it >> 1) & 1);
+                const bool has_next = item + static_cast<int>(gridDim.x) < n_items;
+                mbar_wait(&p_full[0], it & 1);
+                if (plan.spare) mbar_wait(&o_free[0], (it & 1) ^ 1);  // O_0 of the previous item drained
                 tc_fence_after();
-                for (int t = 0; t < nqt; ++t) {
-                    mbar_wait(&o_free[t], (it & 1) ^ 1);  // previous item's O_t drained
+                issue_pv(0, s);
+                if (has_next) {
+                    mbar_wait(&kv_full[s ^ 1], ((it + 1) >> 1) & 1);
+                    if (!plan.spare) mbar_wait(&o_free[0], it & 1);  // O_0 shares the S_0 region
                     tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < ATTN_DH / 16; ++k)
-                        umma_f16(tmem_base + t * 256, desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
-                                 desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
-                    umma_commit(&s_full[t]);
+                    issue_s(0, s ^ 1);
                 }
-                for (int t = 0; t < nqt; ++t) {
-                    mbar_wait(&p_full[t], it & 1);
+                if (nqt > 1) {
+                    mbar_wait(&p_full[1], it & 1);
                     tc_fence_after();
-                    for (int ks = 0; ks < ksteps; ++ks)
-                        umma_f16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + ks * 8, desc_mnmajor_sw128(v_addr, ks),
-                                    idesc_o, ks != 0);
-                    umma_commit(&o_full[t]);
+                    issue_pv(1, s);
                 }
                 umma_commit(&stage_free[s]);
+                if (has_next && nqt > 1) {
+                    mbar_wait(&o_free[1], it & 1);  // O_1 (inside the S_1 region) of this item drained
+                    tc_fence_after();
+                    issue_s(1, s ^ 1);
+                }
             }
         }
     } else {
@@ -316,7 +358,9 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
         const int quarter = warp & 3;
         const int qrow = t * 128 + quarter * 32 + lane;
         const bool warp_active = t < nqt && (t * 128 + quarter * 32) < p.tokens;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
+        const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t taddr = tmem_base + lane_bits + plan.s_col(t & 1);
+        const uint32_t oaddr = tmem_base + lane_bits + plan.o_col(t & 1);
         const int nch = p.kpad / 16;
         int it = 0;
         // A warp whose rows are all padding still walks the barriers in lockstep (an mbarrier cannot
@@ -336,16 +380,16 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                     if (2 * st + 1 < nch) tmem_ld_x16p(taddr + st * 32 + 16, buf + 16);
                 };
                 // pass 1: row maximum over the valid keys
-                float mx = -INFINITY;
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
                 auto max_step = [&](const uint32_t* v, int st) {
                     const int base = st * 32;
                     if (base + 32 <= p.tokens) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (base + j < p.tokens) mx = fmaxf(mx, __uint_as_float(v[j]));
+                            if (base + j < p.tokens) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
                     }
                 };
                 load_step(ra, 0);
@@ -361,8 +405,9 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                 }
                 // pass 2: p = exp2((s - max) * scale*log2e), row sum, P written back in place
                 // (P columns [16 st, 16 st + 16) never overlap S columns not yet read)
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 const float moff = -mx * p.scale_log2;
-                float sum = 0.f;
+                float sum4[4] = {0.f, 0.f, 0.f, 0.f};
                 auto exp_step = [&](const uint32_t* v, int st) {
                     const int base = st * 32;
                     uint32_t packed[16];
@@ -371,7 +416,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                         for (int j = 0; j < 16; ++j) {
                             const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
                             const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-                            sum += e0 + e1;
+                            sum4[j & 3] += e0 + e1;
                             packed[j] = pack2<T>(e0, e1);
                         }
                     } else {
@@ -381,7 +426,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                             float e0 = 0.f, e1 = 0.f;
                             if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
                             if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-                            sum += e0 + e1;
+                            sum4[j & 3] += e0 + e1;
                             packed[j] = pack2<T>(e0, e1);
                         }
                     }
@@ -399,7 +444,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                         exp_step(rb, st + 1);
                     }
                 }
-                inv_sum = 1.0f / sum;
+                inv_sum = fast_rcp((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
                 tmem_st_wait();
                 tc_fence_before();
             }
@@ -408,8 +453,8 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
             tc_fence_after();
             if (warp_active) {
                 uint32_t r0[32], r1[32];
-                tmem_ld_x32(taddr + 128, r0);
-                tmem_ld_x32(taddr + 160, r1);
+                tmem_ld_x32(oaddr, r0);
+                tmem_ld_x32(oaddr + 32, r1);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&o_free[t]);

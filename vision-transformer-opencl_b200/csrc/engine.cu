@@ -638,6 +638,14 @@ int vit_cuda_forward_device(int gpu_slot, const float* d_images, int n, float* d
     return vit_cuda_sync(gpu_slot);
 }
 
+int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi) {
+    if (n < 0 || n_gpus <= 0 || g < 0 || g >= n_gpus || !lo || !hi) return set_err(VIT_E_ARG, "bad shard arguments");
+    const int per_gpu = (n + n_gpus - 1) / n_gpus;
+    *lo = std::min(n, g * per_gpu);
+    *hi = std::min(n, *lo + per_gpu);
+    return 0;
+}
+
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out) {
     Engine& e = g_eng;
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
@@ -655,7 +663,8 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
     for (int pass = 0; pass < max_passes; ++pass) {
         for (int g = 0; g < G; ++g) {
             DeviceCtx& c = e.ctx[g];
-            const int lo = std::min(n, g * per_gpu), hi = std::min(n, lo + per_gpu);
+            int lo, hi;
+            vit_cuda_shard_range(n, G, g, &lo, &hi);
             const int first = lo + pass * pass_size;
             if (first >= hi) continue;
             const int nb = std::min(pass_size, hi - first);

@@ -55,6 +55,7 @@ def _sig(name, res, *args):
 _sig("vit_cuda_init", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_init_ex", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int)
 _sig("vit_cuda_forward", C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+_sig("vit_cuda_shard_range", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p)
 _sig("vit_cuda_forward_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_enqueue_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_sync", C.c_int, C.c_int)
@@ -226,6 +227,12 @@ class Engine:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def shard_range(n: int, n_gpus: int, g: int) -> tuple[int, int]:
+    lo, hi = C.c_int(), C.c_int()
+    _check(lib.vit_cuda_shard_range(n, n_gpus, g, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
 
 
 def dev_alloc(slot: int, nbytes: int) -> int:
