@@ -17,6 +17,13 @@ def _rand(shape, seed, scale=1.0):
     return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
 
 
+def _round_qkv(qkv, prec):
+    """Q, K in the operand precision; V always bf16 (the in_proj epilogue stores the V block so)."""
+    out = round_operand(qkv, prec)
+    out[:, 1536:] = round_operand(qkv[:, 1536:], 0)
+    return out
+
+
 def _close(got, ref, rtol, atol, what):
     err = np.abs(got - ref)
     bound = atol + rtol * np.abs(ref)
@@ -74,15 +81,34 @@ def test_layernorm(vit, oracle, prec, rows):
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 256), (2, 130), (40, 197), (70, 100)])
 def test_attention(vit, oracle, prec, batch, tokens):
-    qkv = round_operand(_rand((batch * tokens, 2304), 14 + tokens), prec)
+    qkv = _round_qkv(_rand((batch * tokens, 2304), 14 + tokens), prec)
     got = vit.op_attention(qkv, batch, tokens, precision=prec)
     ref = np.empty((batch * tokens, 768), dtype=np.float32)
     for i in range(batch):
         blk = qkv[i * tokens:(i + 1) * tokens]
         ref[i * tokens:(i + 1) * tokens] = oracle.attention_core(
             np.ascontiguousarray(blk[:, :768]), np.ascontiguousarray(blk[:, 768:1536]), np.ascontiguousarray(blk[:, 1536:]))
-    # P is rounded to the operand type before P.V and the output once more
-    _close(got, ref, 4 * OUT_RTOL[prec], 6 * OUT_RTOL[prec], f"attention batch={batch} tokens={tokens}")
+    # P is rounded to bf16 before P.V (both precisions) and the output once more to the operand type
+    _close(got, ref, 4 * OUT_RTOL[0], 6 * OUT_RTOL[0], f"attention batch={batch} tokens={tokens}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_attention_dominant_late_key(vit, oracle, prec):
+    """A key far down the row whose score exceeds everything in the first 32 columns by > 2^60 in the
+    softmax's exponent: the single-pass kernel must take its exact power-of-two repair path."""
+    batch, tokens = 2, 197
+    qkv = _rand((batch * tokens, 2304), 77)
+    qkv[:, :768] *= 4.0
+    qkv[150::tokens, 768:1536] = 6.0 * qkv[3::tokens, :768]   # key 150 of each image is aligned with query 3
+    qkv = _round_qkv(qkv, prec)
+    got = vit.op_attention(qkv, batch, tokens, precision=prec)
+    ref = np.empty((batch * tokens, 768), dtype=np.float32)
+    for i in range(batch):
+        blk = qkv[i * tokens:(i + 1) * tokens]
+        ref[i * tokens:(i + 1) * tokens] = oracle.attention_core(
+            np.ascontiguousarray(blk[:, :768]), np.ascontiguousarray(blk[:, 768:1536]), np.ascontiguousarray(blk[:, 1536:]))
+    assert np.isfinite(got).all()
+    _close(got, ref, 4 * OUT_RTOL[0], 6 * OUT_RTOL[0], "attention with a dominant late key")
 
 
 @pytest.mark.parametrize("prec", PRECS)

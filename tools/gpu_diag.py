@@ -71,10 +71,21 @@ def case_layernorm(rows, prec):
     stats(f"layernorm rows={rows} prec={prec}", V.op_layernorm(x, w, b, precision=prec), O.layer_norm(x, w, b))
 
 
-def case_attention(batch, tokens, prec):
+def round_qkv(qkv, prec):
+    from conftest import round_operand
+    out = round_operand(qkv, prec)
+    out[:, 1536:] = round_operand(qkv[:, 1536:], 0)
+    return out
+
+
+def case_attention(batch, tokens, prec, peaky=False):
     import vit_b200 as V, oracle_py as O
     from conftest import round_operand
-    qkv = round_operand(rand((batch * tokens, 2304), 14 + tokens), prec)
+    qkv = round_qkv(rand((batch * tokens, 2304), 14 + tokens), prec)
+    if peaky:  # one late key dominates: exercises the exact power-of-two repair of the single-pass softmax
+        qkv[:, :768] *= 4.0
+        qkv[150::tokens, 768:1536] = 6.0 * qkv[3::tokens, :768]
+        qkv = round_qkv(qkv, prec)
     got = V.op_attention(qkv, batch, tokens, precision=prec)
     ref = np.empty((batch * tokens, 768), dtype=np.float32)
     for i in range(batch):
@@ -148,6 +159,8 @@ CASES = {
     "attention_197_fp16": lambda: case_attention(2, 197, 1),
     "attention_256": lambda: case_attention(1, 256, 0),
     "attention_many": lambda: case_attention(40, 197, 0),
+    "attention_peaky": lambda: case_attention(2, 197, 0, True),
+    "attention_peaky_fp16": lambda: case_attention(2, 197, 1, True),
     "attention_many_small": lambda: case_attention(70, 100, 0),
     "embed": lambda: case_embed(0),
     "head": case_head,

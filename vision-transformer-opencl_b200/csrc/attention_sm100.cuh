@@ -94,7 +94,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
             mbar_wait(bar_load, 0);
             tc_fence_after();
             const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
-            const uint32_t idesc_o = make_idesc<T>(128, ATTN_DH, 0, 1);
+            const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
             const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
             for (int t = 0; t < nqt; ++t) {
 #pragma unroll
@@ -153,7 +153,7 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
                     e0 = (c0 < p.tokens) ? e0 : 0.f;
                     e1 = (c0 + 1 < p.tokens) ? e1 : 0.f;
                     sum += e0 + e1;
-                    packed[j] = pack2<T>(e0, e1);
+                    packed[j] = pack2<__nv_bfloat16>(e0, e1);
                 }
                 // keys [ch*16, ch*16+16) = 16B chunks 2ch, 2ch+1 of the row; K-block = chunk / 8
                 const int c8 = ch * 2;
@@ -297,58 +297,92 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
         }
     } else if (warp == 9) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp runs the (warp-uniform) state machine so that descriptors and barrier
+        // addresses live in uniform registers; one elected lane issues the tcgen05 instructions.
+        {
             const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
-            const uint32_t idesc_o = make_idesc<T>(128, ATTN_DH, 0, 1);
+            const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
             const int ksteps = p.kpad / 16;
+            auto ready = [&](uint64_t* bar, uint32_t parity) {  // non-blocking, warp-uniform
+                return __shfl_sync(0xffffffffu, mbar_test_wait(bar, parity) ? 1 : 0, 0) != 0;
+            };
             auto issue_s = [&](int t, int stage) {  // S_t = Q_t K^T of the item staged in `stage`
-                const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
-                const uint32_t k_addr = q_addr + 2 * ATTN_Q_TILE_BYTES;
+                if (elect_one()) {
+                    const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t k_addr = q_addr + 2 * ATTN_Q_TILE_BYTES;
 #pragma unroll
-                for (int k = 0; k < ATTN_DH / 16; ++k)
-                    umma_f16(tmem_base + plan.s_col(t), desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
-                             desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
-                umma_commit(&s_full[t]);
+                    for (int k = 0; k < ATTN_DH / 16; ++k)
+                        umma_f16(tmem_base + plan.s_col(t), desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
+                                 desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
+                    umma_commit(&s_full[t]);
+                }
+                __syncwarp();
             };
             auto issue_pv = [&](int t, int stage) {  // O_t = P_t V, P_t read from TMEM
-                const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * ATTN_Q_TILE_BYTES + kv_bytes;
-                for (int ks = 0; ks < ksteps; ++ks)
-                    umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8, desc_mnmajor_sw128(v_addr, ks),
-                                idesc_o, ks != 0);
-                umma_commit(&o_full[t]);
+                if (elect_one()) {
+                    const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * ATTN_Q_TILE_BYTES + kv_bytes;
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8,
+                                    desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
+                    umma_commit(&o_full[t]);
+                }
+                __syncwarp();
             };
-            // Issue order per item i:  PV_0(i), S_0(i+1), PV_1(i), S_1(i+1).  O_0 lives outside the S
-            // regions (spare columns), so S_0 of the next item does not wait for the output drain of
-            // this one; the tensor pipe executes in issue order, which protects P_0(i) from S_0(i+1).
-            int it = 0;
-            if (blockIdx.x < n_items) {
+            // Event-driven issue: each query tile is a small state machine
+            //     need P_t(i)  -> issue PV_t(i)            [t = 0 with spare columns: also O_0(i-1) drained]
+            //     need K(i+1)  -> issue S_t(i+1)           [O_t inside the S region: also O_t(i) drained]
+            // polled round robin, so the two softmax warpgroups run out of phase instead of being
+            // re-synchronised by a fixed issue order, and the tensor pipe serves whichever is ready.
+            // The tensor pipe executes in issue order, which protects P_t(i) from S_t(i+1).
+            const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+            if (my_items > 0) {
                 mbar_wait(&kv_full[0], 0);
                 tc_fence_after();
                 for (int t = 0; t < nqt; ++t) issue_s(t, 0);
             }
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int s = it & 1;
-                const bool has_next = item + static_cast<int>(gridDim.x) < n_items;
-                mbar_wait(&p_full[0], it & 1);
-                if (plan.spare) mbar_wait(&o_free[0], (it & 1) ^ 1);  // O_0 of the previous item drained
-                tc_fence_after();
-                issue_pv(0, s);
-                if (has_next) {
-                    mbar_wait(&kv_full[s ^ 1], ((it + 1) >> 1) & 1);
-                    if (!plan.spare) mbar_wait(&o_free[0], it & 1);  // O_0 shares the S_0 region
-                    tc_fence_after();
-                    issue_s(0, s ^ 1);
+            int it_t[2] = {0, 0};       // item each tile is working on
+            int phase_t[2] = {0, 0};    // 0: waiting for P (issue PV), 1: waiting to issue S of the next item
+            int pv_issued[2] = {0, 0};  // number of items whose PV_t has been issued
+            int stage_committed = 0;    // items whose smem stage has been handed back to the producer
+            int active = (my_items > 0) ? nqt : 0;
+            uint32_t spins = 0;
+            uint64_t t_start = 0;
+            while (active > 0) {
+                if ((++spins & 0xfff) == 0) {  // watchdog: a protocol bug must trap, not hang the GPU
+                    const uint64_t now = global_timer_ns();
+                    if (t_start == 0) t_start = now;
+                    else if (now - t_start > VIT_WATCHDOG_NS) { atomicExch(&g_watchdog_flag, 2u); __trap(); }
                 }
-                if (nqt > 1) {
-                    mbar_wait(&p_full[1], it & 1);
-                    tc_fence_after();
-                    issue_pv(1, s);
-                }
-                umma_commit(&stage_free[s]);
-                if (has_next && nqt > 1) {
-                    mbar_wait(&o_free[1], it & 1);  // O_1 (inside the S_1 region) of this item drained
-                    tc_fence_after();
-                    issue_s(1, s ^ 1);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (t >= nqt || it_t[t] >= my_items) continue;
+                    const int it = it_t[t];
+                    if (phase_t[t] == 0) {
+                        if (!ready(&p_full[t], it & 1)) continue;
+                        if (t == 0 && plan.spare && !ready(&o_free[0], (it & 1) ^ 1)) continue;
+                        tc_fence_after();
+                        issue_pv(t, it & 1);
+                        pv_issued[t] = it + 1;
+                        // both tiles' PV of item `stage_committed` issued: its Q/K/V stage can be refilled
+                        while (stage_committed < pv_issued[0] && (nqt == 1 || stage_committed < pv_issued[1])) {
+                            if (elect_one()) umma_commit(&stage_free[stage_committed & 1]);
+                            __syncwarp();
+                            ++stage_committed;
+                        }
+                        if (it + 1 >= my_items) {
+                            it_t[t] = my_items;
+                            --active;
+                        } else {
+                            phase_t[t] = 1;
+                        }
+                    } else {
+                        if (!ready(&kv_full[(it + 1) & 1], ((it + 1) >> 1) & 1)) continue;
+                        if (!(t == 0 && plan.spare) && !ready(&o_free[t], it & 1)) continue;
+                        tc_fence_after();
+                        issue_s(t, (it + 1) & 1);
+                        it_t[t] = it + 1;
+                        phase_t[t] = 0;
+                    }
                 }
             }
         }
@@ -371,53 +405,72 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
             mbar_wait(&s_full[t], it & 1);
             tc_fence_after();
             if (warp_active) {
-                // Both passes walk the S row in steps of 32 columns: two x16 TMEM loads per round
-                // trip, the next step's loads in flight while the current one is processed.
+                // ONE pass over the S row (TMEM reads, 64 B/clk/SM, are this kernel's scarcest resource).
+                // Softmax is shift invariant, so the exponent offset need not be the row maximum (which
+                // would cost a first full pass): it starts as the maximum of the first 32 scores and is
+                // raised lazily.  Before the exponentials of each 32-column step the step maximum is
+                // compared with the offset; only if it exceeds it by more than 2^kLazy is everything
+                // written so far (P in TMEM, the row sum) rescaled by an exact integer power of two and
+                // the offset moved -- the online-softmax recurrence with the rescale made rare.  P is
+                // bf16 (fp32 exponent range), so values up to 2^kLazy are harmless, and no exponential
+                // is ever evaluated above that bound, whatever the scores are.
+                // Two x16 TMEM loads per round trip, the next step's loads in flight while the current
+                // one is processed.  P columns [16 st, 16 st + 16) are written in place and never overlap
+                // S columns not yet read.
+                constexpr float kLazy = 24.f;
                 const int nsteps = (nch + 1) >> 1;
                 uint32_t ra[32], rb[32];
                 auto load_step = [&](uint32_t* buf, int st) {
                     tmem_ld_x16p(taddr + st * 32, buf);
                     if (2 * st + 1 < nch) tmem_ld_x16p(taddr + st * 32 + 16, buf + 16);
                 };
-                // pass 1: row maximum over the valid keys
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
-                auto max_step = [&](const uint32_t* v, int st) {
+                float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
+                float moff = 0.f;                      // -(offset) * scale * log2(e)
+                auto exp_step = [&](const uint32_t* v, int st) {
                     const int base = st * 32;
-                    if (base + 32 <= p.tokens) {
+                    const bool full = base + 32 <= p.tokens;
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+                        for (int j = 0; j < 16; ++j)
+                            m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (base + j < p.tokens) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+                            if (base + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
                     }
-                };
-                load_step(ra, 0);
-                for (int st = 0; st < nsteps; st += 2) {
-                    tmem_ld_wait();
-                    if (st + 1 < nsteps) load_step(rb, st + 1);
-                    max_step(ra, st);
-                    if (st + 1 < nsteps) {
-                        tmem_ld_wait();
-                        if (st + 2 < nsteps) load_step(ra, st + 2);
-                        max_step(rb, st + 1);
+                    const float smax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    if (st == 0) {
+                        moff = -smax * p.scale_log2;
+                    } else {
+                        const float over = fmaf(smax, p.scale_log2, moff);  // log2 of this step's largest p
+                        if (__any_sync(0xffffffffu, over > kLazy)) {
+                            // exact repair: 2^-sh on P[0, 16 st) and on the sum, offset raised by sh
+                            const int sh = over > kLazy ? static_cast<int>(ceilf(fminf(over, 1.0e6f))) : 0;
+                            const float f = sh > 126 ? 0.f : __int_as_float((127 - sh) << 23);
+                            tmem_st_wait();
+                            for (int c8 = 0; c8 < 2 * st; ++c8) {
+                                uint32_t w[8];
+                                tmem_ld_x8p(taddr + c8 * 8, w);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    w[j] = pack2<__nv_bfloat16>(__uint_as_float(w[j] << 16) * f, __uint_as_float(w[j] & 0xffff0000u) * f);
+                                tmem_st_x8p(taddr + c8 * 8, w);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sum4[j] *= f;
+                            moff -= static_cast<float>(sh);
+                        }
                     }
-                }
-                // pass 2: p = exp2((s - max) * scale*log2e), row sum, P written back in place
-                // (P columns [16 st, 16 st + 16) never overlap S columns not yet read)
-                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-                const float moff = -mx * p.scale_log2;
-                float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-                auto exp_step = [&](const uint32_t* v, int st) {
-                    const int base = st * 32;
                     uint32_t packed[16];
-                    if (base + 32 <= p.tokens) {
+                    if (full) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
                             const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
                             sum4[j & 3] += e0 + e1;
-                            packed[j] = pack2<T>(e0, e1);
+                            packed[j] = pack2<__nv_bfloat16>(e0, e1);
                         }
                     } else {
 #pragma unroll
@@ -427,7 +480,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                             if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
                             if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
                             sum4[j & 3] += e0 + e1;
-                            packed[j] = pack2<T>(e0, e1);
+                            packed[j] = pack2<__nv_bfloat16>(e0, e1);
                         }
                     }
                     tmem_st_x8p(taddr + st * 16, packed);
@@ -444,7 +497,8 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                         exp_step(rb, st + 1);
                     }
                 }
-                inv_sum = fast_rcp((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+                const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+                inv_sum = fast_rcp(sum);
                 tmem_st_wait();
                 tc_fence_before();
             }

@@ -134,7 +134,8 @@ template <typename T, int EPI>
 int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
                          int sm_count, cudaStream_t st) {
     using L = GemmStagedSmem<kStagedStages, kStagedSlots>;
-    auto kern = gemm_sm100_staged_kernel<T, kStagedStages, kStagedSlots, EPI>;
+    constexpr int kEpiWarps = 8;  // 16 was measured no faster for the GELU epilogue (issue bound, not latency bound)
+    auto kern = gemm_sm100_staged_kernel<T, kStagedStages, kStagedSlots, EPI, kEpiWarps>;
     static int configured_dev_mask = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -146,7 +147,7 @@ int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
         return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64)", p.M, p.N, p.K);
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int grid = 2 * std::min(tiles, sm_count / 2);
-    kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, tout, p);
+    kern<<<grid, (GEMM_NON_EPI_WARPS + kEpiWarps) * 32, L::DYN_BYTES, st>>>(ta, tb, tout, p);
     return check_launch("gemm_staged");
 }
 // tout: store map of the output (for the residual epilogue also the load map of the residual, in place)
@@ -499,7 +500,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         }
         {
             ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
-            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0};
+            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 2 * kDim};  // V block stored as bf16
             if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
         }
@@ -614,6 +615,7 @@ int vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d
     if (gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
     if (n <= 0 || n > e.max_batch) return set_err(VIT_E_ARG, "n=%d outside (0, max_batch=%d]", n, e.max_batch);
     if (e.tokens > 256) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    if (gemm_impl() != 2 && e.prec != VIT_PREC_BF16) return set_err(VIT_E_ARG, "VIT_GEMM_IMPL=1 (A/B test kernels) supports bf16 only");
     DeviceCtx& c = e.ctx[gpu_slot];
     CU_TRY(cudaSetDevice(c.device));
     return enqueue_forward(c, e, d_images, n, d_logits);
@@ -923,7 +925,16 @@ int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, i
     const size_t rows = (size_t)batch * tokens;
     const int kpad = (tokens + 15) / 16 * 16;
     void *dqkv, *dout;
-    VIT_TRY(s.upload_operand(&dqkv, qkv, rows * 3 * kDim, precision));
+    {   // Q, K in the operand precision; V in bf16 (as the in_proj epilogue stores it)
+        float* tmp = nullptr;
+        VIT_TRY(s.upload_f32(&tmp, qkv, rows * 3 * kDim));
+        VIT_TRY(s.alloc(&dqkv, rows * 3 * kDim * 2, true));
+        const int grid = static_cast<int>(std::min<size_t>((rows * 3 * kDim + 255) / 256, 148 * 16));
+        if (precision == VIT_PREC_FP16) convert_qkv_from_f32_kernel<__half><<<grid, 256>>>(tmp, static_cast<uint16_t*>(dqkv), rows * 3 * kDim);
+        else convert_qkv_from_f32_kernel<__nv_bfloat16><<<grid, 256>>>(tmp, static_cast<uint16_t*>(dqkv), rows * 3 * kDim);
+        VIT_TRY(check_launch("convert_qkv"));
+        CU_TRY(cudaDeviceSynchronize());
+    }
     VIT_TRY(s.alloc(&dout, rows * kDim * 2, true));
     CUtensorMap tq, tkv;
     VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, 256));

@@ -32,6 +32,8 @@ struct GemmParams {
     const float* residual;  // EPI_BIAS_RESIDUAL: [M][N] fp32; EPI_PATCH_EMBED: pos_embedding [tokens][N]
     int patches;            // EPI_PATCH_EMBED: patches per image (196 / 576)
     int tokens;             // EPI_PATCH_EMBED: tokens per image  (197 / 577)
+    int bf16_from_col;      // staged EPI_BIAS: output columns >= this are stored as bf16 whatever T is
+                            // (the V block of in_proj: attention keeps P and V in bf16); <= 0: never
 };
 
 constexpr int GEMM_BM = 128;
@@ -464,10 +466,13 @@ struct GemmStagedSmem {
     static constexpr int DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16;  // base must be 1024-aligned (checked)
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
-template <typename T, int STAGES, int SLOTS, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+// EPI_WARPS: 8 (two warps per TMEM lane quarter) or 16 (four per quarter; for the GELU epilogue, whose
+// ~13 dependent FP32 ops + 2 MUFU per element are latency bound with only two warps per scheduler).
+template <typename T, int STAGES, int SLOTS, int EPI, int EPI_WARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GEMM_NON_EPI_WARPS + EPI_WARPS) * 32, 1)
 gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
     using L = GemmStagedSmem<STAGES, SLOTS>;
@@ -476,7 +481,12 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     constexpr int BN = 256;
     constexpr int CHUNK_COLS = kResidual ? 32 : 64;      // one 128-byte row segment per chunk
     constexpr int NCHUNK = BN / CHUNK_COLS;
-    constexpr int COLS_PER_WARP = CHUNK_COLS / 2;        // two warps share a TMEM lane quarter
+    constexpr int PARTS = EPI_WARPS / 4;                 // warps sharing a TMEM lane quarter split the chunk's columns
+    constexpr int COLS_PER_WARP = CHUNK_COLS / PARTS;
+    constexpr int PIECES = COLS_PER_WARP * (kResidual ? 4 : 2) / 16;  // 16-byte pieces of the 128-byte row per thread
+    constexpr int EPI_THREADS = EPI_WARPS * 32;
+    static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "epilogue warps");
+    static_assert(!(kResidual && EPI_WARPS == 16), "residual epilogue uses 8 warps");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
@@ -488,6 +498,10 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* slot_free = res_full + SLOTS;  // [SLOTS] the store out of the slot has drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_free + SLOTS);
 
+    // Warp roles.  The epilogue warps come FIRST: the SM's warp scheduler favours higher warp ids
+    // among eligible warps, and the single-thread TMA producer / MMA issuer must never be starved
+    // by eight warps of GELU arithmetic (measured: mlp_0 tensor-pipe activity 64 % -> see profiles/).
+    constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_TMEM = EPI_WARPS + 2, W_LOADER = EPI_WARPS + 3;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -499,19 +513,19 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_kb = p.K / GEMM_BK;
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzle atoms need 1 KB alignment
-    if (warp == 0 && lane == 0) {
+    if (warp == W_PRODUCER && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         tma_prefetch_desc(&tmap_out);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 16);  // one arrival per epilogue warp of both CTAs (used in the leader)
+            mbar_init(&tempty_bar[s], 2 * EPI_WARPS);  // one arrival per epilogue warp of both CTAs (used in the leader)
         }
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(&res_full[s], 1);
@@ -519,34 +533,37 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+    if (warp == W_TMEM) tmem_alloc_pair<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == W_PRODUCER) {
         // ------------------------------------------------------------ operand producer (both CTAs)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m0 = (tile / tiles_n) * 256 + rank * 128;
-                const int n0 = (tile % tiles_n) * BN + rank * 128;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // The whole warp walks the loop (warp-uniform control flow keeps addresses and barrier
+        // operands in uniform registers); one elected lane issues.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m0 = (tile / tiles_n) * 256 + rank * 128;
+            const int n0 = (tile % tiles_n) * BN + rank * 128;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
                     tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
                     tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
             constexpr uint32_t idesc = make_idesc<T>(256, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -559,20 +576,24 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + L::A_BYTES;
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                        const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
-                                      (kb | k) != 0);
-                    umma_commit_pair(&empty_bar[stage], 0x3);
+                        for (int k = 0; k < GEMM_BK / 16; ++k)
+                            umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
+                                          (kb | k) != 0);
+                        umma_commit_pair(&empty_bar[stage], 0x3);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_pair(&tfull_bar[acc], 0x3);
+                if (elect_one()) umma_commit_pair(&tfull_bar[acc], 0x3);
+                __syncwarp();
                 if ((acc ^= 1) == 0) acc_phase ^= 1;
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == W_LOADER) {
         // ------------------------------------------------------------ residual loader (EPI_BIAS_RESIDUAL)
         if (kResidual && lane == 0) {
             uint32_t k = 0;
@@ -587,12 +608,12 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
         }
-    } else if (warp >= GEMM_NON_EPI_WARPS) {
+    } else if (warp < EPI_WARPS) {
         // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-        const int ew = warp - GEMM_NON_EPI_WARPS;
+        const int ew = warp;
         const int quarter = warp & 3;
-        const int half = ew >> 2;                 // which half of the chunk's columns
-        const int etid = threadIdx.x - GEMM_NON_EPI_WARPS * 32;
+        const int half = ew >> 2;                 // which part of the chunk's columns
+        const int etid = threadIdx.x;
         const bool storer = etid == 0;
         const int row = quarter * 32 + lane;      // row inside the CTA's 128-row block
         const uint32_t row_off = row * 128, sw = row & 7;
@@ -605,25 +626,34 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int m0 = (tile / tiles_n) * 256 + rank * 128;
             const int n0 = (tile % tiles_n) * BN;
             float* sb = s_bias + tile_par * 256;
-            sb[etid] = p.bias[n0 + etid];         // visible after the first chunk barrier below... used before: sync now
-            epi_bar_sync();
+            if (etid < 256) sb[etid] = p.bias[n0 + etid];
+            epi_bar_sync<EPI_THREADS>();
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
-#pragma unroll 1
+            // Early accumulator release: the thread's whole share of the accumulator stage (NCHUNK x
+            // COLS_PER_WARP = 128 fp32) is pulled into registers first and the TMEM stage is handed back
+            // to the MMA issuer at once, so the next-but-one tile's MMAs never wait for this tile's
+            // GELU arithmetic or stores -- with only two accumulator stages, releasing the stage at the
+            // end of the epilogue couples the MMA and epilogue periods (measured: MMA issuer spinning
+            // on the stage barrier while the epilogue warps wait for the next accumulator).
+            uint32_t racc[NCHUNK][COLS_PER_WARP];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                tmem_ld_x16p(taddr + c * CHUNK_COLS, racc[c]);
+                if constexpr (COLS_PER_WARP == 32) tmem_ld_x16p(taddr + c * CHUNK_COLS + 16, racc[c] + 16);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+#pragma unroll
             for (int c = 0; c < NCHUNK; ++c, ++k) {
                 const uint32_t slot = k % SLOTS;
                 uint8_t* srow = smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES + row_off;
                 const float* bcol = sb + c * CHUNK_COLS + half * COLS_PER_WARP;
+                const uint32_t* r = racc[c];
                 if constexpr (kResidual) {
-                    uint32_t r[16];
-                    tmem_ld_x16p(taddr + c * CHUNK_COLS, r);
-                    tmem_ld_wait();
-                    if (c == NCHUNK - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
-                    }
                     mbar_wait(&res_full[slot], (k / SLOTS) & 1);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -636,35 +666,28 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         *q = v;
                     }
                 } else {
-                    uint32_t r[32];
-                    tmem_ld_x32(taddr + c * CHUNK_COLS, r);
-                    tmem_ld_wait();
-                    if (c == NCHUNK - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
-                    }
-                    uint32_t packed[16];
+                    uint32_t packed[COLS_PER_WARP / 2];
+                    const bool as_bf16 = EPI == EPI_BIAS && p.bf16_from_col > 0 && n0 + c * CHUNK_COLS >= p.bf16_from_col;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < COLS_PER_WARP / 2; ++j) {
                         float v0 = __uint_as_float(r[2 * j]) + bcol[2 * j];
                         float v1 = __uint_as_float(r[2 * j + 1]) + bcol[2 * j + 1];
                         if constexpr (EPI == EPI_BIAS_GELU) {
                             v0 = gelu_erf(v0);
                             v1 = gelu_erf(v1);
                         }
-                        packed[j] = pack2<T>(v0, v1);
+                        packed[j] = as_bf16 ? pack2<__nv_bfloat16>(v0, v1) : pack2<T>(v0, v1);
                     }
                     // the slot's previous store (chunk k - SLOTS) has drained: the storer checked before
                     // the barrier that ended chunk k - 1
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ sw) << 4)) =
+                    for (int j = 0; j < PIECES; ++j)
+                        *reinterpret_cast<uint4*>(srow + (((half * PIECES + j) ^ sw) << 4)) =
                             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
                 fence_proxy_async_smem();
                 if (!kResidual && storer) tma_store_wait_read<SLOTS - 2>();  // frees the slot of chunk k + 1
-                epi_bar_sync();
+                epi_bar_sync<EPI_THREADS>();
                 if (storer) {
                     tma_store_2d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, m0);
                     tma_store_commit();
@@ -684,7 +707,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 2) {
+    if (warp == W_TMEM) {
         tc_fence_after();
         tmem_dealloc_pair<512>(tmem_base);
     }

@@ -173,6 +173,21 @@ __global__ void convert_from_f32_kernel(const float* __restrict__ src, T* __rest
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
         dst[i] = from_float<T>(src[i]);
 }
+// packed QKV activation [rows][2304] for the attention operator test: Q, K columns in T, V columns
+// (>= 1536) in bf16 -- the layout the in_proj epilogue produces
+template <typename T>
+__global__ void convert_qkv_from_f32_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        if (i % 2304 >= 1536) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(src[i]);
+            dst[i] = *reinterpret_cast<const uint16_t*>(&v);
+        } else {
+            const T v = from_float<T>(src[i]);
+            dst[i] = *reinterpret_cast<const uint16_t*>(&v);
+        }
+    }
+}
 template <typename T>
 __global__ void convert_to_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
