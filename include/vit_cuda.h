@@ -169,6 +169,12 @@ int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float*
  * MHA_gemm_kernel + softmax_reduction_kernel loop, ViT_opencl.c:546-564. */
 int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision);
 
+/* Debug: runs the attention kernel as above and returns SM-clock timestamps of the pipeline events
+ * of CTA 0 (11 warps x 16 items x 8 events of uint64, layout in csrc/attention_sm100.cuh) instead of
+ * the result.  Used by tools/attn_trace.py to read the kernel's timeline; not part of the hot path. */
+int vit_cuda_debug_attention_trace(const float* qkv, int batch, int tokens, int precision,
+                                   unsigned long long* trace, int trace_len);
+
 /* Patch embedding for `batch` images [batch][3][S][S]: conv_proj + class token + position
  * embedding -> out [batch*tokens][768] fp32.  Replaces Conv2d/flatten_transpose/
  * class_token/pos_emb, ViT_seq.c:25-101 / Conv2d_Kernel, kernel.cl:120-175. */

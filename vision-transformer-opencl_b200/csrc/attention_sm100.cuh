@@ -1,19 +1,11 @@
 // attention_sm100.cuh -- fused multi-head softmax(Q K^T / sqrt(64)) V for sm_100a.
 //
 // Replaces the reference's per-head loop (ViT_seq.c:156-215; OpenCL: MHA_gemm_kernel +
-// softmax_reduction_kernel + MHA_gemm_kernel per head, ViT_opencl.c:546-564).  One CTA per
-// (image, head).  The [tokens x tokens] score matrix lives only in TMEM / registers / smem.
-//
-//   warp 8 (1 thread)  TMA: Q (2 x 128 rows), K, V tiles of the head straight out of the packed
-//                      QKV activation [rows][2304]; tcgen05.mma S_t = Q_t K^T (K-major x K-major)
-//                      and O_t = P_t V (V used as an MN-major B operand, no transpose pass)
-//   warps 0-3 / 4-7    softmax warpgroup for query tile 0 / 1: one thread per query row reads its
-//                      S row from TMEM (two passes: max, then exp2 + sum), writes P (operand
-//                      precision) into 128B-swizzled smem, later scales O by 1/sum and stores it
-//
-// Keys are padded to a multiple of 16 (197 -> 208); padded columns are masked to -inf before
-// the max, padded/foreign V rows meet P == 0.  This variant keeps the whole key range in one
-// block, so tokens <= 256.
+// softmax_reduction_kernel + MHA_gemm_kernel per head, ViT_opencl.c:546-564).  The [tokens x tokens]
+// score matrix lives only in TMEM and registers.  Keys are padded to a multiple of 16 (197 -> 208);
+// padded columns get P == 0, so the foreign / zero-filled V rows behind them never contribute.
+// The whole key range of an image is one block, so tokens <= 256 here; longer sequences (384^2:
+// 577 tokens) use the key-blocked kernel below.
 #pragma once
 
 #include "ptx.cuh"
@@ -26,182 +18,27 @@ struct AttnParams {
     int kpad;          // tokens rounded up to 16
     void* out;         // [batch*tokens][768], operand precision
     float scale_log2;  // (1/sqrt(64)) * log2(e)
+    unsigned long long* trace;  // optional (debug): SM-clock timestamps of CTA 0's pipeline events, see ATTN_TRACE
 };
 
-constexpr int ATTN_THREADS = 288;
+// Pipeline trace of CTA 0 (vit_cuda_debug_attention_trace): trace[(warp * ITEMS + item) * EVENTS + event] = clock64().
+// softmax warps 0-7: 0 item start, 1 S ready, 2 P written, 3 O ready, 4 O in registers, 5 O stored
+// warp 8 (producer): 0 stage free / TMA issued        warps 9, 10 (MMA issuers): 0 S_t issued, 1 PV_t issued
+constexpr int ATTN_TRACE_ITEMS = 16, ATTN_TRACE_EVENTS = 8, ATTN_TRACE_WARPS = 11;
+#define ATTN_TRACE(warp_, it_, ev_)                                                                          \
+    do {                                                                                                     \
+        if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) < ATTN_TRACE_ITEMS)    \
+            p.trace[((warp_) * ATTN_TRACE_ITEMS + (it_)) * ATTN_TRACE_EVENTS + (ev_)] = clock64();           \
+    } while (0)
+
 constexpr int ATTN_DIM = 768;
 constexpr int ATTN_DH = 64;
 constexpr int ATTN_Q_TILE_BYTES = 128 * 128;  // 128 rows x 64 x 2 B
 
 __host__ __device__ inline int attn_kv_bytes(int kpad) { return kpad * 128; }
-__host__ __device__ inline int attn_p_tile_bytes(int kpad) { return ((kpad + 63) / 64) * ATTN_Q_TILE_BYTES; }
-__host__ inline int attn_smem_bytes(int kpad) {
-    return 2 * ATTN_Q_TILE_BYTES + 2 * attn_kv_bytes(kpad) + 2 * attn_p_tile_bytes(kpad) + 128 + 1024;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
-attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                       const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int kv_bytes = attn_kv_bytes(p.kpad);
-    const int p_bytes = attn_p_tile_bytes(p.kpad);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + 2 * ATTN_Q_TILE_BYTES;
-    uint8_t* sV = sK + kv_bytes;
-    uint8_t* sP = sV + kv_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * p_bytes);
-    uint64_t* bar_load = bars;       // Q,K,V landed
-    uint64_t* bar_s = bars + 1;      // [2] S_t ready in TMEM
-    uint64_t* bar_p = bars + 3;      // [2] P_t written (128 arrivals)
-    uint64_t* bar_o = bars + 5;      // [2] O_t ready in TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int img = blockIdx.x / 12;
-    const int head = blockIdx.x - img * 12;
-    const int row0 = img * p.tokens;  // first activation row of this image
-    const int nqt = p.tokens > 128 ? 2 : 1;
-
-    if (warp == 8) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmap_q);
-            tma_prefetch_desc(&tmap_kv);
-            mbar_init(bar_load, 1);
-            for (int t = 0; t < 2; ++t) {
-                mbar_init(&bar_s[t], 1);
-                mbar_init(&bar_p[t], 128);
-                mbar_init(&bar_o[t], 1);
-            }
-            fence_barrier_init();
-        }
-        __syncwarp();
-        tmem_alloc<512>(tmem_slot);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 8) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar_load, 2 * ATTN_Q_TILE_BYTES + 2 * kv_bytes);
-            tma_load_2d(sQ, &tmap_q, bar_load, head * ATTN_DH, row0);
-            tma_load_2d(sK, &tmap_kv, bar_load, ATTN_DIM + head * ATTN_DH, row0);
-            tma_load_2d(sV, &tmap_kv, bar_load, 2 * ATTN_DIM + head * ATTN_DH, row0);
-            mbar_wait(bar_load, 0);
-            tc_fence_after();
-            const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
-            const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
-            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-            for (int t = 0; t < nqt; ++t) {
-#pragma unroll
-                for (int k = 0; k < ATTN_DH / 16; ++k)
-                    umma_f16(tmem_base + t * 256, desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
-                             desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
-                umma_commit(&bar_s[t]);
-            }
-            const int ksteps = p.kpad / 16;
-            for (int t = 0; t < nqt; ++t) {
-                mbar_wait(&bar_p[t], 0);
-                tc_fence_after();
-                for (int ks = 0; ks < ksteps; ++ks)
-                    umma_f16(tmem_base + t * 256,
-                             desc_kmajor_sw128(p_addr + t * p_bytes + (ks >> 2) * ATTN_Q_TILE_BYTES, ks & 3),
-                             desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
-                umma_commit(&bar_o[t]);
-            }
-        }
-    } else {
-        const int t = warp >> 2;        // query tile of this warpgroup
-        const int quarter = warp & 3;   // TMEM lane quarter
-        const int qrow = t * 128 + quarter * 32 + lane;  // query index inside the image
-        const bool warp_active = t < nqt && (t * 128 + quarter * 32) < p.tokens;
-        float inv_sum = 0.f;
-        if (warp_active) {
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-            mbar_wait(&bar_s[t], 0);
-            tc_fence_after();
-            const int nch = p.kpad / 16;
-            float mx = -INFINITY;
-            for (int ch = 0; ch < nch; ++ch) {
-                uint32_t r[16];
-                tmem_ld_x16(taddr + ch * 16, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float v = (ch * 16 + j < p.tokens) ? __uint_as_float(r[j]) : -INFINITY;
-                    mx = fmaxf(mx, v);
-                }
-            }
-            const float moff = -mx * p.scale_log2;
-            float sum = 0.f;
-            uint8_t* prow = sP + t * p_bytes + (quarter * 32 + lane) * 128;
-            const int sw = lane & 7;  // (row % 8) of the 128B swizzle; row = quarter*32+lane
-            for (int ch = 0; ch < nch; ++ch) {
-                uint32_t r[16];
-                tmem_ld_x16(taddr + ch * 16, r);
-                tmem_ld_wait();
-                uint32_t packed[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c0 = ch * 16 + 2 * j;
-                    float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * j]), p.scale_log2, moff));
-                    float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2, moff));
-                    e0 = (c0 < p.tokens) ? e0 : 0.f;
-                    e1 = (c0 + 1 < p.tokens) ? e1 : 0.f;
-                    sum += e0 + e1;
-                    packed[j] = pack2<__nv_bfloat16>(e0, e1);
-                }
-                // keys [ch*16, ch*16+16) = 16B chunks 2ch, 2ch+1 of the row; K-block = chunk / 8
-                const int c8 = ch * 2;
-                uint8_t* blk = prow + (c8 >> 3) * ATTN_Q_TILE_BYTES;
-                *reinterpret_cast<uint4*>(blk + (((c8 & 7) ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4*>(blk + ((((c8 + 1) & 7) ^ sw) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            }
-            inv_sum = 1.0f / sum;
-            fence_proxy_async_smem();
-            tc_fence_before();
-        }
-        if (t < 2) mbar_arrive(&bar_p[t]);
-        if (warp_active) {
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-            mbar_wait(&bar_o[t], 0);
-            tc_fence_after();
-            T* orow = static_cast<T*>(p.out) + static_cast<size_t>(row0 + qrow) * ATTN_DIM + head * ATTN_DH;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld_x32(taddr + half * 32, r);
-                tmem_ld_wait();
-                if (qrow < p.tokens) {
-                    uint4* dst = reinterpret_cast<uint4*>(orow + half * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            w[q] = pack2<T>(__uint_as_float(r[8 * j + 2 * q]) * inv_sum,
-                                            __uint_as_float(r[8 * j + 2 * q + 1]) * inv_sum);
-                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
 
 // =============================================================================================
-// Persistent, software-pipelined variant (the one the engine uses).
+// Persistent, software-pipelined kernel.
 //
 // One CTA per SM loops over (image, head) items.  Per item the two 128-row query tiles own one
 // 256-column TMEM region each:   S_t fp32 [0,kpad)  ->  P_t (operand precision, packed two per
@@ -211,9 +48,9 @@ attention_sm100_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 // of item i+1 run under the softmax of item i, and while one warpgroup is in its softmax the
 // tensor core works for the other one.
 //
-//   warp 8  TMA producer          warp 9  MMA issuer + TMEM owner
+//   warp 8  TMA producer          warps 9, 10  MMA issuers for query tile 0 / 1 (warp 9 owns TMEM)
 //   warps 0-3 / 4-7  softmax + output warpgroups for query tile 0 / 1
-constexpr int ATTN2_THREADS = 320;
+constexpr int ATTN2_THREADS = 352;
 // TMEM column plan (512 columns).  With kpad <= 224 (ViT-B/16 at 224^2: kpad = 208):
 //   S_0/P_0 [0,kpad)   S_1/P_1 [kpad,2 kpad)   O_1 inside its S region at +128   O_0 [2 kpad, 2 kpad+64)
 // so S_0 of the next item can be issued without waiting for O_0 to be drained.  Otherwise
@@ -232,18 +69,28 @@ __device__ __forceinline__ AttnTmemPlan attn2_tmem_plan(int kpad) {
     pl.o0 = pl.spare ? 2 * kpad : 128;
     return pl;
 }
-__host__ __device__ inline int attn2_stage_bytes(int kpad) { return 2 * ATTN_Q_TILE_BYTES + 2 * attn_kv_bytes(kpad); }
-__host__ inline int attn2_smem_bytes(int kpad) { return 2 * attn2_stage_bytes(kpad) + 256 + 1024; }
+// Shared memory: two stages of {Q, K, V} x kpad rows x 128 B (Q only needs `tokens` rows; the second
+// query tile's descriptor runs on into the K rows behind it, whose S rows nobody reads), then one
+// 128 x 128 B output staging tile per query tile.
+__host__ __device__ inline int attn2_stage_bytes(int kpad) { return 3 * attn_kv_bytes(kpad); }
+constexpr int ATTN2_OSTAGE_BYTES = 128 * 128;
+__host__ inline int attn2_smem_bytes(int kpad) { return 2 * attn2_stage_bytes(kpad) + 2 * ATTN2_OSTAGE_BYTES + 256 + 1024; }
+
+template <int NTHREADS>
+__device__ __forceinline__ void attn_tile_bar_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
+}
 
 template <typename T>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
-attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                                   const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kv_bytes = attn_kv_bytes(p.kpad);
     const int stage_bytes = attn2_stage_bytes(p.kpad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+    uint8_t* sO = smem + 2 * stage_bytes;  // [2 tiles] output staging, 128B-swizzled rows of 64 x 16-bit
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATTN2_OSTAGE_BYTES);
     uint64_t* kv_full = bars;        // [2 stages] Q,K,V of an item landed (tx)
     uint64_t* stage_free = bars + 2; // [2 stages] every MMA reading the stage has completed
     uint64_t* s_full = bars + 4;     // [2 tiles]  S_t in TMEM
@@ -259,11 +106,11 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
     const AttnTmemPlan plan = attn2_tmem_plan(p.kpad);
 
     if (warp == 8 && lane == 0) {
-        tma_prefetch_desc(&tmap_q);
-        tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_out);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&stage_free[i], 1);
+            mbar_init(&stage_free[i], nqt);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 128);
             mbar_init(&o_full[i], 1);
@@ -279,110 +126,98 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
 
     if (warp == 8) {
         // ------------------------------------------------------------ TMA producer
+        // One TMA operation keeps only a few dozen 128-byte row requests in flight, and every row of
+        // a head's Q/K/V slice lies in a different DRAM page (row pitch 4608 B): a whole item issued
+        // as three boxes took ~10 k cycles to land and set the kernel's period (profiles/r1_attention_
+        // trace.md).  So each of Q, K, V is fetched as two half-height boxes (six operations in flight),
+        // and the item after next is pulled into L2 ahead of time, where the real load then hits.
         if (lane == 0) {
+            const int half_rows = p.kpad >> 1, half_bytes = half_rows * 128;
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int s = it & 1;
                 const int img = item / 12, head = item - img * 12;
                 const int row0 = img * p.tokens;
                 uint8_t* sQ = smem + s * stage_bytes;
-                uint8_t* sK = sQ + 2 * ATTN_Q_TILE_BYTES;
+                uint8_t* sK = sQ + kv_bytes;
                 uint8_t* sV = sK + kv_bytes;
                 mbar_wait(&stage_free[s], ((it >> 1) & 1) ^ 1);
+                ATTN_TRACE(8, it, 0);
                 mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
-                tma_load_2d(sQ, &tmap_q, &kv_full[s], head * ATTN_DH, row0);
-                tma_load_2d(sK, &tmap_kv, &kv_full[s], ATTN_DIM + head * ATTN_DH, row0);
-                tma_load_2d(sV, &tmap_kv, &kv_full[s], 2 * ATTN_DIM + head * ATTN_DH, row0);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tma_load_2d(sQ + h * half_bytes, &tmap_qkv, &kv_full[s], head * ATTN_DH, row0 + h * half_rows);
+                    tma_load_2d(sK + h * half_bytes, &tmap_qkv, &kv_full[s], ATTN_DIM + head * ATTN_DH, row0 + h * half_rows);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d(sV + h * half_bytes, &tmap_qkv, &kv_full[s], 2 * ATTN_DIM + head * ATTN_DH, row0 + h * half_rows);
+                const int ahead = item + 2 * static_cast<int>(gridDim.x);
+                if (ahead < n_items) {
+                    const int img2 = ahead / 12, head2 = ahead - img2 * 12;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        tma_prefetch_l2_2d(&tmap_qkv, head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
+                        tma_prefetch_l2_2d(&tmap_qkv, ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
+                        tma_prefetch_l2_2d(&tmap_qkv, 2 * ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
+                    }
+                }
             }
         }
-    } else if (warp == 9) {
-        // ------------------------------------------------------------ MMA issuer
-        // The whole warp runs the (warp-uniform) state machine so that descriptors and barrier
-        // addresses live in uniform registers; one elected lane issues the tcgen05 instructions.
-        {
-            const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
-            const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
-            const int ksteps = p.kpad / 16;
-            auto ready = [&](uint64_t* bar, uint32_t parity) {  // non-blocking, warp-uniform
-                return __shfl_sync(0xffffffffu, mbar_test_wait(bar, parity) ? 1 : 0, 0) != 0;
-            };
-            auto issue_s = [&](int t, int stage) {  // S_t = Q_t K^T of the item staged in `stage`
-                if (elect_one()) {
-                    const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
-                    const uint32_t k_addr = q_addr + 2 * ATTN_Q_TILE_BYTES;
+    } else if (warp >= 9) {
+        // ------------------------------------------------------------ MMA issuers: warp 9 for query tile 0, warp 10 for tile 1
+        // One issuer per query tile, each a plain blocking loop  P_t(i) -> PV_t(i) -> K(i+1) -> S_t(i+1).
+        // (A single warp polling both tiles' barriers sat on the critical path of both: sharing an SM
+        // sub-partition with two softmax warps, each of its four issue actions per item cost 0.6-1.1 k
+        // cycles, profiles/r1_attention_trace.md.)  The two tiles share no TMEM columns, and the tensor
+        // pipe executes each issuer's instructions in order, which protects P_t(i) from S_t(i+1).
+        // The whole warp walks the loop so that descriptors and barrier addresses live in uniform
+        // registers; one elected lane issues.
+        const int t = warp - 9;
+        const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
+        const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
+        const int ksteps = p.kpad / 16;
+        auto issue_s = [&](int stage, int it) {  // S_t = Q_t K^T of the item staged in `stage`
+            ATTN_TRACE(warp, it, 0);
+            if (elect_one()) {
+                const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+                const uint32_t k_addr = q_addr + kv_bytes;
 #pragma unroll
-                    for (int k = 0; k < ATTN_DH / 16; ++k)
-                        umma_f16(tmem_base + plan.s_col(t), desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
-                                 desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
-                    umma_commit(&s_full[t]);
-                }
-                __syncwarp();
-            };
-            auto issue_pv = [&](int t, int stage) {  // O_t = P_t V, P_t read from TMEM
-                if (elect_one()) {
-                    const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * ATTN_Q_TILE_BYTES + kv_bytes;
-                    for (int ks = 0; ks < ksteps; ++ks)
-                        umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8,
-                                    desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
-                    umma_commit(&o_full[t]);
-                }
-                __syncwarp();
-            };
-            // Event-driven issue: each query tile is a small state machine
-            //     need P_t(i)  -> issue PV_t(i)            [t = 0 with spare columns: also O_0(i-1) drained]
-            //     need K(i+1)  -> issue S_t(i+1)           [O_t inside the S region: also O_t(i) drained]
-            // polled round robin, so the two softmax warpgroups run out of phase instead of being
-            // re-synchronised by a fixed issue order, and the tensor pipe serves whichever is ready.
-            // The tensor pipe executes in issue order, which protects P_t(i) from S_t(i+1).
-            const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-            if (my_items > 0) {
-                mbar_wait(&kv_full[0], 0);
-                tc_fence_after();
-                for (int t = 0; t < nqt; ++t) issue_s(t, 0);
+                for (int k = 0; k < ATTN_DH / 16; ++k)
+                    umma_f16(tmem_base + plan.s_col(t), desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
+                             desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
+                umma_commit(&s_full[t]);
             }
-            int it_t[2] = {0, 0};       // item each tile is working on
-            int phase_t[2] = {0, 0};    // 0: waiting for P (issue PV), 1: waiting to issue S of the next item
-            int pv_issued[2] = {0, 0};  // number of items whose PV_t has been issued
-            int stage_committed = 0;    // items whose smem stage has been handed back to the producer
-            int active = (my_items > 0) ? nqt : 0;
-            uint32_t spins = 0;
-            uint64_t t_start = 0;
-            while (active > 0) {
-                if ((++spins & 0xfff) == 0) {  // watchdog: a protocol bug must trap, not hang the GPU
-                    const uint64_t now = global_timer_ns();
-                    if (t_start == 0) t_start = now;
-                    else if (now - t_start > VIT_WATCHDOG_NS) { atomicExch(&g_watchdog_flag, 2u); __trap(); }
-                }
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (t >= nqt || it_t[t] >= my_items) continue;
-                    const int it = it_t[t];
-                    if (phase_t[t] == 0) {
-                        if (!ready(&p_full[t], it & 1)) continue;
-                        if (t == 0 && plan.spare && !ready(&o_free[0], (it & 1) ^ 1)) continue;
-                        tc_fence_after();
-                        issue_pv(t, it & 1);
-                        pv_issued[t] = it + 1;
-                        // both tiles' PV of item `stage_committed` issued: its Q/K/V stage can be refilled
-                        while (stage_committed < pv_issued[0] && (nqt == 1 || stage_committed < pv_issued[1])) {
-                            if (elect_one()) umma_commit(&stage_free[stage_committed & 1]);
-                            __syncwarp();
-                            ++stage_committed;
-                        }
-                        if (it + 1 >= my_items) {
-                            it_t[t] = my_items;
-                            --active;
-                        } else {
-                            phase_t[t] = 1;
-                        }
-                    } else {
-                        if (!ready(&kv_full[(it + 1) & 1], ((it + 1) >> 1) & 1)) continue;
-                        if (!(t == 0 && plan.spare) && !ready(&o_free[t], it & 1)) continue;
-                        tc_fence_after();
-                        issue_s(t, (it + 1) & 1);
-                        it_t[t] = it + 1;
-                        phase_t[t] = 0;
-                    }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int stage, int it) {  // O_t = P_t V, P_t read from TMEM; then hand the stage back
+            ATTN_TRACE(warp, it, 1);
+            if (elect_one()) {
+                const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * kv_bytes;
+                for (int ks = 0; ks < ksteps; ++ks)
+                    umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8,
+                                desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
+                umma_commit(&o_full[t]);
+                umma_commit(&stage_free[stage]);  // one arrival per query tile
+            }
+            __syncwarp();
+        };
+        const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+        const bool own_o = t == 0 && plan.spare;  // O_t has columns of its own (not inside the S_t region)
+        if (t < nqt && my_items > 0) {
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            for (int it = 0; it < my_items; ++it) {
+                mbar_wait(&p_full[t], it & 1);
+                if (own_o) mbar_wait(&o_free[t], (it & 1) ^ 1);  // O_t(it-1) drained
+                tc_fence_after();
+                issue_pv(it & 1, it);
+                if (it + 1 < my_items) {
+                    mbar_wait(&kv_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
+                    if (!own_o) mbar_wait(&o_free[t], it & 1);   // O_t(it) lives inside the S_t region
+                    tc_fence_after();
+                    issue_s((it + 1) & 1, it + 1);
                 }
             }
         }
@@ -396,14 +231,17 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
         const uint32_t taddr = tmem_base + lane_bits + plan.s_col(t & 1);
         const uint32_t oaddr = tmem_base + lane_bits + plan.o_col(t & 1);
         const int nch = p.kpad / 16;
+        const bool storer = quarter == 0 && lane == 0;  // issues this tile's output stores
         int it = 0;
         // A warp whose rows are all padding still walks the barriers in lockstep (an mbarrier cannot
         // take arrivals for a future phase); a whole unused warpgroup (tokens <= 128) does nothing.
         for (int item = blockIdx.x; t < nqt && item < n_items; item += gridDim.x, ++it) {
             const int img = item / 12, head = item - img * 12;
             float inv_sum = 0.f;
+            ATTN_TRACE(warp, it, 0);
             mbar_wait(&s_full[t], it & 1);
             tc_fence_after();
+            ATTN_TRACE(warp, it, 1);
             if (warp_active) {
                 // ONE pass over the S row (TMEM reads, 64 B/clk/SM, are this kernel's scarcest resource).
                 // Softmax is shift invariant, so the exponent offset need not be the row maximum (which
@@ -473,14 +311,24 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                             packed[j] = pack2<__nv_bfloat16>(e0, e1);
                         }
                     } else {
+                        // ragged step: 16-column halves, the second one only if it holds a valid key
+                        // (at 197 tokens the last step has 5 valid keys: 8 pairs instead of 16)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int c0 = base + 2 * j;
-                            float e0 = 0.f, e1 = 0.f;
-                            if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
-                            if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-                            sum4[j & 3] += e0 + e1;
-                            packed[j] = pack2<__nv_bfloat16>(e0, e1);
+                        for (int hh = 0; hh < 2; ++hh) {
+                            if (base + 16 * hh < p.tokens) {
+#pragma unroll
+                                for (int j = 8 * hh; j < 8 * hh + 8; ++j) {
+                                    const int c0 = base + 2 * j;
+                                    float e0 = 0.f, e1 = 0.f;
+                                    if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
+                                    if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
+                                    sum4[j & 3] += e0 + e1;
+                                    packed[j] = pack2<__nv_bfloat16>(e0, e1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 8 * hh; j < 8 * hh + 8; ++j) packed[j] = 0u;
+                            }
                         }
                     }
                     tmem_st_x8p(taddr + st * 16, packed);
@@ -502,9 +350,15 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                 tmem_st_wait();
                 tc_fence_before();
             }
+            ATTN_TRACE(warp, it, 2);
+            // The previous item's output store must have finished reading the staging tile before anyone
+            // rewrites it: its issuer checks here, and nobody passes o_full (the PV MMA needs all 128
+            // p_full arrivals, this one included) before that.
+            if (storer) tma_store_wait_read<0>();
             mbar_arrive(&p_full[t]);
             mbar_wait(&o_full[t], it & 1);
             tc_fence_after();
+            ATTN_TRACE(warp, it, 3);
             if (warp_active) {
                 uint32_t r0[32], r1[32];
                 tmem_ld_x32(oaddr, r0);
@@ -512,30 +366,41 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, co
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&o_free[t]);
-                if (qrow < p.tokens) {
-                    T* orow = static_cast<T*>(p.out) + (static_cast<size_t>(img) * p.tokens + qrow) * ATTN_DIM + head * ATTN_DH;
-                    uint4* dst = reinterpret_cast<uint4*>(orow);
+                ATTN_TRACE(warp, it, 4);
+                // O row -> staging tile (128B-swizzled rows, conflict-free 16-byte pieces).  Rows past the
+                // image's last token are written too; the 3-D store below clips them.
+                uint8_t* srow = sO + t * ATTN2_OSTAGE_BYTES + (quarter * 32 + lane) * 128;
+                const uint32_t sw = lane & 7;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t w[4];
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            w[q] = pack2<T>(__uint_as_float(r0[8 * j + 2 * q]) * inv_sum, __uint_as_float(r0[8 * j + 2 * q + 1]) * inv_sum);
-                        dst[j] = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            w[q] = pack2<T>(__uint_as_float(r1[8 * j + 2 * q]) * inv_sum, __uint_as_float(r1[8 * j + 2 * q + 1]) * inv_sum);
-                        dst[4 + j] = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        w[q] = pack2<T>(__uint_as_float(r0[8 * j + 2 * q]) * inv_sum, __uint_as_float(r0[8 * j + 2 * q + 1]) * inv_sum);
+                    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        w[q] = pack2<T>(__uint_as_float(r1[8 * j + 2 * q]) * inv_sum, __uint_as_float(r1[8 * j + 2 * q + 1]) * inv_sum);
+                    *reinterpret_cast<uint4*>(srow + (((4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_proxy_async_smem();
             } else {
                 mbar_arrive(&o_free[t]);
             }
+            // one full-width TMA store per query tile instead of 32 scattered 128-byte rows per warp
+            // instruction (the direct stores cost ~1.7 k LSU cycles per item, profiles/r1_attention_trace.md)
+            attn_tile_bar_sync<128>(1 + t);
+            if (storer) {
+                tma_store_3d(&tmap_out, sO + t * ATTN2_OSTAGE_BYTES, head * ATTN_DH, t * 128, img);
+                tma_store_commit();
+            }
+            ATTN_TRACE(warp, it, 5);
         }
+        if (storer) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -91,6 +91,22 @@ int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows
     return make_tmap_raw(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, cols, rows, 32, box_rows);
 }
 
+// 3-D [d2][d1][d0] tensor of 16-bit elements, dense, box {64, box_d1, 1}, 128B swizzle: per-image views
+// whose rows past d1 are clipped on store / zero-filled on load.
+int make_tmap_3d(CUtensorMap* m, int prec, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box_d1) {
+    VIT_TRY(load_driver());
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    const cuuint32_t box[3] = {64, box_d1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode(m, prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                                const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu,%llu,%llu", (int)r,
+                                          (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ launches
 constexpr int kGemmBN = 256, kGemmStages = 4, kGemmEpiWG = 2;
 constexpr int kGemmThreads = (GEMM_NON_EPI_WARPS + 4 * kGemmEpiWG) * 32;
@@ -189,35 +205,20 @@ int launch_gemm(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
                                  : launch_gemm_t<__nv_bfloat16, EPI>(ta, tb, p, sm_count, st);
 }
 
-int attention_impl() {  // VIT_ATTN_IMPL=1 selects the simple one-CTA-per-head kernel (A/B testing)
-    static int impl = -1;
-    if (impl < 0) {
-        const char* s = getenv("VIT_ATTN_IMPL");
-        impl = (s && atoi(s) == 1) ? 1 : 2;
-    }
-    return impl;
-}
-
 template <typename T>
-int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, int sm_count, cudaStream_t st) {
-    if (attention_impl() == 2) {
-        auto kern2 = attention_sm100_persistent_kernel<T>;
-        const int smem2 = attn2_smem_bytes(p.kpad);
-        CU_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-        kern2<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem2, st>>>(tq, tkv, p);
-        return check_launch("attention");
-    }
-    auto kern = attention_sm100_kernel<T>;
-    const int smem = attn_smem_bytes(p.kpad);
+int launch_attention_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count, cudaStream_t st) {
+    auto kern = attention_sm100_persistent_kernel<T>;
+    const int smem = attn2_smem_bytes(p.kpad);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<p.batch * kHeads, ATTN_THREADS, smem, st>>>(tq, tkv, p);
+    kern<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem, st>>>(tqkv, tout, p);
     return check_launch("attention");
 }
-int launch_attention(int prec, const CUtensorMap& tq, const CUtensorMap& tkv, const AttnParams& p, int sm_count,
+// tqkv: load map of the packed QKV activation (attention_load_map), tout: 3-D store map of the output
+int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count,
                      cudaStream_t st) {
     if (p.tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", p.tokens);
-    return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tq, tkv, p, sm_count, st)
-                                 : launch_attention_t<__nv_bfloat16>(tq, tkv, p, sm_count, st);
+    return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tqkv, tout, p, sm_count, st)
+                                 : launch_attention_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
 }
 
 int launch_layernorm(int prec, const float* x, const float* w, const float* b, void* y, int rows, cudaStream_t st) {
@@ -302,7 +303,7 @@ struct DeviceCtx {
     // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
     // use, so TMA zero-fills loads and clips stores past the last image
     int maps_nb = -1;
-    CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_x, tm_q, tm_kv;
+    CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_x, tm_q /* attention loads */, tm_kv /* attention store */;
     size_t ws_bytes = 0;
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
@@ -441,8 +442,8 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
     if (e.tokens <= 256) {
         const int kpad = (e.tokens + 15) / 16 * 16;
-        VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, 256));
-        VIT_TRY(make_tmap(&c.tm_kv, prec, c.qkv, 3 * kDim, rows, ATTN_DH, kpad));
+        VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, kpad / 2));          // Q/K/V half boxes
+        VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                 // per-image output tiles
     }
     c.maps_nb = nb;
     return 0;
@@ -491,7 +492,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
         VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
     }
-    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f};
+    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, nullptr};
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
         {
@@ -916,10 +917,11 @@ int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float*
     return op_end("op_layernorm");
 }
 
-int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision) {
+static int op_attention_impl(const float* qkv, float* out, int batch, int tokens, int precision,
+                             unsigned long long* trace_out, int trace_len) {
     int sms = 0;
     VIT_TRY(op_begin(&sms));
-    if (!qkv || !out || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (!qkv || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
     if (tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", tokens);
     Scratch s;
     const size_t rows = (size_t)batch * tokens;
@@ -937,13 +939,29 @@ int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, i
     }
     VIT_TRY(s.alloc(&dout, rows * kDim * 2, true));
     CUtensorMap tq, tkv;
-    VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, 256));
-    VIT_TRY(make_tmap(&tkv, precision, dqkv, 3 * kDim, rows, ATTN_DH, kpad));
-    AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f};
+    VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, kpad / 2));
+    VIT_TRY(make_tmap_3d(&tkv, precision, dout, kDim, tokens, batch, 128));
+    AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f, nullptr};
+    constexpr size_t kTraceLen = static_cast<size_t>(ATTN_TRACE_WARPS) * ATTN_TRACE_ITEMS * ATTN_TRACE_EVENTS;
+    if (trace_out) VIT_TRY(s.alloc(reinterpret_cast<void**>(&p.trace), kTraceLen * 8, true));
     VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr));
     VIT_TRY(op_end("op_attention"));
-    VIT_TRY(s.download_operand(out, dout, rows * kDim, precision));
+    if (trace_out)
+        CU_TRY(cudaMemcpy(trace_out, p.trace, std::min(kTraceLen, static_cast<size_t>(std::max(trace_len, 0))) * 8,
+                          cudaMemcpyDeviceToHost));
+    if (out) VIT_TRY(s.download_operand(out, dout, rows * kDim, precision));
     return op_end("op_attention");
+}
+
+int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision) {
+    if (!out) return set_err(VIT_E_ARG, "bad arguments");
+    return op_attention_impl(qkv, out, batch, tokens, precision, nullptr, 0);
+}
+
+int vit_cuda_debug_attention_trace(const float* qkv, int batch, int tokens, int precision, unsigned long long* trace,
+                                   int trace_len) {
+    if (!trace || trace_len <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    return op_attention_impl(qkv, nullptr, batch, tokens, precision, trace, trace_len);
 }
 
 int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w, const float* conv_b, const float* pos,

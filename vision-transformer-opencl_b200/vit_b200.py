@@ -77,6 +77,7 @@ _sig("vit_cuda_host_free_pinned", C.c_int, C.c_void_p)
 _sig("vit_cuda_op_linear", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_op_layernorm", C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int)
 _sig("vit_cuda_op_attention", C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
+_sig("vit_cuda_debug_attention_trace", C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int)
 _sig("vit_cuda_op_embed", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_op_head", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int)
 # ---- include/vit_host.h
@@ -285,6 +286,13 @@ def op_attention(qkv, batch, tokens, precision=PREC_BF16):
     out = np.empty((batch * tokens, 768), dtype=np.float32)
     _check(lib.vit_cuda_op_attention(fptr(qkv), fptr(out), batch, tokens, precision))
     return out
+
+
+def attention_trace(qkv, batch, tokens, precision=PREC_BF16):
+    """SM-clock timestamps [warp 11][item 16][event 8] of CTA 0 of the attention kernel (debug)."""
+    tr = np.zeros((11, 16, 8), dtype=np.uint64)
+    _check(lib.vit_cuda_debug_attention_trace(fptr(qkv), batch, tokens, precision, tr.ctypes.data_as(C.POINTER(C.c_uint64)), tr.size))
+    return tr
 
 
 def op_embed(images, cls, conv_w, conv_b, pos, precision=PREC_BF16):
