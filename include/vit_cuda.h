@@ -170,7 +170,7 @@ int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float*
 int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision);
 
 /* Debug: runs the attention kernel as above and returns SM-clock timestamps of the pipeline events
- * of CTA 0 (11 warps x 16 items x 8 events of uint64, layout in csrc/attention_sm100.cuh) instead of
+ * of CTA 0 (19 warps x 16 items x 8 events of uint64, layout in csrc/attention_sm100.cuh) instead of
  * the result.  Used by tools/attn_trace.py to read the kernel's timeline; not part of the hot path. */
 int vit_cuda_debug_attention_trace(const float* qkv, int batch, int tokens, int precision,
                                    unsigned long long* trace, int trace_len);

@@ -22,9 +22,9 @@ struct AttnParams {
 };
 
 // Pipeline trace of CTA 0 (vit_cuda_debug_attention_trace): trace[(warp * ITEMS + item) * EVENTS + event] = clock64().
-// softmax warps 0-7: 0 item start, 1 S ready, 2 P written, 3 O ready, 4 O in registers, 5 O stored
-// warp 8 (producer): 0 stage free / TMA issued        warps 9, 10 (MMA issuers): 0 S_t issued, 1 PV_t issued
-constexpr int ATTN_TRACE_ITEMS = 16, ATTN_TRACE_EVENTS = 8, ATTN_TRACE_WARPS = 11;
+// softmax warps 0-15: 0 item start, 1 S ready, 2 P written, 3 O ready, 4 O in registers, 5 O stored
+// warp 16 (producer): 0 stage free / TMA issued        warps 17, 18 (MMA issuers): 0 S_t issued, 1 PV_t issued
+constexpr int ATTN_TRACE_ITEMS = 16, ATTN_TRACE_EVENTS = 8, ATTN_TRACE_WARPS = 19;
 #define ATTN_TRACE(warp_, it_, ev_)                                                                          \
     do {                                                                                                     \
         if (p.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) < ATTN_TRACE_ITEMS)    \
@@ -41,20 +41,30 @@ __host__ __device__ inline int attn_kv_bytes(int kpad) { return kpad * 128; }
 // Persistent, software-pipelined kernel.
 //
 // One CTA per SM loops over (image, head) items.  Per item the two 128-row query tiles own one
-// 256-column TMEM region each:   S_t fp32 [0,kpad)  ->  P_t (operand precision, packed two per
-// column, written back in place by the softmax threads) [0,kpad/2)  ->  O_t fp32 [128,192).
-// P never touches shared memory: the second MMA takes its A operand from TMEM.  Shared memory
-// holds only the double-buffered Q/K/V tiles of the current and the next item, so the TMA loads
-// of item i+1 run under the softmax of item i, and while one warpgroup is in its softmax the
-// tensor core works for the other one.
+// TMEM region each:   S_t fp32 [0,kpad)  ->  P_t (bf16, packed two per column, written back in
+// place by the softmax threads)  ->  O_t fp32.  P never touches shared memory: the second MMA
+// takes its A operand from TMEM.  Shared memory holds the double-buffered Q/K/V tiles of the
+// current and the next item (TMA loads of item i+1 run under the softmax of item i) and one
+// output staging tile per query tile.
 //
-//   warp 8  TMA producer          warps 9, 10  MMA issuers for query tile 0 / 1 (warp 9 owns TMEM)
-//   warps 0-3 / 4-7  softmax + output warpgroups for query tile 0 / 1
-constexpr int ATTN2_THREADS = 352;
+// TWO threads per query row.  One softmax warp per SM sub-partition and tile issues a dependent
+// instruction only every ~4 cycles (fixed-latency stalls; the MUFU pipe sat at 40 % with one thread
+// per row, profiles/r1_attention_trace.md), so every row is split by key range between two threads
+// of two different warps -- both may address the row's TMEM lane, as lane access is by (warp % 4):
+//     half A: keys [0,128)     S cols [0,128)     -> P cols [0,64)
+//     half B: keys [128,kpad)  S cols [128,kpad)  -> P cols [128, 128 + (kpad-128)/2)
+// Each half overwrites only S columns it has itself already read, and S cols [64,128) are dead
+// once half A is through, which is where O_t goes.  The halves agree on the row maximum through
+// shared memory (one 64-thread named barrier per item) and add their row sums in the epilogue.
+//
+//   warps 0-7 / 8-15  softmax + output for query tile 0 / 1: warp = tile*8 + half*4 + lane quarter
+//   warp 16  TMA producer     warps 17, 18  MMA issuers for query tile 0 / 1 (warp 17 owns TMEM)
+constexpr int ATTN2_THREADS = 19 * 32;
+constexpr int ATTN2_W_PRODUCER = 16, ATTN2_W_ISSUER = 17;
 // TMEM column plan (512 columns).  With kpad <= 224 (ViT-B/16 at 224^2: kpad = 208):
-//   S_0/P_0 [0,kpad)   S_1/P_1 [kpad,2 kpad)   O_1 inside its S region at +128   O_0 [2 kpad, 2 kpad+64)
+//   S_0 [0,kpad)   S_1 [kpad,2 kpad)   O_1 at S_1 + 64   O_0 [2 kpad, 2 kpad+64)
 // so S_0 of the next item can be issued without waiting for O_0 to be drained.  Otherwise
-//   S_0 [0,256)  S_1 [256,512)  O_t inside its own S region at +128.
+//   S_0 [0,256)  S_1 [256,512)  O_t at S_t + 64.
 struct AttnTmemPlan {
     uint32_t s1, o0, o1;  // column of S_1, O_0, O_1 (S_0 is at column 0)
     bool spare;
@@ -65,20 +75,29 @@ __device__ __forceinline__ AttnTmemPlan attn2_tmem_plan(int kpad) {
     AttnTmemPlan pl;
     pl.spare = 2 * kpad + 64 <= 512;
     pl.s1 = pl.spare ? kpad : 256;
-    pl.o1 = pl.s1 + 128;
-    pl.o0 = pl.spare ? 2 * kpad : 128;
+    pl.o1 = pl.s1 + 64;
+    pl.o0 = pl.spare ? 2 * kpad : 64;
     return pl;
 }
 // Shared memory: two stages of {Q, K, V} x kpad rows x 128 B (Q only needs `tokens` rows; the second
-// query tile's descriptor runs on into the K rows behind it, whose S rows nobody reads), then one
-// 128 x 128 B output staging tile per query tile.
+// query tile's descriptor runs on into the K rows behind it, whose S rows nobody reads), one
+// 128 x 128 B output staging tile per query tile, the row max / row sum exchange between the two
+// halves of a row, and the barriers.
 __host__ __device__ inline int attn2_stage_bytes(int kpad) { return 3 * attn_kv_bytes(kpad); }
 constexpr int ATTN2_OSTAGE_BYTES = 128 * 128;
-__host__ inline int attn2_smem_bytes(int kpad) { return 2 * attn2_stage_bytes(kpad) + 2 * ATTN2_OSTAGE_BYTES + 256 + 1024; }
+constexpr int ATTN2_XCH_BYTES = (2 * 2 * 128 + 2 * 2 * 2 * 128) * 4;  // max [tile][half][row], sum [parity][tile][half][row]
+__host__ inline int attn2_smem_bytes(int kpad) {
+    return 2 * attn2_stage_bytes(kpad) + 2 * ATTN2_OSTAGE_BYTES + ATTN2_XCH_BYTES + 256 + 1024;
+}
 
 template <int NTHREADS>
-__device__ __forceinline__ void attn_tile_bar_sync(int id) {
+__device__ __forceinline__ void attn_bar_sync(int id) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
+}
+
+template <int NTHREADS>
+__device__ __forceinline__ void attn_bar_arrive(int id) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
 }
 
 template <typename T>
@@ -90,13 +109,15 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
     const int kv_bytes = attn_kv_bytes(p.kpad);
     const int stage_bytes = attn2_stage_bytes(p.kpad);
     uint8_t* sO = smem + 2 * stage_bytes;  // [2 tiles] output staging, 128B-swizzled rows of 64 x 16-bit
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATTN2_OSTAGE_BYTES);
+    float* xmax = reinterpret_cast<float*>(sO + 2 * ATTN2_OSTAGE_BYTES);  // [tile][half][128]
+    float* xsum = xmax + 2 * 2 * 128;                                     // [item parity][tile][half][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + ATTN2_XCH_BYTES);
     uint64_t* kv_full = bars;        // [2 stages] Q,K,V of an item landed (tx)
     uint64_t* stage_free = bars + 2; // [2 stages] every MMA reading the stage has completed
     uint64_t* s_full = bars + 4;     // [2 tiles]  S_t in TMEM
-    uint64_t* p_full = bars + 6;     // [2 tiles]  P_t written back (128 arrivals)
+    uint64_t* p_full = bars + 6;     // [2 tiles]  P_t written back (256 arrivals)
     uint64_t* o_full = bars + 8;     // [2 tiles]  O_t in TMEM
-    uint64_t* o_free = bars + 10;    // [2 tiles]  O_t drained, region reusable (128 arrivals)
+    uint64_t* o_free = bars + 10;    // [2 tiles]  O_t drained, region reusable (256 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
@@ -105,26 +126,26 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
     const int nqt = p.tokens > 128 ? 2 : 1;
     const AttnTmemPlan plan = attn2_tmem_plan(p.kpad);
 
-    if (warp == 8 && lane == 0) {
+    if (warp == ATTN2_W_PRODUCER && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
         tma_prefetch_desc(&tmap_out);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1);
             mbar_init(&stage_free[i], nqt);
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
+            mbar_init(&p_full[i], 256);
             mbar_init(&o_full[i], 1);
-            mbar_init(&o_free[i], 128);
+            mbar_init(&o_free[i], 256);
         }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    if (warp == ATTN2_W_ISSUER) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == ATTN2_W_PRODUCER) {
         // ------------------------------------------------------------ TMA producer
         // One TMA operation keeps only a few dozen 128-byte row requests in flight, and every row of
         // a head's Q/K/V slice lies in a different DRAM page (row pitch 4608 B): a whole item issued
@@ -142,7 +163,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
                 uint8_t* sK = sQ + kv_bytes;
                 uint8_t* sV = sK + kv_bytes;
                 mbar_wait(&stage_free[s], ((it >> 1) & 1) ^ 1);
-                ATTN_TRACE(8, it, 0);
+                ATTN_TRACE(warp, it, 0);
                 mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -164,16 +185,15 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
                 }
             }
         }
-    } else if (warp >= 9) {
-        // ------------------------------------------------------------ MMA issuers: warp 9 for query tile 0, warp 10 for tile 1
-        // One issuer per query tile, each a plain blocking loop  P_t(i) -> PV_t(i) -> K(i+1) -> S_t(i+1).
-        // (A single warp polling both tiles' barriers sat on the critical path of both: sharing an SM
-        // sub-partition with two softmax warps, each of its four issue actions per item cost 0.6-1.1 k
-        // cycles, profiles/r1_attention_trace.md.)  The two tiles share no TMEM columns, and the tensor
-        // pipe executes each issuer's instructions in order, which protects P_t(i) from S_t(i+1).
+    } else if (warp >= ATTN2_W_ISSUER) {
+        // ------------------------------------------------------------ MMA issuers: one warp per query tile
+        // Each a plain blocking loop  P_t(i) -> PV_t(i) -> K(i+1) -> S_t(i+1).  (A single warp polling both
+        // tiles' barriers sat on the critical path of both: each of its four issue actions per item cost
+        // 0.6-1.1 k cycles, profiles/r1_attention_trace.md.)  The two tiles share no TMEM columns, and the
+        // tensor pipe executes each issuer's instructions in order, which protects P_t(i) from S_t(i+1).
         // The whole warp walks the loop so that descriptors and barrier addresses live in uniform
         // registers; one elected lane issues.
-        const int t = warp - 9;
+        const int t = warp - ATTN2_W_ISSUER;
         const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
         const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
         const int ksteps = p.kpad / 16;
@@ -194,8 +214,8 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
             ATTN_TRACE(warp, it, 1);
             if (elect_one()) {
                 const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * kv_bytes;
-                for (int ks = 0; ks < ksteps; ++ks)
-                    umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8,
+                for (int ks = 0; ks < ksteps; ++ks)  // keys [16 ks, 16 ks + 16): P cols of half A, then of half B
+                    umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8 + (ks >= 8 ? 64 : 0),
                                 desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
                 umma_commit(&o_full[t]);
                 umma_commit(&stage_free[stage]);  // one arrival per query tile
@@ -222,137 +242,142 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
             }
         }
     } else {
-        // ------------------------------------------------------------ softmax / output warpgroups
-        const int t = warp >> 2;
-        const int quarter = warp & 3;
-        const int qrow = t * 128 + quarter * 32 + lane;
+        // ------------------------------------------------------------ softmax / output warps
+        const int t = warp >> 3;            // query tile
+        const int half = (warp >> 2) & 1;   // key range: A = [0,128), B = [128,kpad)
+        const int quarter = warp & 3;       // TMEM lane quarter (must be warp % 4)
+        const int row = quarter * 32 + lane;  // row inside the tile
         const bool warp_active = t < nqt && (t * 128 + quarter * 32) < p.tokens;
         const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t taddr = tmem_base + lane_bits + plan.s_col(t & 1);
-        const uint32_t oaddr = tmem_base + lane_bits + plan.o_col(t & 1);
+        const uint32_t oaddr = tmem_base + lane_bits + plan.o_col(t & 1) + half * 32;  // this half's 32 O columns
         const int nch = p.kpad / 16;
-        const bool storer = quarter == 0 && lane == 0;  // issues this tile's output stores
+        const int ch0 = half ? 8 : 0;                        // first 16-key chunk of this half
+        const int ch1 = half ? nch : (nch < 8 ? nch : 8);    // one past its last chunk
+        const uint32_t pbias = half ? 64u : 0u;              // P chunk c goes to column 8 c + pbias
+        const bool split = nch > 8;                          // half B has keys at all
+        const bool storer = (warp & 7) == 0 && lane == 0;    // issues this tile's output stores
+        const int pair_bar = 1 + t * 4 + quarter;            // named barrier of the two warps sharing these rows
+        const int nsteps = ch1 - ch0;                        // 16-key chunks of this half (<= 0: none)
+        const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+        if (nqt == 2 && t == 1 && my_items > 0) attn_bar_arrive<512>(11);  // tile 0 exponentiates first
+        float* my_max = xmax + (t * 2 + half) * 128 + row;
+        const float* other_max = xmax + (t * 2 + (half ^ 1)) * 128 + row;
         int it = 0;
         // A warp whose rows are all padding still walks the barriers in lockstep (an mbarrier cannot
-        // take arrivals for a future phase); a whole unused warpgroup (tokens <= 128) does nothing.
+        // take arrivals for a future phase); the warps of an unused tile (tokens <= 128) do nothing.
         for (int item = blockIdx.x; t < nqt && item < n_items; item += gridDim.x, ++it) {
             const int img = item / 12, head = item - img * 12;
-            float inv_sum = 0.f;
+            float* my_sum = xsum + (((it & 1) * 2 + t) * 2 + half) * 128 + row;
+            const float* other_sum = xsum + (((it & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row;
             ATTN_TRACE(warp, it, 0);
             mbar_wait(&s_full[t], it & 1);
             tc_fence_after();
             ATTN_TRACE(warp, it, 1);
+            uint32_t ra[16], rb[16];
+            float mx = 0.f;
             if (warp_active) {
-                // ONE pass over the S row (TMEM reads, 64 B/clk/SM, are this kernel's scarcest resource).
-                // Softmax is shift invariant, so the exponent offset need not be the row maximum (which
-                // would cost a first full pass): it starts as the maximum of the first 32 scores and is
-                // raised lazily.  Before the exponentials of each 32-column step the step maximum is
-                // compared with the offset; only if it exceeds it by more than 2^kLazy is everything
-                // written so far (P in TMEM, the row sum) rescaled by an exact integer power of two and
-                // the offset moved -- the online-softmax recurrence with the rescale made rare.  P is
-                // bf16 (fp32 exponent range), so values up to 2^kLazy are harmless, and no exponential
-                // is ever evaluated above that bound, whatever the scores are.
-                // Two x16 TMEM loads per round trip, the next step's loads in flight while the current
-                // one is processed.  P columns [16 st, 16 st + 16) are written in place and never overlap
-                // S columns not yet read.
-                constexpr float kLazy = 24.f;
-                const int nsteps = (nch + 1) >> 1;
-                uint32_t ra[32], rb[32];
-                auto load_step = [&](uint32_t* buf, int st) {
-                    tmem_ld_x16p(taddr + st * 32, buf);
-                    if (2 * st + 1 < nch) tmem_ld_x16p(taddr + st * 32 + 16, buf + 16);
-                };
-                float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
-                float moff = 0.f;                      // -(offset) * scale * log2(e)
-                auto exp_step = [&](const uint32_t* v, int st) {
-                    const int base = st * 32;
-                    const bool full = base + 32 <= p.tokens;
-                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    if (full) {
+                // Two passes over this half's S columns.  Pass 1 finds the exact row maximum (tcgen05.ld +
+                // max only; TMEM reads are cheap, a warp pulls 32 x 64 fp32 in ~80 cycles).  Pass 2 is a
+                // straight stream  tcgen05.ld -> FFMA -> ex2 -> add / pack -> tcgen05.st  with no vote,
+                // branch or rescale between the exponentials.  With the true maximum every P is <= 1,
+                // exactly as in the reference's softmax (ViT_seq.c:178-191).
+                // pass 1 in 32-column loads (tcgen05.ld has a high per-instruction cost: 16-column loads
+                // reached ~140 B/clk/SM here, the 32-column O loads ~290), a ragged rest in 16s
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                {
+                    int c = ch0;
+                    for (; c + 2 <= ch1; c += 2) {
+                        uint32_t v[32];
+                        tmem_ld_x32(taddr + c * 16, v);
+                        tmem_ld_wait();
+                        if (c * 16 + 32 <= p.tokens) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
-                    } else {
+                            for (int j = 0; j < 16; ++j)
+                                m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (base + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
-                    }
-                    const float smax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                    if (st == 0) {
-                        moff = -smax * p.scale_log2;
-                    } else {
-                        const float over = fmaf(smax, p.scale_log2, moff);  // log2 of this step's largest p
-                        if (__any_sync(0xffffffffu, over > kLazy)) {
-                            // exact repair: 2^-sh on P[0, 16 st) and on the sum, offset raised by sh
-                            const int sh = over > kLazy ? static_cast<int>(ceilf(fminf(over, 1.0e6f))) : 0;
-                            const float f = sh > 126 ? 0.f : __int_as_float((127 - sh) << 23);
-                            tmem_st_wait();
-                            for (int c8 = 0; c8 < 2 * st; ++c8) {
-                                uint32_t w[8];
-                                tmem_ld_x8p(taddr + c8 * 8, w);
-                                tmem_ld_wait();
-#pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    w[j] = pack2<__nv_bfloat16>(__uint_as_float(w[j] << 16) * f, __uint_as_float(w[j] & 0xffff0000u) * f);
-                                tmem_st_x8p(taddr + c8 * 8, w);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) sum4[j] *= f;
-                            moff -= static_cast<float>(sh);
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
                         }
                     }
-                    uint32_t packed[16];
-                    if (full) {
+                    for (; c < ch1; ++c) {
+                        uint32_t v[16];
+                        tmem_ld_x16p(taddr + c * 16, v);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < 16; ++j)
+                            if (c * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+                    }
+                }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                ATTN_TRACE(warp, it, 6);
+                if (nsteps > 0) tmem_ld_x16p(taddr + ch0 * 16, ra);  // pass 2's first load flies during the exchange
+                if (split) {
+                    *my_max = mx;
+                    attn_bar_sync<64>(pair_bar);
+                    mx = fmaxf(mx, *other_max);
+                }
+            }
+            // Ping-pong: the exponentials of the two query tiles take turns on the MUFU pipe, so that one
+            // tile's MMA round trips, maximum pass and output epilogue run under the other tile's
+            // exponentials instead of both tiles computing and then both waiting.
+            if (nqt == 2) attn_bar_sync<512>(11 + t);
+            if (warp_active) {
+                const float moff = -mx * p.scale_log2;
+                ATTN_TRACE(warp, it, 7);
+                float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
+                auto exp_step = [&](const uint32_t* v, int c) {
+                    const int base = c * 16;
+                    uint32_t packed[8];
+                    if (base + 16 <= p.tokens) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
                             const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
                             const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
                             sum4[j & 3] += e0 + e1;
                             packed[j] = pack2<__nv_bfloat16>(e0, e1);
                         }
-                    } else {
-                        // ragged step: 16-column halves, the second one only if it holds a valid key
-                        // (at 197 tokens the last step has 5 valid keys: 8 pairs instead of 16)
+                    } else {  // ragged last chunk (at 197 tokens: 5 valid keys)
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            if (base + 16 * hh < p.tokens) {
-#pragma unroll
-                                for (int j = 8 * hh; j < 8 * hh + 8; ++j) {
-                                    const int c0 = base + 2 * j;
-                                    float e0 = 0.f, e1 = 0.f;
-                                    if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
-                                    if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-                                    sum4[j & 3] += e0 + e1;
-                                    packed[j] = pack2<__nv_bfloat16>(e0, e1);
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 8 * hh; j < 8 * hh + 8; ++j) packed[j] = 0u;
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            const int c0 = base + 2 * j;
+                            float e0 = 0.f, e1 = 0.f;
+                            if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
+                            if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
+                            sum4[j & 3] += e0 + e1;
+                            packed[j] = pack2<__nv_bfloat16>(e0, e1);
                         }
                     }
-                    tmem_st_x8p(taddr + st * 16, packed);
-                    if (2 * st + 1 < nch) tmem_st_x8p(taddr + st * 16 + 8, packed + 8);
+                    // in place: P chunk c lands on S columns this thread has already read
+                    tmem_st_x8p(taddr + c * 8 + pbias, packed);
                 };
-                load_step(ra, 0);
-                for (int st = 0; st < nsteps; st += 2) {
-                    tmem_ld_wait();
-                    if (st + 1 < nsteps) load_step(rb, st + 1);
-                    exp_step(ra, st);
-                    if (st + 1 < nsteps) {
+                // fully unrolled over the (at most 8) chunks of a half: TMEM addresses become base + immediate
+                // (no per-step R2UR / loop branch), the next chunk's load is in flight while this one is processed
+                const uint32_t sbase = taddr + ch0 * 16;
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) {
+                    if (i < nsteps) {
                         tmem_ld_wait();
-                        if (st + 2 < nsteps) load_step(ra, st + 2);
-                        exp_step(rb, st + 1);
+                        if (i + 1 < nsteps) tmem_ld_x16p(sbase + (i + 1) * 16, rb);
+                        exp_step(ra, ch0 + i);
+                    }
+                    if (i + 1 < nsteps) {
+                        tmem_ld_wait();
+                        if (i + 2 < nsteps) tmem_ld_x16p(sbase + (i + 2) * 16, ra);
+                        exp_step(rb, ch0 + i + 1);
                     }
                 }
-                const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-                inv_sum = fast_rcp(sum);
+                *my_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+            }
+            if (nqt == 2 && (t == 0 || it + 1 < my_items)) attn_bar_arrive<512>(11 + (t ^ 1));  // the other tile's turn
+            if (warp_active) {
                 tmem_st_wait();
                 tc_fence_before();
             }
             ATTN_TRACE(warp, it, 2);
             // The previous item's output store must have finished reading the staging tile before anyone
-            // rewrites it: its issuer checks here, and nobody passes o_full (the PV MMA needs all 128
+            // rewrites it: its issuer checks here, and nobody passes o_full (the PV MMA needs all 256
             // p_full arrivals, this one included) before that.
             if (storer) tma_store_wait_read<0>();
             mbar_arrive(&p_full[t]);
@@ -360,16 +385,19 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
             tc_fence_after();
             ATTN_TRACE(warp, it, 3);
             if (warp_active) {
-                uint32_t r0[32], r1[32];
+                // both halves' row sums were written before their p_full arrivals (release), which the PV
+                // MMA behind o_full waited for; the buffer alternates per item, so a fast partner cannot
+                // overwrite it before this read
+                const float inv_sum = fast_rcp(*my_sum + *other_sum);  // a half without keys wrote 0
+                uint32_t r0[32];
                 tmem_ld_x32(oaddr, r0);
-                tmem_ld_x32(oaddr + 32, r1);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&o_free[t]);
                 ATTN_TRACE(warp, it, 4);
-                // O row -> staging tile (128B-swizzled rows, conflict-free 16-byte pieces).  Rows past the
-                // image's last token are written too; the 3-D store below clips them.
-                uint8_t* srow = sO + t * ATTN2_OSTAGE_BYTES + (quarter * 32 + lane) * 128;
+                // this half's 32 O columns -> staging tile (128B-swizzled rows, conflict-free 16-byte
+                // pieces).  Rows past the image's last token are written too; the 3-D store clips them.
+                uint8_t* srow = sO + t * ATTN2_OSTAGE_BYTES + row * 128;
                 const uint32_t sw = lane & 7;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -377,15 +405,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         w[q] = pack2<T>(__uint_as_float(r0[8 * j + 2 * q]) * inv_sum, __uint_as_float(r0[8 * j + 2 * q + 1]) * inv_sum);
-                    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        w[q] = pack2<T>(__uint_as_float(r1[8 * j + 2 * q]) * inv_sum, __uint_as_float(r1[8 * j + 2 * q + 1]) * inv_sum);
-                    *reinterpret_cast<uint4*>(srow + (((4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();
             } else {
@@ -393,7 +413,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
             }
             // one full-width TMA store per query tile instead of 32 scattered 128-byte rows per warp
             // instruction (the direct stores cost ~1.7 k LSU cycles per item, profiles/r1_attention_trace.md)
-            attn_tile_bar_sync<128>(1 + t);
+            attn_bar_sync<256>(9 + t);
             if (storer) {
                 tma_store_3d(&tmap_out, sO + t * ATTN2_OSTAGE_BYTES, head * ATTN_DH, t * 128, img);
                 tma_store_commit();
@@ -405,7 +425,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == ATTN2_W_ISSUER) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }

@@ -216,7 +216,7 @@ int launch_attention_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const A
 // tqkv: load map of the packed QKV activation (attention_load_map), tout: 3-D store map of the output
 int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count,
                      cudaStream_t st) {
-    if (p.tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", p.tokens);
+    if (p.tokens > 224) return set_err(VIT_E_ARG, "attention: tokens=%d > 224 not supported by the single-block kernel", p.tokens);
     return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tqkv, tout, p, sm_count, st)
                                  : launch_attention_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
 }
@@ -440,7 +440,7 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));     // mlp_0 store + mlp_3 A load
     VIT_TRY(make_tmap(&c.tm_qkv_st, prec, c.qkv, 3 * kDim, rows, GEMM_BK, GEMM_BM)); // in_proj store
     VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
-    if (e.tokens <= 256) {
+    if (e.tokens <= 224) {
         const int kpad = (e.tokens + 15) / 16 * 16;
         VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, kpad / 2));          // Q/K/V half boxes
         VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                 // per-image output tiles
@@ -615,7 +615,7 @@ int vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
     if (gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
     if (n <= 0 || n > e.max_batch) return set_err(VIT_E_ARG, "n=%d outside (0, max_batch=%d]", n, e.max_batch);
-    if (e.tokens > 256) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    if (e.tokens > 224) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
     if (gemm_impl() != 2 && e.prec != VIT_PREC_BF16) return set_err(VIT_E_ARG, "VIT_GEMM_IMPL=1 (A/B test kernels) supports bf16 only");
     DeviceCtx& c = e.ctx[gpu_slot];
     CU_TRY(cudaSetDevice(c.device));
@@ -654,7 +654,7 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
     if (!images_nchw || !logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
     if (n == 0) return 0;
-    if (e.tokens > 256) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    if (e.tokens > 224) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
     const int G = static_cast<int>(e.ctx.size());
     const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
     const int per_gpu = (n + G - 1) / G;  // contiguous shards
@@ -922,7 +922,7 @@ static int op_attention_impl(const float* qkv, float* out, int batch, int tokens
     int sms = 0;
     VIT_TRY(op_begin(&sms));
     if (!qkv || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    if (tokens > 256) return set_err(VIT_E_ARG, "attention: tokens=%d > 256 not supported by the single-block kernel", tokens);
+    if (tokens > 224) return set_err(VIT_E_ARG, "attention: tokens=%d > 224 not supported by the single-block kernel", tokens);
     Scratch s;
     const size_t rows = (size_t)batch * tokens;
     const int kpad = (tokens + 15) / 16 * 16;

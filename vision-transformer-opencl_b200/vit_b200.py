@@ -289,8 +289,8 @@ def op_attention(qkv, batch, tokens, precision=PREC_BF16):
 
 
 def attention_trace(qkv, batch, tokens, precision=PREC_BF16):
-    """SM-clock timestamps [warp 11][item 16][event 8] of CTA 0 of the attention kernel (debug)."""
-    tr = np.zeros((11, 16, 8), dtype=np.uint64)
+    """SM-clock timestamps [warp 19][item 16][event 8] of CTA 0 of the attention kernel (debug)."""
+    tr = np.zeros((19, 16, 8), dtype=np.uint64)
     _check(lib.vit_cuda_debug_attention_trace(fptr(qkv), batch, tokens, precision, tr.ctypes.data_as(C.POINTER(C.c_uint64)), tr.size))
     return tr
 
