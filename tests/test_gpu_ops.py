@@ -79,7 +79,8 @@ def test_layernorm(vit, oracle, prec, rows):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 256), (2, 130), (40, 197), (70, 100)])
+@pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 224), (2, 130), (2, 17), (40, 197), (70, 100),
+                                          (1, 225), (1, 256), (2, 300), (2, 577), (1, 640), (30, 577)])
 def test_attention(vit, oracle, prec, batch, tokens):
     qkv = _round_qkv(_rand((batch * tokens, 2304), 14 + tokens), prec)
     got = vit.op_attention(qkv, batch, tokens, precision=prec)

@@ -122,14 +122,14 @@ def case_head():
     stats("head", got, ref)
 
 
-def case_model(n, prec, max_batch):
+def case_model(n, prec, max_batch, img=224):
     import vit_b200 as V, oracle_py as O
-    w = V.synth_weights(224, 42)
-    imgs = V.synth_images(n, 224, 7)
+    w = V.synth_weights(img, 42)
+    imgs = V.synth_images(n, img, 7)
     t = time.time()
-    ref = O.forward(w, imgs, 224)
+    ref = O.forward(w, imgs, img)
     t_or = time.time() - t
-    with V.Engine(w, 224, max_batch=max_batch, precision=prec) as eng:
+    with V.Engine(w, img, max_batch=max_batch, precision=prec) as eng:
         print("engine info", eng.info(), flush=True)
         t = time.time()
         got, top1 = eng.forward(imgs, want_top1=True)
@@ -157,7 +157,14 @@ CASES = {
     "attention_64": lambda: case_attention(1, 64, 0),
     "attention_197": lambda: case_attention(2, 197, 0),
     "attention_197_fp16": lambda: case_attention(2, 197, 1),
+    "attention_224": lambda: case_attention(1, 224, 0),
     "attention_256": lambda: case_attention(1, 256, 0),
+    "attention_300": lambda: case_attention(2, 300, 0),
+    "attention_577": lambda: case_attention(2, 577, 0),
+    "attention_577_fp16": lambda: case_attention(2, 577, 1),
+    "attention_640": lambda: case_attention(1, 640, 0),
+    "attention_577_many": lambda: case_attention(30, 577, 0),
+    "model384_bf16": lambda: case_model(2, 0, 2, 384),
     "attention_many": lambda: case_attention(40, 197, 0),
     "attention_peaky": lambda: case_attention(2, 197, 0, True),
     "attention_peaky_fp16": lambda: case_attention(2, 197, 1, True),

@@ -277,13 +277,11 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
             uint32_t ra[16], rb[16];
             float mx = 0.f;
             if (warp_active) {
-                // Two passes over this half's S columns.  Pass 1 finds the exact row maximum (tcgen05.ld +
-                // max only; TMEM reads are cheap, a warp pulls 32 x 64 fp32 in ~80 cycles).  Pass 2 is a
-                // straight stream  tcgen05.ld -> FFMA -> ex2 -> add / pack -> tcgen05.st  with no vote,
-                // branch or rescale between the exponentials.  With the true maximum every P is <= 1,
-                // exactly as in the reference's softmax (ViT_seq.c:178-191).
-                // pass 1 in 32-column loads (tcgen05.ld has a high per-instruction cost: 16-column loads
-                // reached ~140 B/clk/SM here, the 32-column O loads ~290), a ragged rest in 16s
+                // Two passes over this half's S columns: pass 1 finds the exact row maximum (tcgen05.ld + max
+                // only), pass 2 is a straight stream  tcgen05.ld -> FFMA -> ex2 -> add / pack -> tcgen05.st  with
+                // no vote, branch or rescale.  With the true maximum every P is <= 1, exactly as in the
+                // reference's softmax (ViT_seq.c:178-191).  Cost: S is read twice, and TMEM reads (~64 B/clk/SM)
+                // are this kernel's ceiling -- see profiles/r1_attention_trace.md for the single-pass plan.
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 {
                     int c = ch0;
@@ -426,6 +424,290 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
     tc_fence_before();
     __syncthreads();
     if (warp == ATTN2_W_ISSUER) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace vit
+
+namespace vit {
+
+// =============================================================================================
+// Key-blocked kernel for longer sequences (224 < tokens <= 640; ViT-B/16 at 384^2: 577 tokens).
+//
+// One CTA per SM loops over (image, head) units.  The head's whole K and V (ceil(tokens/64) blocks of
+// 64 keys x 128 B, <= 80 KB each) stay in shared memory for all of the head's 128-row query tiles,
+// which the CTA's two softmax warpgroups take alternately (warpgroup w: tiles w, w+2, ...), each
+// with its own Q buffer, MMA-issuer warp and TMEM columns:
+//     S block buffers [0,64) [64,128) (double buffered: the MMA of block g+1 runs under the softmax
+//     of block g), O [128,192); warpgroup 1 at +192.
+// A row of S (up to 640 fp32) does not fit in TMEM next to O, so keys go in blocks of 64, and to
+// keep O free of rescaling the tile makes TWO passes over its key blocks:
+//     pass A   S_j = Q K_j^T  ->  running row maximum (exact)
+//     pass B   S_j again      ->  P_j = exp2((S_j - max) / 8 * log2 e) written in place (bf16, 32 columns)
+//                             ->  O += P_j V_j   (A operand from TMEM, V_j MN-major from shared memory)
+// i.e. the reference's max / exp / sum / divide (ViT_seq.c:178-191) block by block, the division
+// applied once to O.  QK^T is computed twice -- the tensor pipe has the slack (TMEM reads at
+// ~64 B/clk/SM bound this kernel, profiles/r1_attention_trace.md); a single-pass variant with a
+// lazy power-of-two rescale of O is the planned successor.
+//
+//   warps 0-3 / 4-7  softmax + output warpgroups 0 / 1 (one thread per query row)
+//   warp 8  TMA producer      warps 9, 10  MMA issuers of warpgroup 0 / 1 (warp 9 owns TMEM)
+constexpr int ATTNL_THREADS = 11 * 32;
+constexpr int ATTNL_MAX_TOKENS = 640;
+constexpr int ATTNL_KB = 64;                        // keys per block
+constexpr int ATTNL_BLOCK_BYTES = ATTNL_KB * 128;   // one K or V block in shared memory
+__host__ __device__ inline int attnl_blocks(int tokens) { return (tokens + ATTNL_KB - 1) / ATTNL_KB; }
+__host__ inline int attnl_smem_bytes(int tokens) {
+    return 2 * attnl_blocks(tokens) * ATTNL_BLOCK_BYTES + 2 * ATTN_Q_TILE_BYTES + 2 * ATTN2_OSTAGE_BYTES + 256 + 1024;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ATTNL_THREADS, 1)
+attention_sm100_blocked_kernel(const __grid_constant__ CUtensorMap tmap_qkv /* box {64, 64 rows} */,
+                               const __grid_constant__ CUtensorMap tmap_out /* 3-D, box {64, 128, 1} */, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nb = attnl_blocks(p.tokens);          // key blocks per head
+    const int nq = (p.tokens + 127) / 128;          // query tiles per head
+    const int last_cols = ((p.tokens - (nb - 1) * ATTNL_KB) + 15) & ~15;  // S columns of the last key block
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + nb * ATTNL_BLOCK_BYTES;
+    uint8_t* sQ = sV + nb * ATTNL_BLOCK_BYTES;      // [2 warpgroups] 128 x 128 B
+    uint8_t* sO = sQ + 2 * ATTN_Q_TILE_BYTES;       // [2 warpgroups] output staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATTN2_OSTAGE_BYTES);
+    uint64_t* kv_full = bars;          // K, V of a head landed (tx)
+    uint64_t* kv_free = bars + 1;      // both issuers are through with the head (2 arrivals)
+    uint64_t* q_full = bars + 2;       // [wg]      Q tile landed (tx)
+    uint64_t* q_free = bars + 4;       // [wg]      every MMA reading the Q tile has completed
+    uint64_t* s_full = bars + 6;       // [wg][buf] S block in TMEM
+    uint64_t* s_free = bars + 10;      // [wg][buf] pass A has read the block (128 arrivals)
+    uint64_t* p_full = bars + 14;      // [wg][buf] pass B has written P over the block (128 arrivals)
+    uint64_t* o_full = bars + 18;      // [wg]      O complete in TMEM
+    uint64_t* o_free = bars + 20;      // [wg]      O drained (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_units = p.batch * 12;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_out);
+        mbar_init(kv_full, 1);
+        mbar_init(kv_free, 2);
+        for (int w = 0; w < 2; ++w) {
+            mbar_init(&q_full[w], 1);
+            mbar_init(&q_free[w], 1);
+            mbar_init(&o_full[w], 1);
+            mbar_init(&o_free[w], 128);
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&s_full[w * 2 + b], 1);
+                mbar_init(&s_free[w * 2 + b], 128);
+                mbar_init(&p_full[w * 2 + b], 128);
+            }
+        }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t heads = 0, qcnt[2] = {0, 0};
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++heads) {
+                const int img = unit / 12, head = unit - img * 12;
+                const int row0 = img * p.tokens;
+                mbar_wait(kv_free, (heads & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full, 2 * nb * ATTNL_BLOCK_BYTES);
+                for (int j = 0; j < nb; ++j)
+                    tma_load_2d(sK + j * ATTNL_BLOCK_BYTES, &tmap_qkv, kv_full, ATTN_DIM + head * ATTN_DH, row0 + j * ATTNL_KB);
+                for (int j = 0; j < nb; ++j)
+                    tma_load_2d(sV + j * ATTNL_BLOCK_BYTES, &tmap_qkv, kv_full, 2 * ATTN_DIM + head * ATTN_DH, row0 + j * ATTNL_KB);
+                for (int t = 0; t < nq; ++t) {
+                    const int w = t & 1;
+                    mbar_wait(&q_free[w], (qcnt[w] & 1) ^ 1);
+                    ++qcnt[w];
+                    mbar_arrive_expect_tx(&q_full[w], ATTN_Q_TILE_BYTES);
+                    tma_load_2d(sQ + w * ATTN_Q_TILE_BYTES, &tmap_qkv, &q_full[w], head * ATTN_DH, row0 + t * 128);
+                    tma_load_2d(sQ + w * ATTN_Q_TILE_BYTES + ATTNL_BLOCK_BYTES, &tmap_qkv, &q_full[w], head * ATTN_DH, row0 + t * 128 + 64);
+                }
+                const int next = unit + static_cast<int>(gridDim.x);  // pull the next head's K, V towards L2
+                if (next < n_units) {
+                    const int img2 = next / 12, head2 = next - img2 * 12;
+                    for (int j = 0; j < nb; ++j) {
+                        tma_prefetch_l2_2d(&tmap_qkv, ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + j * ATTNL_KB);
+                        tma_prefetch_l2_2d(&tmap_qkv, 2 * ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + j * ATTNL_KB);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 9) {
+        // ------------------------------------------------------------ MMA issuer of warpgroup w
+        const int w = warp - 9;
+        const uint32_t tw = tmem_base + w * 192;
+        const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
+        const uint32_t q_addr = smem_u32(sQ + w * ATTN_Q_TILE_BYTES), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        uint32_t n_sfree[2] = {0, 0}, n_pfull[2] = {0, 0}, n_qfull = 0, n_ofree = 0, heads = 0;
+        auto cols_of = [&](int j) { return j == nb - 1 ? last_cols : ATTNL_KB; };
+        auto issue_s = [&](int g) {  // S block g of the tile's stream (g < nb: pass A, else pass B), key block g % nb
+            const int j = g < nb ? g : g - nb, b = g & 1;
+            if (elect_one()) {
+                const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(cols_of(j)), 0, 0);
+#pragma unroll
+                for (int k = 0; k < ATTN_DH / 16; ++k)
+                    umma_f16(tw + b * 64, desc_kmajor_sw128(q_addr, k), desc_kmajor_sw128(k_addr + j * ATTNL_BLOCK_BYTES, k), idesc_s, k != 0);
+                umma_commit(&s_full[w * 2 + b]);
+            }
+            __syncwarp();
+        };
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++heads) {
+            mbar_wait(kv_full, heads & 1);
+            for (int t = w; t < nq; t += 2) {
+                mbar_wait(&q_full[w], n_qfull & 1);
+                ++n_qfull;
+                tc_fence_after();
+                // the stream of 2 nb S blocks alternates between the two buffers; block g may be issued once
+                // the previous user of its buffer is done: a pass-A read (s_free), or a pass-B P block, whose PV
+                // MMA is issued just before it below (the tensor pipe keeps issue order)
+                issue_s(0);
+                issue_s(1);
+                for (int g = 2; g < nb + 2; ++g) {
+                    const int b = g & 1;
+                    mbar_wait(&s_free[w * 2 + b], n_sfree[b] & 1);
+                    ++n_sfree[b];
+                    tc_fence_after();
+                    issue_s(g);
+                }
+                for (int j = 0; j < nb; ++j) {
+                    const int g = nb + j, b = g & 1;
+                    mbar_wait(&p_full[w * 2 + b], n_pfull[b] & 1);
+                    ++n_pfull[b];
+                    if (j == 0) {  // O of this warpgroup's previous tile has been drained
+                        mbar_wait(&o_free[w], (n_ofree & 1) ^ 1);
+                        ++n_ofree;
+                    }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int ks_n = cols_of(j) / 16;
+                        for (int ks = 0; ks < ks_n; ++ks)
+                            umma_f16_ts(tw + 128, tw + b * 64 + ks * 8, desc_mnmajor_sw128(v_addr + j * ATTNL_BLOCK_BYTES, ks), idesc_o,
+                                        (j | ks) != 0);
+                    }
+                    __syncwarp();
+                    if (g + 2 < 2 * nb) issue_s(g + 2);
+                }
+                if (elect_one()) {
+                    umma_commit(&o_full[w]);
+                    umma_commit(&q_free[w]);
+                    if (t + 2 >= nq) umma_commit(kv_free);  // this warpgroup's last tile of the head
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax / output warpgroups
+        const int w = warp >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t tw = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + w * 192;
+        const bool storer = quarter == 0 && lane == 0;
+        uint32_t n_sfull[2] = {0, 0}, n_ofull = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const int img = unit / 12, head = unit - img * 12;
+            for (int t = w; t < nq; t += 2) {
+                // ---- pass A: exact row maximum
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                for (int g = 0; g < nb; ++g) {
+                    const int b = g & 1, key0 = g * ATTNL_KB;
+                    const int cols = g == nb - 1 ? last_cols : ATTNL_KB;
+                    mbar_wait(&s_full[w * 2 + b], n_sfull[b] & 1);
+                    ++n_sfull[b];
+                    tc_fence_after();
+                    for (int c = 0; c < cols; c += 16) {
+                        uint32_t v[16];
+                        tmem_ld_x16p(tw + b * 64 + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (key0 + c + i < p.tokens) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&s_free[w * 2 + b]);
+                }
+                const float moff = -fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
+                // ---- pass B: exponentials, P in place, row sum
+                float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < nb; ++j) {
+                    const int g = nb + j, b = g & 1, key0 = j * ATTNL_KB;
+                    const int cols = j == nb - 1 ? last_cols : ATTNL_KB;
+                    mbar_wait(&s_full[w * 2 + b], n_sfull[b] & 1);
+                    ++n_sfull[b];
+                    tc_fence_after();
+                    for (int c = 0; c < cols; c += 16) {  // P chunk (8 columns) lands on S columns already read
+                        uint32_t v[16], packed[8];
+                        tmem_ld_x16p(tw + b * 64 + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int k0 = key0 + c + 2 * i;
+                            float e0 = 0.f, e1 = 0.f;
+                            if (k0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, moff));
+                            if (k0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, moff));
+                            sum4[i & 3] += e0 + e1;
+                            packed[i] = pack2<__nv_bfloat16>(e0, e1);
+                        }
+                        tmem_st_x8p(tw + b * 64 + (c >> 1), packed);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&p_full[w * 2 + b]);
+                }
+                const float inv_sum = fast_rcp((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+                // ---- output: O / sum -> staging tile -> one TMA store (clipped at the image's last token)
+                if (storer) tma_store_wait_read<0>();   // the previous tile's store has left the staging tile
+                mbar_wait(&o_full[w], n_ofull & 1);
+                ++n_ofull;
+                tc_fence_after();
+                uint32_t r0[32], r1[32];
+                tmem_ld_x32(tw + 128, r0);
+                tmem_ld_x32(tw + 160, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_free[w]);
+                attn_bar_sync<128>(1 + w);              // ... as everybody in the warpgroup now knows
+                uint8_t* srow = sO + w * ATTN2_OSTAGE_BYTES + row * 128;
+                const uint32_t sw = lane & 7;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t x[4], y[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        x[q] = pack2<T>(__uint_as_float(r0[8 * j + 2 * q]) * inv_sum, __uint_as_float(r0[8 * j + 2 * q + 1]) * inv_sum);
+                        y[q] = pack2<T>(__uint_as_float(r1[8 * j + 2 * q]) * inv_sum, __uint_as_float(r1[8 * j + 2 * q + 1]) * inv_sum);
+                    }
+                    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<uint4*>(srow + (((4 + j) ^ sw) << 4)) = make_uint4(y[0], y[1], y[2], y[3]);
+                }
+                fence_proxy_async_smem();
+                attn_bar_sync<128>(1 + w);
+                if (storer) {
+                    tma_store_3d(&tmap_out, sO + w * ATTN2_OSTAGE_BYTES, head * ATTN_DH, t * 128, img);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (storer) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }

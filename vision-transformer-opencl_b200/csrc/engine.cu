@@ -213,10 +213,27 @@ int launch_attention_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const A
     kern<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem, st>>>(tqkv, tout, p);
     return check_launch("attention");
 }
-// tqkv: load map of the packed QKV activation (attention_load_map), tout: 3-D store map of the output
+template <typename T>
+int launch_attention_blocked_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count, cudaStream_t st) {
+    auto kern = attention_sm100_blocked_kernel<T>;
+    const int smem = attnl_smem_bytes(p.tokens);
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<std::min(p.batch * kHeads, sm_count), ATTNL_THREADS, smem, st>>>(tqkv, tout, p);
+    return check_launch("attention_blocked");
+}
+constexpr int kAttnSingleBlockMaxTokens = 224;  // up to here the whole key range of an image is one S block in TMEM
+// rows per box of the Q/K/V load map (make_tmap over the packed QKV activation) that launch_attention expects
+int attention_load_box_rows(int tokens) {
+    return tokens <= kAttnSingleBlockMaxTokens ? ((tokens + 15) / 16 * 16) / 2 : ATTNL_KB;
+}
+// tqkv: load map of the packed QKV activation with attention_load_box_rows(tokens) rows per box,
+// tout: 3-D store map of the output (make_tmap_3d, 128 rows per box)
 int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count,
                      cudaStream_t st) {
-    if (p.tokens > 224) return set_err(VIT_E_ARG, "attention: tokens=%d > 224 not supported by the single-block kernel", p.tokens);
+    if (p.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", p.tokens, ATTNL_MAX_TOKENS);
+    if (p.tokens > kAttnSingleBlockMaxTokens)
+        return prec == VIT_PREC_FP16 ? launch_attention_blocked_t<__half>(tqkv, tout, p, sm_count, st)
+                                     : launch_attention_blocked_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
     return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tqkv, tout, p, sm_count, st)
                                  : launch_attention_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
 }
@@ -440,11 +457,8 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));     // mlp_0 store + mlp_3 A load
     VIT_TRY(make_tmap(&c.tm_qkv_st, prec, c.qkv, 3 * kDim, rows, GEMM_BK, GEMM_BM)); // in_proj store
     VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
-    if (e.tokens <= 224) {
-        const int kpad = (e.tokens + 15) / 16 * 16;
-        VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, kpad / 2));          // Q/K/V half boxes
-        VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                 // per-image output tiles
-    }
+    VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(e.tokens)));  // Q/K/V boxes
+    VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                                   // per-image output tiles
     c.maps_nb = nb;
     return 0;
 }
@@ -615,7 +629,7 @@ int vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
     if (gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
     if (n <= 0 || n > e.max_batch) return set_err(VIT_E_ARG, "n=%d outside (0, max_batch=%d]", n, e.max_batch);
-    if (e.tokens > 224) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
     if (gemm_impl() != 2 && e.prec != VIT_PREC_BF16) return set_err(VIT_E_ARG, "VIT_GEMM_IMPL=1 (A/B test kernels) supports bf16 only");
     DeviceCtx& c = e.ctx[gpu_slot];
     CU_TRY(cudaSetDevice(c.device));
@@ -654,7 +668,7 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
     if (!images_nchw || !logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
     if (n == 0) return 0;
-    if (e.tokens > 224) return set_err(VIT_E_ARG, "img_size %d (%d tokens) needs the multi-block attention kernel", e.img, e.tokens);
+    if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
     const int G = static_cast<int>(e.ctx.size());
     const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
     const int per_gpu = (n + G - 1) / G;  // contiguous shards
@@ -922,7 +936,7 @@ static int op_attention_impl(const float* qkv, float* out, int batch, int tokens
     int sms = 0;
     VIT_TRY(op_begin(&sms));
     if (!qkv || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    if (tokens > 224) return set_err(VIT_E_ARG, "attention: tokens=%d > 224 not supported by the single-block kernel", tokens);
+    if (tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", tokens, ATTNL_MAX_TOKENS);
     Scratch s;
     const size_t rows = (size_t)batch * tokens;
     const int kpad = (tokens + 15) / 16 * 16;
@@ -939,7 +953,7 @@ static int op_attention_impl(const float* qkv, float* out, int batch, int tokens
     }
     VIT_TRY(s.alloc(&dout, rows * kDim * 2, true));
     CUtensorMap tq, tkv;
-    VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, kpad / 2));
+    VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(tokens)));
     VIT_TRY(make_tmap_3d(&tkv, precision, dout, kDim, tokens, batch, 128));
     AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f, nullptr};
     constexpr size_t kTraceLen = static_cast<size_t>(ATTN_TRACE_WARPS) * ATTN_TRACE_ITEMS * ATTN_TRACE_EVENTS;
