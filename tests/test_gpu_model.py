@@ -147,15 +147,21 @@ def test_plain_c_driver_on_100_images_through_the_loader(vit, oracle, tmp_path):
     from pathlib import Path
     exe = Path(vit.PKG_DIR) / "bin" / "vit_main"
     assert exe.exists(), "build with make -C vision-transformer-opencl_b200"
-    n, n_cand = 100, 150
+    n, chunk = 100, 48
     w = vit.synth_weights(224, 42)
-    cand = vit.synth_images(n_cand, 224, 7)
-    logits = oracle.forward(w, cand, 224)
-    srt = np.sort(logits, 1)
-    keep = np.flatnonzero(srt[:, -1] - srt[:, -2] > 0.12)[:n]
-    assert len(keep) == n, f"only {len(keep)} decisive images among {n_cand}"
-    imgs = np.ascontiguousarray(cand[keep])
-    probs = oracle.softmax(logits[keep])
+    sel_imgs, sel_logits, first = [], [], 0
+    while sum(len(x) for x in sel_imgs) < n and first < 10 * n:   # seeded stream, taken chunk by chunk
+        cand = vit.synth_images(chunk, 224, 7, first_index=first)
+        lg = oracle.forward(w, cand, 224)
+        srt = np.sort(lg, 1)
+        keep = np.flatnonzero(srt[:, -1] - srt[:, -2] > 0.12)
+        sel_imgs.append(cand[keep])
+        sel_logits.append(lg[keep])
+        first += chunk
+    imgs = np.ascontiguousarray(np.concatenate(sel_imgs)[:n])
+    logits = np.concatenate(sel_logits)[:n]
+    assert len(imgs) == n, f"only {len(imgs)} decisive images among {first}"
+    probs = oracle.softmax(logits)
     img_file, wdir = tmp_path / "input-100.bin", tmp_path / "Network"
     assert vit.lib.save_image_data(str(img_file).encode(), vit.fptr(imgs), n, 3, 224, 224) == 0
     assert vit.lib.save_weights(str(wdir).encode(), vit.as_network(w), 152, 224) == 0
