@@ -39,7 +39,9 @@ enum {
     VIT_E_NODEVICE    = -2,  /* no CUDA device, or device is not sm_100 */
     VIT_E_CUDA        = -3,  /* CUDA runtime/driver error (see last_error) */
     VIT_E_NOMEM       = -4,
-    VIT_E_DEVICE_TRAP = -5   /* a kernel watchdog fired (pipeline dead-lock guard) */
+    VIT_E_DEVICE_TRAP = -5,  /* a kernel watchdog fired (pipeline dead-lock guard) */
+    VIT_E_RANGE       = -6   /* vit_cuda_sync only: the single-pass softmax flagged a row (see
+                                vit_cuda_set_attention_exact); the pass must be enqueued again */
 };
 
 /* GEMM-operand storage type.  Accumulation, residual stream, LayerNorm statistics,
@@ -99,8 +101,17 @@ const char* vit_cuda_last_error(void);
  * report gpu_launches. */
 long long vit_cuda_launch_count(void);
 
+/* Softmax variant of the fused attention kernel (224x224 path).  Default (0): ONE pass over the
+ * scores with the exponent offset taken from 16 of the row's scores -- exact unless some logit
+ * exceeds those by more than ~110, which the kernel detects; vit_cuda_forward then transparently
+ * repeats the call with the exact variant, vit_cuda_sync returns VIT_E_RANGE and switches the
+ * engine over.  1: always the exact two-pass softmax (row maximum first, ViT_seq.c:178-191).
+ * The environment variable VIT_ATTN_EXACT=1 selects it at init. */
+int vit_cuda_set_attention_exact(int on);
+
 /* Facts about the engine/device, for logs: fills up to n entries of
- * {sm_count, cc_major, cc_minor, max_batch, tokens, precision, n_gpus, ws_bytes>>20}. */
+ * {sm_count, cc_major, cc_minor, max_batch, tokens, precision, n_gpus, ws_bytes>>20,
+ *  attention_exact, attention_fallbacks}. */
 int vit_cuda_info(long long* out, int n);
 
 /* CUDA-event stopwatch on a slot's stream: start records an event, stop records a second one,

@@ -18,6 +18,7 @@ struct AttnParams {
     int kpad;          // tokens rounded up to 16
     void* out;         // [batch*tokens][768], operand precision
     float scale_log2;  // (1/sqrt(64)) * log2(e)
+    int no_pingpong;   // debug / tuning: 1 = the two query tiles do not take turns on the exponentials
     unsigned long long* trace;  // optional (debug): SM-clock timestamps of CTA 0's pipeline events, see ATTN_TRACE
 };
 
@@ -100,7 +101,22 @@ __device__ __forceinline__ void attn_bar_arrive(int id) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
 }
 
-template <typename T>
+// Set (sticky) by the single-pass softmax when a row's exponent range left its safe window (see the
+// kernel): the host then repeats the work with the exact two-pass variant.
+__device__ unsigned int g_attn_range_flag = 0;
+constexpr float ATTN_FAST_SHIFT = 64.f;      // exponent head-room of the single-pass softmax (log2 units)
+constexpr float ATTN_FAST_SUM_MAX = 1.0e30f; // ~2^100: a larger row sum means the window was left
+
+// EXACT = true : two passes over S (exact row maximum first), P <= 1 as in the reference.
+// EXACT = false: ONE pass.  Softmax is shift invariant, so the exponent offset need not be the row
+//   maximum: it is m_ref = max of 16 of the row's scores (a chunk read by both halves of the row, so they
+//   agree without an exchange), lowered by 2^-64:  P_j = 2^((s_j - m_ref) c - 64).  The true maximum is
+//   >= m_ref, so the largest P is >= 2^-64 (nothing relevant underflows: bf16 and fp32 share the 8-bit
+//   exponent), and nothing overflows unless some score exceeds m_ref by more than ~160 / c (a logit
+//   gap of > 110 between a key and the best of those 16 keys).  That case is DETECTED (row sum
+//   beyond 2^100 or not finite -> g_attn_range_flag) and the host reruns with EXACT = true.
+//   TMEM reads (~64 B/clk/SM) bound this kernel, and this halves the reads of S.
+template <typename T, bool EXACT>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                                   const AttnParams p) {
@@ -260,7 +276,8 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
         const int pair_bar = 1 + t * 4 + quarter;            // named barrier of the two warps sharing these rows
         const int nsteps = ch1 - ch0;                        // 16-key chunks of this half (<= 0: none)
         const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-        if (nqt == 2 && t == 1 && my_items > 0) attn_bar_arrive<512>(11);  // tile 0 exponentiates first
+        const bool pingpong = nqt == 2 && !p.no_pingpong;
+        if (pingpong && t == 1 && my_items > 0) attn_bar_arrive<512>(11);  // tile 0 exponentiates first
         float* my_max = xmax + (t * 2 + half) * 128 + row;
         const float* other_max = xmax + (t * 2 + (half ^ 1)) * 128 + row;
         int it = 0;
@@ -277,11 +294,12 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
             uint32_t ra[16], rb[16];
             float mx = 0.f;
             if (warp_active) {
+              if constexpr (EXACT) {
                 // Two passes over this half's S columns: pass 1 finds the exact row maximum (tcgen05.ld + max
                 // only), pass 2 is a straight stream  tcgen05.ld -> FFMA -> ex2 -> add / pack -> tcgen05.st  with
                 // no vote, branch or rescale.  With the true maximum every P is <= 1, exactly as in the
                 // reference's softmax (ViT_seq.c:178-191).  Cost: S is read twice, and TMEM reads (~64 B/clk/SM)
-                // are this kernel's ceiling -- see profiles/r1_attention_trace.md for the single-pass plan.
+                // are this kernel's ceiling (profiles/r1_attention_trace.md).
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 {
                     int c = ch0;
@@ -316,13 +334,36 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
                     attn_bar_sync<64>(pair_bar);
                     mx = fmaxf(mx, *other_max);
                 }
+              } else {
+                // m_ref = max of the 16 scores of half A's LAST chunk, read by both halves of the row.  That
+                // chunk's columns never receive P (chunk c's P lands on columns [8c, 8c+8) < 8 * chunks of A)
+                // and become part of O only after every thread has arrived at p_full, so both halves see the
+                // same 16 scores whatever their relative progress.  The first chunk of the stream is fetched
+                // by the same round trip.
+                const int cm = (nch < 8 ? nch : 8) - 1;
+                tmem_ld_x16p(taddr + cm * 16, rb);
+                if (nsteps > 0) tmem_ld_x16p(taddr + ch0 * 16, ra);
+                tmem_ld_wait();
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (cm * 16 + 16 <= p.tokens) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (cm * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rb[j]));
+                }
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                ATTN_TRACE(warp, it, 6);
+              }
             }
             // Ping-pong: the exponentials of the two query tiles take turns on the MUFU pipe, so that one
             // tile's MMA round trips, maximum pass and output epilogue run under the other tile's
             // exponentials instead of both tiles computing and then both waiting.
-            if (nqt == 2) attn_bar_sync<512>(11 + t);
+            if (pingpong) attn_bar_sync<512>(11 + t);
             if (warp_active) {
-                const float moff = -mx * p.scale_log2;
+                const float moff = EXACT ? -mx * p.scale_log2 : fmaf(-mx, p.scale_log2, -ATTN_FAST_SHIFT);
                 ATTN_TRACE(warp, it, 7);
                 float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
                 auto exp_step = [&](const uint32_t* v, int c) {
@@ -368,7 +409,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
                 }
                 *my_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
             }
-            if (nqt == 2 && (t == 0 || it + 1 < my_items)) attn_bar_arrive<512>(11 + (t ^ 1));  // the other tile's turn
+            if (pingpong && (t == 0 || it + 1 < my_items)) attn_bar_arrive<512>(11 + (t ^ 1));  // the other tile's turn
             if (warp_active) {
                 tmem_st_wait();
                 tc_fence_before();
@@ -386,7 +427,11 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
                 // both halves' row sums were written before their p_full arrivals (release), which the PV
                 // MMA behind o_full waited for; the buffer alternates per item, so a fast partner cannot
                 // overwrite it before this read
-                const float inv_sum = fast_rcp(*my_sum + *other_sum);  // a half without keys wrote 0
+                const float row_sum = *my_sum + *other_sum;  // a half without keys wrote 0
+                if constexpr (!EXACT) {
+                    if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN
+                }
+                const float inv_sum = fast_rcp(row_sum);
                 uint32_t r0[32];
                 tmem_ld_x32(oaddr, r0);
                 tmem_ld_wait();

@@ -118,6 +118,15 @@ int check_launch(const char* what) {
     return 0;
 }
 
+int attn_no_pingpong() {  // VIT_ATTN_NO_PINGPONG=1: tuning switch of the attention kernel (A/B testing)
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("VIT_ATTN_NO_PINGPONG");
+        v = (s && atoi(s) != 0) ? 1 : 0;
+    }
+    return v;
+}
+
 constexpr int kPairStages = 6;
 int gemm_impl() {  // VIT_GEMM_IMPL=1 selects the single-CTA 128x256 kernel (A/B testing)
     static int impl = -1;
@@ -205,9 +214,9 @@ int launch_gemm(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
                                  : launch_gemm_t<__nv_bfloat16, EPI>(ta, tb, p, sm_count, st);
 }
 
-template <typename T>
+template <typename T, bool EXACT>
 int launch_attention_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count, cudaStream_t st) {
-    auto kern = attention_sm100_persistent_kernel<T>;
+    auto kern = attention_sm100_persistent_kernel<T, EXACT>;
     const int smem = attn2_smem_bytes(p.kpad);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem, st>>>(tqkv, tout, p);
@@ -228,14 +237,30 @@ int attention_load_box_rows(int tokens) {
 }
 // tqkv: load map of the packed QKV activation with attention_load_box_rows(tokens) rows per box,
 // tout: 3-D store map of the output (make_tmap_3d, 128 rows per box)
+// exact: two-pass softmax (exact row maximum); otherwise the single-pass variant, which raises
+// g_attn_range_flag when a row left its exponent window (the caller then repeats with exact = true)
 int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool exact) {
     if (p.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", p.tokens, ATTNL_MAX_TOKENS);
     if (p.tokens > kAttnSingleBlockMaxTokens)
         return prec == VIT_PREC_FP16 ? launch_attention_blocked_t<__half>(tqkv, tout, p, sm_count, st)
                                      : launch_attention_blocked_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
-    return prec == VIT_PREC_FP16 ? launch_attention_t<__half>(tqkv, tout, p, sm_count, st)
-                                 : launch_attention_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
+    if (exact)
+        return prec == VIT_PREC_FP16 ? launch_attention_t<__half, true>(tqkv, tout, p, sm_count, st)
+                                     : launch_attention_t<__nv_bfloat16, true>(tqkv, tout, p, sm_count, st);
+    return prec == VIT_PREC_FP16 ? launch_attention_t<__half, false>(tqkv, tout, p, sm_count, st)
+                                 : launch_attention_t<__nv_bfloat16, false>(tqkv, tout, p, sm_count, st);
+}
+// Reads and clears the current device's range flag (after the stream has been synchronised).
+int take_attn_range_flag(bool* was_set) {
+    unsigned int v = 0;
+    CU_TRY(cudaMemcpyFromSymbol(&v, g_attn_range_flag, sizeof(v)));
+    *was_set = v != 0;
+    if (v) {
+        v = 0;
+        CU_TRY(cudaMemcpyToSymbol(g_attn_range_flag, &v, sizeof(v)));
+    }
+    return 0;
 }
 
 int launch_layernorm(int prec, const float* x, const float* w, const float* b, void* y, int rows, cudaStream_t st) {
@@ -331,6 +356,8 @@ struct DeviceCtx {
 struct Engine {
     bool up = false;
     bool profiling = false;
+    bool attn_exact = false;      // two-pass softmax (VIT_ATTN_EXACT=1, vit_cuda_set_attention_exact, or after a range flag)
+    long long attn_fallbacks = 0; // forwards repeated with the exact softmax
     int img = 0, grid = 0, patches = 0, tokens = 0, max_batch = 0, prec = 0;
     std::vector<DeviceCtx> ctx;
 };
@@ -506,7 +533,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
         VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
     }
-    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, nullptr};
+    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
         {
@@ -521,7 +548,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         }
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
-            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, c.sm_count, st));
+            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, c.sm_count, st, e.attn_exact));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
@@ -605,6 +632,11 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size, in
     e.tokens = e.patches + 1;
     e.max_batch = max_batch_per_gpu;
     e.prec = precision;
+    {
+        const char* ex = getenv("VIT_ATTN_EXACT");
+        e.attn_exact = ex && atoi(ex) != 0;
+        e.attn_fallbacks = 0;
+    }
     e.ctx.assign(n_gpus, DeviceCtx());
     for (int g = 0; g < n_gpus; ++g) {
         const int rc = init_ctx(e.ctx[g], device_ids ? device_ids[g] : g, networks, e);
@@ -642,6 +674,22 @@ int vit_cuda_sync(int gpu_slot) {
     CU_TRY(cudaSetDevice(e.ctx[gpu_slot].device));
     const cudaError_t se = cudaStreamSynchronize(e.ctx[gpu_slot].stream);
     if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
+    if (!e.attn_exact) {
+        bool flagged = false;
+        VIT_TRY(take_attn_range_flag(&flagged));
+        if (flagged) {
+            e.attn_exact = true;  // device-resident callers re-enqueue; the engine stays on the exact softmax
+            ++e.attn_fallbacks;
+            return set_err(VIT_E_RANGE, "attention: a row's scores left the single-pass softmax's exponent window; the results of "
+                                        "this pass are invalid.  The engine has switched to the exact two-pass softmax: enqueue again");
+        }
+    }
+    return 0;
+}
+
+int vit_cuda_set_attention_exact(int on) {
+    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
+    g_eng.attn_exact = on != 0;
     return 0;
 }
 
@@ -663,11 +711,38 @@ int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi) {
     return 0;
 }
 
+static int forward_host_once(const float* images_nchw, int n, float* logits_out, bool* range_flag);
+
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out) {
     Engine& e = g_eng;
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
     if (!images_nchw || !logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
     if (n == 0) return 0;
+    bool flagged = false;
+    VIT_TRY(forward_host_once(images_nchw, n, logits_out, &flagged));
+    if (flagged) {
+        // some row left the single-pass softmax's exponent window: repeat with the exact two-pass softmax
+        // (and stay there once this has happened three times -- the data evidently does it regularly)
+        ++e.attn_fallbacks;
+        e.attn_exact = true;
+        const int rc = forward_host_once(images_nchw, n, logits_out, &flagged);
+        if (e.attn_fallbacks < 3) e.attn_exact = false;
+        VIT_TRY(rc);
+    }
+    if (top1_out)
+        for (int i = 0; i < n; ++i) {
+            const float* row = logits_out + static_cast<size_t>(i) * kClasses;
+            int best = 0;
+            for (int j = 1; j < kClasses; ++j)
+                if (row[j] > row[best]) best = j;
+            top1_out[i] = best;
+        }
+    return 0;
+}
+
+static int forward_host_once(const float* images_nchw, int n, float* logits_out, bool* range_flag) {
+    Engine& e = g_eng;
+    *range_flag = false;
     if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
     const int G = static_cast<int>(e.ctx.size());
     const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
@@ -704,15 +779,12 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
         CU_TRY(cudaSetDevice(c.device));
         const cudaError_t se = cudaStreamSynchronize(c.stream);
         if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
-    }
-    if (top1_out)
-        for (int i = 0; i < n; ++i) {
-            const float* row = logits_out + static_cast<size_t>(i) * kClasses;
-            int best = 0;
-            for (int j = 1; j < kClasses; ++j)
-                if (row[j] > row[best]) best = j;
-            top1_out[i] = best;
+        if (!e.attn_exact) {
+            bool f = false;
+            VIT_TRY(take_attn_range_flag(&f));
+            *range_flag |= f;
         }
+    }
     return 0;
 }
 
@@ -721,9 +793,10 @@ int vit_cuda_info(long long* out, int n) {
     const DeviceCtx& c = g_eng.ctx[0];
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, c.device));
-    const long long v[8] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
-                            (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20)};
-    for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+    const long long v[10] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
+                             (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20), g_eng.attn_exact ? 1 : 0,
+                             g_eng.attn_fallbacks};
+    for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
     return 0;
 }
 
@@ -955,11 +1028,21 @@ static int op_attention_impl(const float* qkv, float* out, int batch, int tokens
     CUtensorMap tq, tkv;
     VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(tokens)));
     VIT_TRY(make_tmap_3d(&tkv, precision, dout, kDim, tokens, batch, 128));
-    AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f, nullptr};
+    AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
     constexpr size_t kTraceLen = static_cast<size_t>(ATTN_TRACE_WARPS) * ATTN_TRACE_ITEMS * ATTN_TRACE_EVENTS;
     if (trace_out) VIT_TRY(s.alloc(reinterpret_cast<void**>(&p.trace), kTraceLen * 8, true));
-    VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr));
+    const char* ex = getenv("VIT_ATTN_EXACT");
+    bool exact = ex && atoi(ex) != 0;
+    VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr, exact));
     VIT_TRY(op_end("op_attention"));
+    if (!exact && !trace_out) {  // same contract as vit_cuda_forward: repeat with the exact softmax when flagged
+        bool flagged = false;
+        VIT_TRY(take_attn_range_flag(&flagged));
+        if (flagged) {
+            VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr, true));
+            VIT_TRY(op_end("op_attention"));
+        }
+    }
     if (trace_out)
         CU_TRY(cudaMemcpy(trace_out, p.trace, std::min(kTraceLen, static_cast<size_t>(std::max(trace_len, 0))) * 8,
                           cudaMemcpyDeviceToHost));
