@@ -168,6 +168,22 @@ enum {
 int vit_cuda_op_linear(const float* x, const float* W, const float* b, const float* residual,
                        float* y, int m, int n, int k, int epilogue, int precision);
 
+/* LayerNorm folded into the following linear layer, as the forward pass runs in_proj and mlp_0:
+ * y = epilogue(LN(x; ln_w, ln_b) W^T + b) for x [m][768] fp32, W [n][768], epilogue VIT_EPI_BIAS or
+ * VIT_EPI_BIAS_GELU.  The GEMM multiplies the operand-precision copy of the RAW rows by the folded
+ * weights ln_w (.) W and applies the row statistics in its epilogue (csrc/gemm_sm100.cuh).
+ * Replaces layer_norm + linear_layer, ViT_seq.c:103-121 + 240-250 (called at :281-283, :291-294). */
+int vit_cuda_op_ln_linear(const float* x, const float* ln_w, const float* ln_b, const float* W,
+                          const float* b, float* y, int m, int n, int epilogue, int precision);
+
+/* The residual GEMM in its LayerNorm-producer form (out_proj / mlp_3 of the forward pass):
+ * y = residual + x W^T + b  (fp32, [m][768]; x [m][k], W [768][k]), plus what the next folded GEMM
+ * needs: y_cast = y rounded to the operand precision (widened back to fp32 here) and the per-row
+ * sum and sum of squares of y (added up in the consumer's order). */
+int vit_cuda_op_linear_residual_stats(const float* x, const float* W, const float* b,
+                                      const float* residual, float* y, float* y_cast,
+                                      float* row_sum, float* row_sumsq, int m, int k, int precision);
+
 /* LayerNorm rows of x [rows][768] (fp32) -> y [rows][768] (operand precision widened to
  * fp32).  Replaces layer_norm, ViT_seq.c:103-121 / layer_norm_kernel, kernel.cl:6-80
  * (with the oracle's eps 1e-6, which the OpenCL kernel drops). */

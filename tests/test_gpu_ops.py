@@ -68,6 +68,56 @@ def test_linear_bias_residual(vit, oracle, prec, m, n, k):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("m,n,epi", [(197, 2304, "bias"), (197, 3072, "gelu"), (1000, 2304, "bias"), (333, 3072, "gelu")])
+def test_layernorm_folded_into_linear(vit, oracle, prec, m, n, epi):
+    """in_proj / mlp_0 as the forward pass runs them: LayerNorm folded into the GEMM (raw rows in operand
+    precision x folded weights, row statistics applied in the epilogue) against the oracle's
+    layer_norm -> linear (-> gelu) on the same fp32 rows.  The rows carry a mean of 0.3 sigma and channel-
+    dependent scales, the LayerNorm weights are far from 1: all of that must cancel.  Tolerance: operand
+    rounding of x and W' over K = 768 (no pre-rounded inputs are possible here -- the kernel rounds the raw
+    row, the oracle path would round the normalised one) plus the output rounding."""
+    rng = np.random.default_rng(40 + m + n)
+    x = (rng.standard_normal((m, 768)) * rng.uniform(0.2, 3.0, 768) + 0.3).astype(np.float32)
+    ln_w = rng.uniform(0.05, 1.5, 768).astype(np.float32)
+    ln_b = (rng.standard_normal(768) * 0.2).astype(np.float32)
+    W = (rng.standard_normal((n, 768)) * 0.03).astype(np.float32)
+    b = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    got = vit.op_ln_linear(x, ln_w, ln_b, W, b, epilogue=vit.EPI_BIAS_GELU if epi == "gelu" else vit.EPI_BIAS, precision=prec)
+    ref = oracle.linear(oracle.layer_norm(x, ln_w, ln_b), W, b)
+    if epi == "gelu":
+        ref = oracle.gelu(ref)
+    # two operand roundings per product, 768 products of typical size |xn W| ~ 0.03 -> rms error ~ eps * 0.03 * sqrt(768)
+    eps = 2.0 ** -8 if prec == 0 else 2.0 ** -11
+    atol = 6 * eps * 0.03 * np.sqrt(768) * float(np.abs(ln_w).max())
+    _close(got, ref, OUT_RTOL[prec], atol, f"LN-folded linear {m}x{n} {epi}")
+    # and it must be as accurate as the unfused pair of kernels is
+    unfused = vit.op_linear(vit.op_layernorm(x, ln_w, ln_b, precision=prec), round_operand(W, prec), b,
+                            epilogue=vit.EPI_BIAS_GELU if epi == "gelu" else vit.EPI_BIAS, precision=prec)
+    e_f, e_u = np.abs(got - ref), np.abs(unfused - ref)
+    assert e_f.mean() <= 1.5 * e_u.mean() + 1e-6, (e_f.mean(), e_u.mean())
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("m,k", [(197, 768), (197, 3072), (600, 3072)])
+def test_linear_residual_emits_cast_copy_and_row_statistics(vit, oracle, prec, m, k):
+    """out_proj / mlp_3 in their LayerNorm-producer form: besides the fp32 residual row they emit its
+    operand-precision copy and (sum, sum of squares), which the next folded GEMM consumes."""
+    x = round_operand(_rand((m, k), 51), prec)
+    W = round_operand(_rand((768, k), 52, 0.03), prec)
+    b = _rand((768,), 53, 0.1)
+    r = _rand((m, 768), 54) * 2 + 0.25
+    y, yc, s1, s2 = vit.op_linear_residual_stats(x, W, b, r, precision=prec)
+    ref = r + oracle.linear(x, W, b)
+    _close(y, ref, 1e-5, 3e-4, f"residual producer {m}x768x{k}")
+    assert np.array_equal(yc, round_operand(y, prec)), "operand-precision copy is not the rounding of the fp32 row"
+    y64 = y.astype(np.float64)
+    assert np.allclose(s1, y64.sum(1), rtol=2e-6, atol=2e-4) and np.allclose(s2, (y64 * y64).sum(1), rtol=2e-6, atol=2e-4)
+    # bit-identical to the plain residual kernel
+    plain = vit.op_linear(x, W, b, residual=r, epilogue=vit.EPI_BIAS_RESIDUAL, precision=prec)
+    assert np.array_equal(plain, y)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("rows", [1, 197, 1000])
 def test_layernorm(vit, oracle, prec, rows):
     x = _rand((rows, 768), 11, 2.0) + 0.5

@@ -1,8 +1,6 @@
-python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "attention" > gpurun_out/t4_pytest_attn.log 2>&1; echo "attn rc=$?"; tail -2 gpurun_out/t4_pytest_attn.log
-VIT_ATTN_NO_PINGPONG=1 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "attention" > gpurun_out/t4_pytest_attn_np.log 2>&1; echo "attn(no pingpong) rc=$?"; tail -2 gpurun_out/t4_pytest_attn_np.log
-for v in 0 1; do
-VIT_ATTN_NO_PINGPONG=$v python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/t4_bench_np$v.json 2> gpurun_out/t4_bench.err; echo "bench rc=$?"
+python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "linear or folded or residual" > gpurun_out/t10_ops.log 2>&1; echo "ops rc=$?"; tail -2 gpurun_out/t10_ops.log
+for cfg in "1 0" "1 4" "0 0" "0 5"; do set -- $cfg
+VIT_LN_FUSED=$1 VIT_RES_CFG=$2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/t10_bench_$1_$2.json 2> gpurun_out/t10_bench.err; echo "bench fused=$1 cfg=$2 rc=$?"
 python -c "
-import json;d=json.load(open('gpurun_out/t4_bench_np$v.json'));print(d['value'],d['ms_per_step'],d['step_breakdown_ms']['attention'],d['clocks'])"
+import json;d=json.load(open('gpurun_out/t10_bench_$1_$2.json'));print(d['value'],d['ms_per_step'],{k:round(v,2) for k,v in d['step_breakdown_ms'].items()},d['clocks']['sm_mhz'])"
 done
-VIT_ATTN_NO_PINGPONG=1 python tools/attn_trace.py 160 197 > gpurun_out/t4_trace_np.log 2>&1

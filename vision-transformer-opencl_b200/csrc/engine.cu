@@ -155,12 +155,17 @@ int launch_gemm_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 }
 
 constexpr int kStagedStages = 5, kStagedSlots = 4;
-template <typename T, int EPI>
-int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
-                         int sm_count, cudaStream_t st) {
-    using L = GemmStagedSmem<kStagedStages, kStagedSlots>;
+// LN = true: LayerNorm folded into the GEMM (consumer for EPI_BIAS / EPI_BIAS_GELU, producer for
+// EPI_BIAS_RESIDUAL, see gemm_sm100.cuh).  The producer gives one operand stage up for the two
+// staging tiles of the operand-precision copy.
+template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL)>
+int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
+                           const GemmParams& p, int sm_count, cudaStream_t st) {
+    constexpr int kPreFloats = !PSTAGED ? 0 : (LN ? 256 + 256 + 2 * 128 : 256);
+    using L = GemmStagedSmem<STAGES, SLOTS, CAST, kPreFloats * 4>;
+    static_assert(L::DYN_BYTES <= 232448, "shared memory budget");
     constexpr int kEpiWarps = 8;  // 16 was measured no faster for the GELU epilogue (issue bound, not latency bound)
-    auto kern = gemm_sm100_staged_kernel<T, kStagedStages, kStagedSlots, EPI, kEpiWarps>;
+    auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED>;
     static int configured_dev_mask = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -170,17 +175,58 @@ int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     }
     if (p.N % kGemmBN || p.K % GEMM_BK || p.M <= 0)
         return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64)", p.M, p.N, p.K);
+    if (LN && (EPI == EPI_BIAS_RESIDUAL ? (p.N != kDim || !p.stats_out) : (p.K != kDim || !p.stats_in || !p.colsum || p.stats_parts <= 0)))
+        return set_err(VIT_E_ARG, "LayerNorm-folded gemm: bad statistics arguments (N=%d K=%d)", p.N, p.K);
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int grid = 2 * std::min(tiles, sm_count / 2);
-    kern<<<grid, (GEMM_NON_EPI_WARPS + kEpiWarps) * 32, L::DYN_BYTES, st>>>(ta, tb, tout, p);
+    kern<<<grid, (GEMM_NON_EPI_WARPS + kEpiWarps) * 32, L::DYN_BYTES, st>>>(ta, tb, tout, tcast, p);
     return check_launch("gemm_staged");
+}
+int res_cfg() {  // VIT_RES_CFG: A/B switch of the residual GEMM's shared-memory split (tuning)
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("VIT_RES_CFG");
+        v = s ? atoi(s) : 0;
+    }
+    return v;
+}
+// LN = true: LayerNorm folded into the GEMM (consumer for EPI_BIAS / EPI_BIAS_GELU, producer for
+// EPI_BIAS_RESIDUAL, see gemm_sm100.cuh).  The producer pays for the staging tiles of the
+// operand-precision copy with an operand stage or a residual slot.
+template <typename T, int EPI, bool LN>
+int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
+                         const GemmParams& p, int sm_count, cudaStream_t st) {
+    if constexpr (LN && EPI == EPI_BIAS_RESIDUAL) {
+        // Measured (B = 1024): mlp_3 (K = 3072, tensor bound) needs the fifth operand stage (4 stages: +9 %) and
+        // is indifferent to the slot count; out_proj (K = 768, HBM bound) needs the four residual slots to keep
+        // enough chunk loads in flight (3 slots: +23 %) and is indifferent to the stage count.
+        if ((p.K >= 2048) != (res_cfg() == 1)) return launch_gemm_staged_cfg<T, EPI, LN, 5, 3, 1>(ta, tb, tout, tcast, p, sm_count, st);
+        return launch_gemm_staged_cfg<T, EPI, LN, 4, 4, 2>(ta, tb, tout, tcast, p, sm_count, st);
+    } else if constexpr (EPI == EPI_BIAS_RESIDUAL) {
+        return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0>(ta, tb, tout, tcast, p, sm_count, st);
+    } else if constexpr (LN) {
+        // 6 KB of staged parameters cost one output slot; loading them in the epilogue threads instead (4 slots)
+        // measured 7 % slower on mlp_0
+        if (res_cfg() == 4) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, false>(ta, tb, tout, tcast, p, sm_count, st);
+        return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, 3, 0, true>(ta, tb, tout, tcast, p, sm_count, st);
+    } else {
+        if (res_cfg() == 5) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, false>(ta, tb, tout, tcast, p, sm_count, st);
+        return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, true>(ta, tb, tout, tcast, p, sm_count, st);
+    }
 }
 // tout: store map of the output (for the residual epilogue also the load map of the residual, in place)
 template <int EPI>
 int launch_gemm_staged(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
                        int sm_count, cudaStream_t st) {
-    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI>(ta, tb, tout, p, sm_count, st)
-                                 : launch_gemm_staged_t<__nv_bfloat16, EPI>(ta, tb, tout, p, sm_count, st);
+    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, false>(ta, tb, tout, tout, p, sm_count, st)
+                                 : launch_gemm_staged_t<__nv_bfloat16, EPI, false>(ta, tb, tout, tout, p, sm_count, st);
+}
+// LayerNorm-folded variants; tcast: store map of the operand-precision copy (producer only)
+template <int EPI>
+int launch_gemm_staged_ln(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
+                          const GemmParams& p, int sm_count, cudaStream_t st) {
+    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, true>(ta, tb, tout, tcast, p, sm_count, st)
+                                 : launch_gemm_staged_t<__nv_bfloat16, EPI, true>(ta, tb, tout, tcast, p, sm_count, st);
 }
 
 template <typename T, int EPI>
@@ -270,6 +316,23 @@ int launch_layernorm(int prec, const float* x, const float* w, const float* b, v
     return check_launch("layernorm");
 }
 
+int launch_rowstats_cast(int prec, const float* x, void* y, float2* stats, int rows, cudaStream_t st) {
+    const int grid = (rows + 7) / 8;
+    if (prec == VIT_PREC_FP16) rowstats_cast_kernel<__half><<<grid, 256, 0, st>>>(x, static_cast<__half*>(y), stats, rows);
+    else rowstats_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(y), stats, rows);
+    return check_launch("rowstats_cast");
+}
+
+int launch_fold_ln(int prec, const float* W, const float* ln_w, const float* ln_b, const float* bias, void* Wp, float* colsum,
+                   float* cvec, int N, cudaStream_t st) {
+    const int grid = (N + 7) / 8;
+    if (prec == VIT_PREC_FP16)
+        fold_ln_weights_kernel<__half><<<grid, 256, 0, st>>>(W, ln_w, ln_b, bias, static_cast<__half*>(Wp), colsum, cvec, N);
+    else
+        fold_ln_weights_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(W, ln_w, ln_b, bias, static_cast<__nv_bfloat16*>(Wp), colsum, cvec, N);
+    return check_launch("fold_ln_weights");
+}
+
 int launch_patchify(int prec, const float* img, void* patches, int batch, int S, int sm_count, cudaStream_t st) {
     const size_t total4 = static_cast<size_t>(batch) * 3 * S * S / 4;
     const int grid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(sm_count) * 16));
@@ -324,6 +387,10 @@ struct LayerW {
     float *ln1_w, *ln1_b, *qkv_b, *out_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;  // fp32
     void *qkv_w, *out_w, *fc1_w, *fc2_w;                                    // operand precision
     CUtensorMap tm_qkv_w, tm_out_w, tm_fc1_w, tm_fc2_w;
+    // LayerNorm folded into in_proj / mlp_0: W' = ln_w (.) W, column sums of W', c = bias + W ln_b
+    void *qkv_wf = nullptr, *fc1_wf = nullptr;
+    float *qkv_s = nullptr, *qkv_c = nullptr, *fc1_s = nullptr, *fc1_c = nullptr;
+    CUtensorMap tm_qkv_wf, tm_fc1_wf;
 };
 
 struct DeviceCtx {
@@ -342,6 +409,8 @@ struct DeviceCtx {
     float* images[2] = {nullptr, nullptr};
     void *patches = nullptr, *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr;
     float *x = nullptr, *cls_ln = nullptr, *logits = nullptr;
+    float2* pstats = nullptr;  // [6][max rows] partial (sum, sum of squares) of the residual rows (LN folding)
+    size_t stats_rows = 0;
     // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
     // use, so TMA zero-fills loads and clips stores past the last image
     int maps_nb = -1;
@@ -356,6 +425,7 @@ struct DeviceCtx {
 struct Engine {
     bool up = false;
     bool profiling = false;
+    bool ln_fused = true;         // LayerNorm folded into the GEMMs (VIT_LN_FUSED=0: separate LayerNorm kernels)
     bool attn_exact = false;      // two-pass softmax (VIT_ATTN_EXACT=1, vit_cuda_set_attention_exact, or after a range flag)
     long long attn_fallbacks = 0; // forwards repeated with the exact softmax
     int img = 0, grid = 0, patches = 0, tokens = 0, max_batch = 0, prec = 0;
@@ -381,6 +451,16 @@ int upload_operand(DeviceCtx& c, void** dst, const vit_tensor& t, float* scratch
     VIT_TRY(dev_alloc(c, dst, t.size * 2, false));
     CU_TRY(cudaMemcpyAsync(scratch, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, c.stream));
     return launch_convert_from_f32(prec, scratch, *dst, t.size, c.stream);
+}
+
+// Folded copy of a [N][768] weight whose fp32 values are still in `scratch` (just uploaded by
+// upload_operand): W' = ln_w (.) W in the operand precision, its column sums and c = bias + W ln_b.
+int upload_folded(DeviceCtx& c, void** wf, float** colsum, float** cvec, const float* scratch, const float* ln_w,
+                  const float* ln_b, const float* bias, int N, int prec) {
+    VIT_TRY(dev_alloc(c, wf, static_cast<size_t>(N) * kDim * 2, false));
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(colsum), static_cast<size_t>(N) * 4, false));
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(cvec), static_cast<size_t>(N) * 4, false));
+    return launch_fold_ln(prec, scratch, ln_w, ln_b, bias, *wf, *colsum, *cvec, N, c.stream);
 }
 
 void destroy_ctx(DeviceCtx& c) {
@@ -432,18 +512,22 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
             if ((rc = upload_f32(c, &L.ln1_b, lw[1]))) break;
             if ((rc = upload_operand(c, &L.qkv_w, lw[2], scratch, prec))) break;
             if ((rc = upload_f32(c, &L.qkv_b, lw[3]))) break;
+            if ((rc = upload_folded(c, &L.qkv_wf, &L.qkv_s, &L.qkv_c, scratch, L.ln1_w, L.ln1_b, L.qkv_b, 3 * kDim, prec))) break;
             if ((rc = upload_operand(c, &L.out_w, lw[4], scratch, prec))) break;
             if ((rc = upload_f32(c, &L.out_b, lw[5]))) break;
             if ((rc = upload_f32(c, &L.ln2_w, lw[6]))) break;
             if ((rc = upload_f32(c, &L.ln2_b, lw[7]))) break;
             if ((rc = upload_operand(c, &L.fc1_w, lw[8], scratch, prec))) break;
             if ((rc = upload_f32(c, &L.fc1_b, lw[9]))) break;
+            if ((rc = upload_folded(c, &L.fc1_wf, &L.fc1_s, &L.fc1_c, scratch, L.ln2_w, L.ln2_b, L.fc1_b, kHidden, prec))) break;
             if ((rc = upload_operand(c, &L.fc2_w, lw[10], scratch, prec))) break;
             if ((rc = upload_f32(c, &L.fc2_b, lw[11]))) break;
             if ((rc = make_tmap(&L.tm_qkv_w, prec, L.qkv_w, kDim, 3 * kDim, GEMM_BK, 128))) break;
             if ((rc = make_tmap(&L.tm_out_w, prec, L.out_w, kDim, kDim, GEMM_BK, 128))) break;
             if ((rc = make_tmap(&L.tm_fc1_w, prec, L.fc1_w, kDim, kHidden, GEMM_BK, 128))) break;
             if ((rc = make_tmap(&L.tm_fc2_w, prec, L.fc2_w, kHidden, kDim, GEMM_BK, 128))) break;
+            if ((rc = make_tmap(&L.tm_qkv_wf, prec, L.qkv_wf, kDim, 3 * kDim, GEMM_BK, 128))) break;
+            if ((rc = make_tmap(&L.tm_fc1_wf, prec, L.fc1_wf, kDim, kHidden, GEMM_BK, 128))) break;
         }
         if (rc) break;
         if ((rc = upload_f32(c, &c.lnf_w, w[148]))) break;
@@ -469,6 +553,8 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
     VIT_TRY(dev_alloc(c, &c.ao, rows * kDim * 2, true));
     VIT_TRY(dev_alloc(c, &c.hid, rows * kHidden * 2, true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.cls_ln), B * kDim * 4, true));
+    c.stats_rows = (rows + 255) / 256 * 256;
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.pstats), 6 * c.stats_rows * sizeof(float2), true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.logits), B * kClasses * 4, true));
     CU_TRY(cudaStreamSynchronize(c.stream));
     return 0;
@@ -534,16 +620,32 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
     }
     AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
+    // LayerNorm folded into the GEMMs (default): in_proj / mlp_0 read the operand-precision copy of the raw
+    // residual rows (c.xn) with the per-row statistics (c.pstats) that the previous residual GEMM -- for
+    // layer 0 the rowstats_cast kernel -- left behind.  Otherwise: a LayerNorm kernel before each of them.
+    const bool fused = staged && e.ln_fused;
+    const int stats_rows = static_cast<int>(c.stats_rows);
+    if (fused) {
+        ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
+        VIT_TRY(launch_rowstats_cast(prec, c.x, c.xn, c.pstats, rows, st));
+    }
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
-        {
+        if (!fused) {
             ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
             VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
             GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 2 * kDim};  // V block stored as bf16
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, p, c.sm_count, st));
+            if (fused) {
+                p.bias = L.qkv_c;
+                p.colsum = L.qkv_s;
+                p.stats_in = c.pstats;
+                p.stats_parts = l == 0 ? 1 : 6;
+                p.stats_rows = stats_rows;
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
         }
         {
@@ -553,23 +655,38 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         {
             ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
             GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x, 0, 0};
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, p, c.sm_count, st));
+            if (fused) {
+                p.stats_out = c.pstats;
+                p.stats_rows = stats_rows;
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
         }
-        {
+        if (!fused) {
             ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
             VIT_TRY(launch_layernorm(prec, c.x, L.ln2_w, L.ln2_b, c.xn, rows, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
             GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr, 0, 0};
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, c.tm_hid, p, c.sm_count, st));
+            if (fused) {
+                p.bias = L.fc1_c;
+                p.colsum = L.fc1_s;
+                p.stats_in = c.pstats;
+                p.stats_parts = 6;
+                p.stats_rows = stats_rows;
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_wf, c.tm_hid, c.tm_hid, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, c.tm_hid, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
             GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x, 0, 0};
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, p, c.sm_count, st));
+            if (fused && l + 1 < kDepth) {   // the last layer's output only feeds the class-row LayerNorm of the head
+                p.stats_out = c.pstats;
+                p.stats_rows = stats_rows;
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
         }
     }
@@ -636,6 +753,8 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size, in
         const char* ex = getenv("VIT_ATTN_EXACT");
         e.attn_exact = ex && atoi(ex) != 0;
         e.attn_fallbacks = 0;
+        const char* lf = getenv("VIT_LN_FUSED");
+        e.ln_fused = !(lf && atoi(lf) == 0);
     }
     e.ctx.assign(n_gpus, DeviceCtx());
     for (int g = 0; g < n_gpus; ++g) {
@@ -986,6 +1105,88 @@ int vit_cuda_op_linear(const float* x, const float* W, const float* b, const flo
         VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
     }
     return op_end("op_linear");
+}
+
+int vit_cuda_op_ln_linear(const float* x, const float* ln_w, const float* ln_b, const float* W, const float* b, float* y, int m,
+                          int n, int epilogue, int precision) {
+    int sms = 0;
+    VIT_TRY(op_begin(&sms));
+    if (!x || !ln_w || !ln_b || !W || !b || !y || m <= 0 || n <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (epilogue != VIT_EPI_BIAS && epilogue != VIT_EPI_BIAS_GELU) return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
+    Scratch s;
+    float *dx, *dlw, *dlb, *dW, *db, *dcs, *dcv;
+    void *dxc, *dwf, *dy;
+    float2* dst;
+    const size_t srows = (static_cast<size_t>(m) + 255) / 256 * 256;
+    VIT_TRY(s.upload_f32(&dx, x, (size_t)m * kDim));
+    VIT_TRY(s.upload_f32(&dlw, ln_w, kDim));
+    VIT_TRY(s.upload_f32(&dlb, ln_b, kDim));
+    VIT_TRY(s.upload_f32(&dW, W, (size_t)n * kDim));
+    VIT_TRY(s.upload_f32(&db, b, n));
+    VIT_TRY(s.alloc(&dxc, (size_t)m * kDim * 2, true));
+    VIT_TRY(s.alloc(&dwf, (size_t)n * kDim * 2, true));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dcs), (size_t)n * 4));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dcv), (size_t)n * 4));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dst), srows * sizeof(float2), true));
+    VIT_TRY(s.alloc(&dy, (size_t)m * n * 2, true));
+    VIT_TRY(launch_fold_ln(precision, dW, dlw, dlb, db, dwf, dcs, dcv, n, nullptr));
+    VIT_TRY(launch_rowstats_cast(precision, dx, dxc, dst, m, nullptr));
+    CUtensorMap ta, tb, tout;
+    VIT_TRY(make_tmap(&ta, precision, dxc, kDim, m, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&tb, precision, dwf, kDim, n, GEMM_BK, 128));
+    VIT_TRY(make_tmap(&tout, precision, dy, n, m, GEMM_BK, GEMM_BM));
+    GemmParams p{m, n, kDim, dcv, dy, nullptr, 0, 0};
+    p.colsum = dcs;
+    p.stats_in = dst;
+    p.stats_parts = 1;
+    p.stats_rows = static_cast<int>(srows);
+    if (epilogue == VIT_EPI_BIAS_GELU) VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(precision, ta, tb, tout, tout, p, sms, nullptr));
+    else VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(precision, ta, tb, tout, tout, p, sms, nullptr));
+    VIT_TRY(op_end("op_ln_linear"));
+    VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
+    return op_end("op_ln_linear");
+}
+
+int vit_cuda_op_linear_residual_stats(const float* x, const float* W, const float* b, const float* residual, float* y,
+                                      float* y_cast, float* row_sum, float* row_sumsq, int m, int k, int precision) {
+    int sms = 0;
+    VIT_TRY(op_begin(&sms));
+    if (!x || !W || !b || !residual || !y || !y_cast || !row_sum || !row_sumsq || m <= 0 || k <= 0) return set_err(VIT_E_ARG, "bad arguments");
+    Scratch s;
+    void *dx, *dw, *dyc;
+    float *db, *dy;
+    float2* dst;
+    const size_t srows = (static_cast<size_t>(m) + 255) / 256 * 256;
+    VIT_TRY(s.upload_operand(&dx, x, (size_t)m * k, precision));
+    VIT_TRY(s.upload_operand(&dw, W, (size_t)kDim * k, precision));
+    VIT_TRY(s.upload_f32(&db, b, kDim));
+    VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * kDim));
+    VIT_TRY(s.alloc(&dyc, (size_t)m * kDim * 2, true));
+    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dst), 6 * srows * sizeof(float2), true));
+    CUtensorMap ta, tb, tout, tcast;
+    VIT_TRY(make_tmap(&ta, precision, dx, k, m, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&tb, precision, dw, k, kDim, GEMM_BK, 128));
+    VIT_TRY(make_tmap_f32(&tout, dy, kDim, m, GEMM_BM));
+    VIT_TRY(make_tmap(&tcast, precision, dyc, kDim, m, GEMM_BK, GEMM_BM));
+    GemmParams p{m, kDim, k, db, dy, dy, 0, 0};
+    p.stats_out = dst;
+    p.stats_rows = static_cast<int>(srows);
+    VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(precision, ta, tb, tout, tcast, p, sms, nullptr));
+    VIT_TRY(op_end("op_linear_residual_stats"));
+    CU_TRY(cudaMemcpy(y, dy, (size_t)m * kDim * 4, cudaMemcpyDeviceToHost));
+    VIT_TRY(s.download_operand(y_cast, dyc, (size_t)m * kDim, precision));
+    std::vector<float2> h(6 * srows);
+    CU_TRY(cudaMemcpy(h.data(), dst, h.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < m; ++r) {   // the consumer's summation order (gemm_sm100_staged_kernel, LN consumer)
+        float s1 = 0.f, s2 = 0.f;
+        for (int q = 0; q < 6; ++q) {
+            s1 += h[q * srows + r].x;
+            s2 += h[q * srows + r].y;
+        }
+        row_sum[r] = s1;
+        row_sumsq[r] = s2;
+    }
+    return op_end("op_linear_residual_stats");
 }
 
 int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int precision) {

@@ -34,6 +34,12 @@ struct GemmParams {
     int tokens;             // EPI_PATCH_EMBED: tokens per image  (197 / 577)
     int bf16_from_col;      // staged EPI_BIAS: output columns >= this are stored as bf16 whatever T is
                             // (the V block of in_proj: attention keeps P and V in bf16); <= 0: never
+    // ---- LayerNorm folded into the GEMMs (staged kernel, LN = true), see gemm_sm100_staged_kernel
+    const float2* stats_in;   // consumer: per-row partial (sum, sum of squares) of the fp32 residual row, [parts][stats_rows]
+    float2* stats_out;        // producer (EPI_BIAS_RESIDUAL): partials of the rows it writes, part = 2 * n_tile + column half
+    int stats_parts;          // consumer: number of partials per row to add up (6 after a residual GEMM, 1 after rowstats_cast)
+    int stats_rows;           // row capacity of the stats arrays (stride between parts)
+    const float* colsum;      // consumer: s[n] = sum_k W'[n][k] of the folded, rounded weights W' = ln_w (.) W
 };
 
 constexpr int GEMM_BM = 128;
@@ -454,28 +460,53 @@ gemm_sm100_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // Slots form a ring shared by loader, epilogue warps and the storing thread.
 constexpr int GEMM_SLOT_BYTES = 128 * 128;
 
-template <int STAGES, int SLOTS>
+// PRE_BYTES: per-tile parameters staged one tile ahead by the loader warp of the non-residual kernels
+// (bias, and for the LayerNorm consumer the column sums and the 128 rows' (rstd, -rstd * mean)), two buffers.
+template <int STAGES, int SLOTS, int CAST_BUFS = 0, int PRE_BYTES = 0>
 struct GemmStagedSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = 128 * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SLOT_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = SLOT_OFF + SLOTS * GEMM_SLOT_BYTES;
-    static constexpr int BAR_OFF = BIAS_OFF + 2 * 256 * 4;
-    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * SLOTS;
+    static constexpr int CAST_OFF = SLOT_OFF + SLOTS * GEMM_SLOT_BYTES;   // operand-precision copy of the output (LN producer)
+    static constexpr int BIAS_OFF = CAST_OFF + CAST_BUFS * GEMM_SLOT_BYTES;
+    static constexpr int BIAS_BYTES = PRE_BYTES > 0 ? 2 * PRE_BYTES : 2 * 256 * 4;  // unstaged: [bias | colsum][256] of the current tile
+    static constexpr int BAR_OFF = BIAS_OFF + BIAS_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * SLOTS + 4;
     static constexpr int DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16;  // base must be 1024-aligned (checked)
 };
 
 template <int NTHREADS>
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
+// LayerNorm folded into the GEMMs (LN = true).  The reference normalises every token row before in_proj
+// and mlp_0 (layer_norm, ViT_seq.c:103-121, called at :281 and :291).  Here no normalised activation is
+// ever written: with W' = ln_w (.) W (folded and rounded once at init), s[n] = sum_k W'[n][k] and
+// c[n] = bias[n] + sum_k ln_b[k] W[n][k],
+//     LN(x) W^T + bias  =  rstd * (x W'^T - mean * s) + c ,
+// so the CONSUMER GEMM (EPI_BIAS / EPI_BIAS_GELU, LN = true) multiplies the operand-precision copy of the
+// raw residual row and applies (mean, rstd) per row in its epilogue, and the PRODUCER GEMM
+// (EPI_BIAS_RESIDUAL, LN = true), which writes the fp32 residual row anyway, also emits that copy
+// (tmap_cast) and the row's partial (sum, sum of squares) over its 256 columns.  Partials are plain stores
+// to stats_out[2 * n_tile + column half][row]: no atomics, fixed summation order, results independent of
+// the batch position.  This removes the LayerNorm kernels (read 3 KB + write 1.5 KB per token, twice
+// per layer) from the forward pass.
+//
 // EPI_WARPS: 8 (two warps per TMEM lane quarter) or 16 (four per quarter; for the GELU epilogue, whose
 // ~13 dependent FP32 ops + 2 MUFU per element are latency bound with only two warps per scheduler).
-template <typename T, int STAGES, int SLOTS, int EPI, int EPI_WARPS>
+template <typename T, int STAGES, int SLOTS, int EPI, int EPI_WARPS, bool LN = false, int CAST_BUFS = (LN && EPI == EPI_BIAS_RESIDUAL) ? 2 : 0,
+          bool STAGED = (EPI != EPI_BIAS_RESIDUAL)>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GEMM_NON_EPI_WARPS + EPI_WARPS) * 32, 1)
 gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
-    using L = GemmStagedSmem<STAGES, SLOTS>;
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_cast,
+                         const GemmParams p) {
+    static_assert((CAST_BUFS > 0) == (LN && EPI == EPI_BIAS_RESIDUAL) && CAST_BUFS <= 2, "staging tiles of the operand-precision copy");
+    // STAGED: the tile's parameters are put into shared memory one tile ahead by the loader warp (two buffers);
+    // otherwise the epilogue threads load them themselves, from lines they prefetched into L1 a tile earlier.
+    static_assert(!(STAGED && EPI == EPI_BIAS_RESIDUAL), "the residual kernel's loader warp is busy");
+    constexpr int PRE_FLOATS = !STAGED ? 0 : (LN ? 256 + 256 + 2 * 128 : 256);  // bias | colsum | (rstd, nm) per row
+    using L = GemmStagedSmem<STAGES, SLOTS, CAST_BUFS, PRE_FLOATS * 4>;
+    static_assert(!LN || EPI_WARPS == 8, "LN variants use 8 epilogue warps");
     static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESIDUAL, "staged epilogues");
     constexpr bool kResidual = EPI == EPI_BIAS_RESIDUAL;
     constexpr int BN = 256;
@@ -496,7 +527,9 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* res_full = tempty_bar + 2;     // [SLOTS] residual chunk landed in the slot
     uint64_t* slot_free = res_full + SLOTS;  // [SLOTS] the store out of the slot has drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_free + SLOTS);
+    uint64_t* pre_full = slot_free + SLOTS;  // [2] the tile's staged parameters are in shared memory (32 arrivals)
+    uint64_t* pre_free = pre_full + 2;       // [2] every epilogue warp is through with them
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pre_free + 2);
 
     // Warp roles.  The epilogue warps come FIRST: the SM's warp scheduler favours higher warp ids
     // among eligible warps, and the single-thread TMA producer / MMA issuer must never be starved
@@ -517,6 +550,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         tma_prefetch_desc(&tmap_out);
+        if constexpr (CAST_BUFS > 0) tma_prefetch_desc(&tmap_cast);
     }
     if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -530,6 +564,10 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(&res_full[s], 1);
             mbar_init(&slot_free[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&pre_full[s], kResidual ? 1 : 32);   // residual kernel with ONE cast staging tile: [0] = "tile drained"
+            mbar_init(&pre_free[s], EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -593,6 +631,59 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if ((acc ^= 1) == 0) acc_phase ^= 1;
             }
         }
+    } else if (warp == W_LOADER && STAGED) {
+        // ------------------------------------------------------------ parameter stager (EPI_BIAS / EPI_BIAS_GELU)
+        // One tile ahead of the epilogue: the tile's 256 bias values and, for the LayerNorm consumer, the
+        // column sums of the folded weights and the finished row statistics (the six partial sums of each
+        // of the 128 rows -> rstd and -rstd * mean).  The epilogue warps would otherwise sit through a
+        // global-memory round trip (or several) at the start of every tile.
+        int j = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, ++j) {
+            const int m0 = (tile / tiles_n) * 256 + rank * 128;
+            const int n0 = (tile % tiles_n) * BN;
+            const int b = j & 1;
+            float* pb = s_bias + b * PRE_FLOATS;
+            float4 bv[2];
+            [[maybe_unused]] float4 cv[2];
+            [[maybe_unused]] float2 part[4][6];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + lane + 32 * i);
+                if constexpr (LN) cv[i] = __ldg(reinterpret_cast<const float4*>(p.colsum + n0) + lane + 32 * i);
+            }
+            if constexpr (LN) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = m0 + lane + 32 * i;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q)
+                        part[i][q] = (r < p.M && q < p.stats_parts) ? __ldg(p.stats_in + static_cast<size_t>(q) * p.stats_rows + r)
+                                                                    : make_float2(0.f, 0.f);
+                }
+            }
+            mbar_wait(&pre_free[b], ((j >> 1) & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                reinterpret_cast<float4*>(pb)[lane + 32 * i] = bv[i];
+                if constexpr (LN) reinterpret_cast<float4*>(pb + 256)[lane + 32 * i] = cv[i];
+            }
+            if constexpr (LN) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {   // fixed order: parts 0..5
+                        s1 += part[i][q].x;
+                        s2 += part[i][q].y;
+                    }
+                    const float mean = s1 * (1.0f / 768.0f);
+                    const float var = fmaxf(s2 * (1.0f / 768.0f) - mean * mean, 0.f);  // ViT_seq.c:115 (single pass)
+                    const float rstd = rsqrtf(var + 1e-6f);
+                    reinterpret_cast<float2*>(pb + 512)[lane + 32 * i] = make_float2(rstd, -rstd * mean);
+                }
+            }
+            mbar_arrive(&pre_full[b]);
+        }
     } else if (warp == W_LOADER) {
         // ------------------------------------------------------------ residual loader (EPI_BIAS_RESIDUAL)
         if (kResidual && lane == 0) {
@@ -621,13 +712,72 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t k = 0;  // running chunk counter (ring position)
-        int tile_par = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs, tile_par ^= 1) {
+        [[maybe_unused]] int tile_par = 0;
+        [[maybe_unused]] uint32_t pre_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m0 = (tile / tiles_n) * 256 + rank * 128;
             const int n0 = (tile % tiles_n) * BN;
-            float* sb = s_bias + tile_par * 256;
-            if (etid < 256) sb[etid] = p.bias[n0 + etid];
-            epi_bar_sync<EPI_THREADS>();
+            float* sb = s_bias;
+            float ln_rstd = 1.f, ln_nm = 0.f;  // LN consumer: this thread's row: rstd and -rstd * mean
+            if constexpr (!STAGED) {
+                // Loaded by the epilogue threads themselves.  One buffer is enough: every chunk iteration below
+                // ends with a barrier after its last read of it, so nobody still reads the previous tile's values
+                // here.  The global-memory round trip is short because each thread asked for the NEXT tile's lines
+                // (prefetch.global.L1) one tile ago; TMA traffic bypasses L1, so they are still there.
+                [[maybe_unused]] float2 part[6];
+                if constexpr (LN && !kResidual) {
+                    const bool row_ok = m0 + row < p.M;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q)
+                        part[q] = (row_ok && q < p.stats_parts) ? __ldg(p.stats_in + static_cast<size_t>(q) * p.stats_rows + m0 + row)
+                                                                : make_float2(0.f, 0.f);
+                }
+                if (etid < 256) {
+                    const float bv = __ldg(p.bias + n0 + etid);
+                    [[maybe_unused]] float cv = 0.f;
+                    if constexpr (LN && !kResidual) cv = __ldg(p.colsum + n0 + etid);
+                    sb[etid] = bv;
+                    if constexpr (LN && !kResidual) sb[256 + etid] = cv;
+                }
+                if constexpr (LN && !kResidual) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {   // fixed order: parts 0..5
+                        s1 += part[q].x;
+                        s2 += part[q].y;
+                    }
+                    const float mean = s1 * (1.0f / 768.0f);
+                    const float var = fmaxf(s2 * (1.0f / 768.0f) - mean * mean, 0.f);  // ViT_seq.c:115 (single pass)
+                    ln_rstd = rsqrtf(var + 1e-6f);
+                    ln_nm = -ln_rstd * mean;
+                }
+                const int next = tile + num_pairs;
+                if (next < num_tiles) {
+                    const int m1 = (next / tiles_n) * 256 + rank * 128, n1 = (next % tiles_n) * BN;
+                    if (etid < 256) {
+                        prefetch_l1(p.bias + n1 + etid);
+                        if constexpr (LN && !kResidual) prefetch_l1(p.colsum + n1 + etid);
+                    }
+                    if constexpr (LN && !kResidual) {
+                        if (m1 + row < p.M) {
+#pragma unroll
+                            for (int q = 0; q < 6; ++q)
+                                if (q < p.stats_parts) prefetch_l1(p.stats_in + static_cast<size_t>(q) * p.stats_rows + m1 + row);
+                        }
+                    }
+                }
+                epi_bar_sync<EPI_THREADS>();
+            } else {
+                // staged one tile ahead by the loader warp (bias | column sums | row statistics)
+                sb = s_bias + tile_par * PRE_FLOATS;
+                mbar_wait(&pre_full[tile_par], pre_phase);
+                if constexpr (LN) {
+                    const float2 st = reinterpret_cast<const float2*>(sb + 512)[row];
+                    ln_rstd = st.x;
+                    ln_nm = st.y;
+                }
+            }
+            float st_sum = 0.f, st_sq = 0.f;   // LN producer: partial row statistics over this thread's 128 columns
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -655,6 +805,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const uint32_t* r = racc[c];
                 if constexpr (kResidual) {
                     mbar_wait(&res_full[slot], (k / SLOTS) & 1);
+                    [[maybe_unused]] uint32_t cast[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float4* q = reinterpret_cast<float4*>(srow + (((half * 4 + j) ^ sw) << 4));
@@ -664,19 +815,40 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         v.z += __uint_as_float(r[4 * j + 2]) + bcol[4 * j + 2];
                         v.w += __uint_as_float(r[4 * j + 3]) + bcol[4 * j + 3];
                         *q = v;
+                        if constexpr (LN) {
+                            st_sum += (v.x + v.y) + (v.z + v.w);
+                            st_sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st_sq))));
+                            cast[2 * j] = pack2<T>(v.x, v.y);
+                            cast[2 * j + 1] = pack2<T>(v.z, v.w);
+                        }
+                    }
+                    if constexpr (LN) {
+                        // operand-precision copy: two fp32 chunks (2 x 32 columns) fill one 64-column staging
+                        // tile; this thread's 16 columns are two 16-byte pieces of the 128-byte row
+                        uint8_t* crow = smem + L::CAST_OFF + ((c >> 1) & (CAST_BUFS - 1)) * GEMM_SLOT_BYTES + row_off;
+                        const uint32_t piece = (c & 1) * 4 + half * 2;
+                        if constexpr (CAST_BUFS == 1) {
+                            // single staging tile: the store of the previous 64-column block (issued by the storer
+                            // after the last barrier) must have read it before anyone writes the next block
+                            if ((c & 1) == 0 && k >= 2) mbar_wait(&pre_full[0], ((k >> 1) - 1) & 1);
+                        }
+                        *reinterpret_cast<uint4*>(crow + (((piece + 0) ^ sw) << 4)) = make_uint4(cast[0], cast[1], cast[2], cast[3]);
+                        *reinterpret_cast<uint4*>(crow + (((piece + 1) ^ sw) << 4)) = make_uint4(cast[4], cast[5], cast[6], cast[7]);
                     }
                 } else {
                     uint32_t packed[COLS_PER_WARP / 2];
                     const bool as_bf16 = EPI == EPI_BIAS && p.bf16_from_col > 0 && n0 + c * CHUNK_COLS >= p.bf16_from_col;
+                    [[maybe_unused]] const float* scol = bcol + 256;
 #pragma unroll
                     for (int j = 0; j < COLS_PER_WARP / 2; ++j) {
-                        float v0 = __uint_as_float(r[2 * j]) + bcol[2 * j];
-                        float v1 = __uint_as_float(r[2 * j + 1]) + bcol[2 * j + 1];
-                        if constexpr (EPI == EPI_BIAS_GELU) {
-                            v0 = gelu_erf(v0);
-                            v1 = gelu_erf(v1);
-                        }
-                        packed[j] = as_bf16 ? pack2<__nv_bfloat16>(v0, v1) : pack2<T>(v0, v1);
+                        // two adjacent columns per step, fp32 arithmetic issued in pairs (FFMA2 / FMUL2)
+                        const float2 a = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        const float2 bc = *reinterpret_cast<const float2*>(bcol + 2 * j);
+                        float2 v;
+                        if constexpr (LN) v = fma2(splat2(ln_nm), *reinterpret_cast<const float2*>(scol + 2 * j), fma2(a, splat2(ln_rstd), bc));
+                        else v = add2(a, bc);
+                        if constexpr (EPI == EPI_BIAS_GELU) v = gelu_erf2(v);
+                        packed[j] = as_bf16 ? pack2<__nv_bfloat16>(v.x, v.y) : pack2<T>(v.x, v.y);
                     }
                     // the slot's previous store (chunk k - SLOTS) has drained: the storer checked before
                     // the barrier that ended chunk k - 1
@@ -690,7 +862,21 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 epi_bar_sync<EPI_THREADS>();
                 if (storer) {
                     tma_store_2d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, m0);
+                    if constexpr (kResidual && LN) {
+                        // Same bulk group as the fp32 chunk, so the wait below also covers the staging tile:
+                        // it is rewritten two 64-column blocks later, i.e. after the barriers of chunks c + 1
+                        // and c + 2, which this thread only joins after wait_read<1> has seen this group through.
+                        // (With a single staging tile the storer simply waits for this group before moving on.)
+                        if (c & 1)
+                            tma_store_2d(&tmap_cast, smem + L::CAST_OFF + ((c >> 1) & (CAST_BUFS - 1)) * GEMM_SLOT_BYTES, n0 + (c >> 1) * 64, m0);
+                    }
                     tma_store_commit();
+                    if constexpr (CAST_BUFS == 1) {
+                        if (c & 1) {
+                            tma_store_wait_read<0>();
+                            mbar_arrive(&pre_full[0]);
+                        }
+                    }
                     if constexpr (kResidual) {
                         if (k >= 1) {  // the previous chunk's store has finished reading its slot: hand it to the loader
                             tma_store_wait_read<1>();
@@ -698,6 +884,15 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                     }
                 }
+            }
+            if constexpr (kResidual && LN) {
+                if (m0 + row < p.M)
+                    p.stats_out[static_cast<size_t>(2 * (tile % tiles_n) + half) * p.stats_rows + m0 + row] = make_float2(st_sum, st_sq);
+            }
+            if constexpr (STAGED) {   // all reads of the staged parameters precede the last chunk's barrier
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pre_free[tile_par]);
+                if ((tile_par ^= 1) == 0) pre_phase ^= 1;
             }
             if ((acc ^= 1) == 0) acc_phase ^= 1;
         }

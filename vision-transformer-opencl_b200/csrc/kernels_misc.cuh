@@ -54,6 +54,63 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm folded into the GEMMs (gemm_sm100_staged_kernel, LN = true): the two helpers around it.
+//
+// rowstats_cast: for the rows entering layer 0 (written by the patch-embedding epilogue) -- the
+// operand-precision copy of the raw fp32 row plus its (sum, sum of squares), i.e. what the residual
+// GEMMs emit for every later LayerNorm.  One warp per row, 128-bit loads.
+template <typename T>
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restrict__ x, T* __restrict__ y,
+                                                            float2* __restrict__ stats, int rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * kDim);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * kDim);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float4 v = xr[lane + 32 * i];
+        s += (v.x + v.y) + (v.z + v.w);
+        q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+        uint2 o;
+        o.x = pack2<T>(v.x, v.y);
+        o.y = pack2<T>(v.z, v.w);
+        yr[lane + 32 * i] = o;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) stats[row] = make_float2(s, q);
+}
+
+// fold_ln_weights (once, at init): W'[n][k] = round_T(ln_w[k] * W[n][k]),  colsum[n] = sum_k W'[n][k]
+// (of the ROUNDED values, so that mean * colsum cancels exactly what the tensor cores accumulate),
+// cvec[n] = bias[n] + sum_k ln_b[k] * W[n][k].  One warp per output feature n.
+template <typename T>
+__global__ void __launch_bounds__(256) fold_ln_weights_kernel(const float* __restrict__ W, const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, const float* __restrict__ bias,
+                                                              T* __restrict__ Wp, float* __restrict__ colsum,
+                                                              float* __restrict__ cvec, int N) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f, c = 0.f;
+    for (int k = lane; k < kDim; k += 32) {
+        const float w = W[static_cast<size_t>(n) * kDim + k];
+        const T wp = from_float<T>(ln_w[k] * w);
+        Wp[static_cast<size_t>(n) * kDim + k] = wp;
+        s += to_float<T>(wp);
+        c = fmaf(ln_b[k], w, c);
+    }
+    s = warp_sum(s);
+    c = warp_sum(c);
+    if (lane == 0) {
+        colsum[n] = s;
+        cvec[n] = bias[n] + c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Patch extraction + cast: images [B][3][S][S] fp32 -> patches [B*G*G][768] in operand precision,
 // K order (ic, kh, kw) = the flattened conv_proj.weight row order (Conv2d, ViT_seq.c:33-41), patch
 // index oh*G+ow (flatten_transpose, ViT_seq.c:57-65).  One thread per float4 of the image, reads

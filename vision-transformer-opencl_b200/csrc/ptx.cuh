@@ -27,6 +27,7 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -416,6 +417,45 @@ __device__ __forceinline__ float gelu_erf(float x) {
     q = fmaf(q, t, 0.5f * 0.254829592f);
     const float pe = q * (t * e);
     return fmaf(-ax, pe, fmaxf(x, 0.0f));
+}
+
+
+// ------------------------------------------------------------------ packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2)
+// One instruction issue does two IEEE fp32 operations (same rounding as the scalar forms); the GELU and
+// softmax epilogues are bound by issue slots, not by the FMA pipe.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// gelu_erf on two values: the same operations in the same order as the scalar form above (bit-identical
+// results), with the fp32 multiplies / FMAs issued in pairs.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 nax = make_float2(__uint_as_float(__float_as_uint(x.x) | 0x80000000u), __uint_as_float(__float_as_uint(x.y) | 0x80000000u));  // -|x|
+    const float2 d = fma2(nax, splat2(-(0.3275911f * 0.70710678118654752f)), splat2(1.0f));
+    const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+    const float2 u = mul2(x, splat2(0.84932180028801904f));
+    const float2 w = mul2(u, u);
+    const float2 e = make_float2(fast_exp2(-w.x), fast_exp2(-w.y));
+    float2 q = fma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
+    q = fma2(q, t, splat2(0.5f * 1.421413741f));
+    q = fma2(q, t, splat2(0.5f * -0.284496736f));
+    q = fma2(q, t, splat2(0.5f * 0.254829592f));
+    const float2 pe = mul2(q, mul2(t, e));
+    return fma2(nax, pe, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
 }  // namespace vit

@@ -77,6 +77,8 @@ _sig("vit_cuda_host_alloc_pinned", C.c_int, C.c_size_t, C.POINTER(C.c_void_p))
 _sig("vit_cuda_host_free_pinned", C.c_int, C.c_void_p)
 _sig("vit_cuda_op_linear", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_op_layernorm", C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int)
+_sig("vit_cuda_op_ln_linear", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int)
+_sig("vit_cuda_op_linear_residual_stats", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_op_attention", C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_debug_attention_trace", C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int)
 _sig("vit_cuda_op_embed", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
@@ -280,6 +282,23 @@ def op_linear(x, W, b, residual=None, epilogue=EPI_BIAS, precision=PREC_BF16):
     _check(lib.vit_cuda_op_linear(fptr(x), fptr(W), fptr(b), fptr(residual) if residual is not None else None,
                                   fptr(y), m, n, k, epilogue, precision))
     return y
+
+
+def op_ln_linear(x, ln_w, ln_b, W, b, epilogue=EPI_BIAS, precision=PREC_BF16):
+    """epilogue(LN(x) W^T + b) with the LayerNorm folded into the GEMM (in_proj / mlp_0 of the forward pass)."""
+    m, n = x.shape[0], W.shape[0]
+    y = np.empty((m, n), dtype=np.float32)
+    _check(lib.vit_cuda_op_ln_linear(fptr(x), fptr(ln_w), fptr(ln_b), fptr(W), fptr(b), fptr(y), m, n, epilogue, precision))
+    return y
+
+
+def op_linear_residual_stats(x, W, b, residual, precision=PREC_BF16):
+    """residual + x W^T + b (fp32) plus its operand-precision copy and per-row (sum, sum of squares)."""
+    m, k = x.shape
+    y, yc = np.empty((m, 768), dtype=np.float32), np.empty((m, 768), dtype=np.float32)
+    s1, s2 = np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32)
+    _check(lib.vit_cuda_op_linear_residual_stats(fptr(x), fptr(W), fptr(b), fptr(residual), fptr(y), fptr(yc), fptr(s1), fptr(s2), m, k, precision))
+    return y, yc, s1, s2
 
 
 def op_layernorm(x, w, b, precision=PREC_BF16):
