@@ -163,13 +163,19 @@ def test_attention_dominant_late_key(vit, oracle, prec):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-def test_embed(vit, oracle, prec, weights224):
+@pytest.mark.parametrize("img_size,batch", [(224, 3), (384, 2), (32, 5)])
+def test_embed(vit, oracle, prec, weights224, img_size, batch):
+    """conv_proj + class_token + pos_embedding (Conv2d / flatten_transpose / class_token / pos_emb,
+    ViT_seq.c:25-101).  196 patches fit one 256-row tile per image, 576 (384x384) take three, 4 (32x32)
+    leave most of a tile empty: the per-image tiling must clip and zero-fill correctly in all of them."""
     w = weights224
-    imgs = round_operand(vit.synth_images(3, 224, 21), prec)
+    tokens = (img_size // 16) ** 2 + 1
+    pos = w[3] if img_size == 224 else _rand((tokens * 768,), 90 + img_size, 0.05)
+    imgs = round_operand(vit.synth_images(batch, img_size, 21), prec)
     conv_w = round_operand(w[1], prec)
-    got = vit.op_embed(imgs, w[0], conv_w, w[2], w[3], precision=prec)
-    ref = np.concatenate([oracle.embed(imgs[i], w[0], conv_w, w[2], w[3]) for i in range(3)])
-    _close(got, ref, 1e-5, 2e-5, "patch embedding")
+    got = vit.op_embed(imgs, w[0], conv_w, w[2], pos, precision=prec)
+    ref = np.concatenate([oracle.embed(imgs[i], w[0], conv_w, w[2], pos) for i in range(batch)])
+    _close(got, ref, 1e-5, 2e-5, f"patch embedding {img_size}")
 
 
 def test_head(vit, oracle, weights224):

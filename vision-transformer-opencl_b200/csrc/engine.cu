@@ -107,6 +107,21 @@ int make_tmap_3d(CUtensorMap* m, int prec, const void* base, uint64_t d0, uint64
     return 0;
 }
 
+// 3-D [d2][d1][d0] fp32 tensor, box {32, box_d1, 1} (128 bytes per box row), 128B swizzle
+int make_tmap_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box_d1) {
+    VIT_TRY(load_driver());
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+    const cuuint32_t box[3] = {32, box_d1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled(3d f32) failed (%d) dims=%llu,%llu,%llu", (int)r,
+                                          (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ launches
 constexpr int kGemmBN = 256, kGemmStages = 4, kGemmEpiWG = 2;
 constexpr int kGemmThreads = (GEMM_NON_EPI_WARPS + 4 * kGemmEpiWG) * 32;
@@ -158,14 +173,14 @@ constexpr int kStagedStages = 5, kStagedSlots = 4;
 // LN = true: LayerNorm folded into the GEMM (consumer for EPI_BIAS / EPI_BIAS_GELU, producer for
 // EPI_BIAS_RESIDUAL, see gemm_sm100.cuh).  The producer gives one operand stage up for the two
 // staging tiles of the operand-precision copy.
-template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL)>
+template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false>
 int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
-                           const GemmParams& p, int sm_count, cudaStream_t st) {
+                           const GemmParams& p, int sm_count, cudaStream_t st, const CUtensorMap* tres = nullptr) {
     constexpr int kPreFloats = !PSTAGED ? 0 : (LN ? 256 + 256 + 2 * 128 : 256);
     using L = GemmStagedSmem<STAGES, SLOTS, CAST, kPreFloats * 4>;
     static_assert(L::DYN_BYTES <= 232448, "shared memory budget");
     constexpr int kEpiWarps = 8;  // 16 was measured no faster for the GELU epilogue (issue bound, not latency bound)
-    auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED>;
+    auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED, EMBED>;
     static int configured_dev_mask = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -179,7 +194,7 @@ int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const C
         return set_err(VIT_E_ARG, "LayerNorm-folded gemm: bad statistics arguments (N=%d K=%d)", p.N, p.K);
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int grid = 2 * std::min(tiles, sm_count / 2);
-    kern<<<grid, (GEMM_NON_EPI_WARPS + kEpiWarps) * 32, L::DYN_BYTES, st>>>(ta, tb, tout, tcast, p);
+    kern<<<grid, (GEMM_NON_EPI_WARPS + kEpiWarps) * 32, L::DYN_BYTES, st>>>(ta, tb, tout, tcast, tres ? *tres : tout, p);
     return check_launch("gemm_staged");
 }
 int res_cfg() {  // VIT_RES_CFG: A/B switch of the residual GEMM's shared-memory split (tuning)
@@ -214,19 +229,35 @@ int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
         return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, true>(ta, tb, tout, tcast, p, sm_count, st);
     }
 }
-// tout: store map of the output (for the residual epilogue also the load map of the residual, in place)
-template <int EPI>
-int launch_gemm_staged(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
-                       int sm_count, cudaStream_t st) {
-    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, false>(ta, tb, tout, tout, p, sm_count, st)
-                                 : launch_gemm_staged_t<__nv_bfloat16, EPI, false>(ta, tb, tout, tout, p, sm_count, st);
+// conv_proj as the EMBED variant of the residual kernel (one CTA pair per image): ta 3-D patch map, tout 3-D fp32
+// token map, tcast 3-D operand-precision token map (ln only), tpos 2-D pos_embedding map.  p.M = images * row tiles per image * 256.
+template <typename T>
+int launch_gemm_embed_t(bool ln, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
+                        const CUtensorMap& tpos, const GemmParams& p, int sm_count, cudaStream_t st) {
+    if (ln) return launch_gemm_staged_cfg<T, EPI_BIAS_RESIDUAL, true, 4, 4, 2, false, true>(ta, tb, tout, tcast, p, sm_count, st, &tpos);
+    return launch_gemm_staged_cfg<T, EPI_BIAS_RESIDUAL, false, kStagedStages, kStagedSlots, 0, false, true>(ta, tb, tout, tcast, p, sm_count, st, &tpos);
 }
-// LayerNorm-folded variants; tcast: store map of the operand-precision copy (producer only)
+int launch_gemm_embed(int prec, bool ln, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
+                      const CUtensorMap& tpos, const GemmParams& p, int sm_count, cudaStream_t st) {
+    return prec == VIT_PREC_FP16 ? launch_gemm_embed_t<__half>(ln, ta, tb, tout, tcast, tpos, p, sm_count, st)
+                                 : launch_gemm_embed_t<__nv_bfloat16>(ln, ta, tb, tout, tcast, tpos, p, sm_count, st);
+}
+
+// tout: store map of the output, 128-row boxes (for the residual epilogue also the load map of the residual, in
+// place).  taux: EPI_BIAS / EPI_BIAS_GELU: store map of the same output with 32-row boxes (one per TMEM lane quarter);
+// EPI_BIAS_RESIDUAL: unused.
 template <int EPI>
-int launch_gemm_staged_ln(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
+int launch_gemm_staged(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& taux,
+                       const GemmParams& p, int sm_count, cudaStream_t st) {
+    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, false>(ta, tb, tout, taux, p, sm_count, st)
+                                 : launch_gemm_staged_t<__nv_bfloat16, EPI, false>(ta, tb, tout, taux, p, sm_count, st);
+}
+// LayerNorm-folded variants; taux as above, for the producer (EPI_BIAS_RESIDUAL): store map of the operand-precision copy
+template <int EPI>
+int launch_gemm_staged_ln(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& taux,
                           const GemmParams& p, int sm_count, cudaStream_t st) {
-    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, true>(ta, tb, tout, tcast, p, sm_count, st)
-                                 : launch_gemm_staged_t<__nv_bfloat16, EPI, true>(ta, tb, tout, tcast, p, sm_count, st);
+    return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, true>(ta, tb, tout, taux, p, sm_count, st)
+                                 : launch_gemm_staged_t<__nv_bfloat16, EPI, true>(ta, tb, tout, taux, p, sm_count, st);
 }
 
 template <typename T, int EPI>
@@ -414,7 +445,7 @@ struct DeviceCtx {
     // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
     // use, so TMA zero-fills loads and clips stores past the last image
     int maps_nb = -1;
-    CUtensorMap tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_x, tm_q /* attention loads */, tm_kv /* attention store */;
+    CUtensorMap tm_patches3, tm_x3, tm_xn3 /* per-image 3-D views for conv_proj */, tm_pos, tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_hid32, tm_qkv_st32 /* 32-row store boxes */, tm_x, tm_q /* attention loads */, tm_kv /* attention store */;
     size_t ws_bytes = 0;
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
@@ -569,6 +600,12 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap(&c.tm_ao, prec, c.ao, kDim, rows, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));     // mlp_0 store + mlp_3 A load
     VIT_TRY(make_tmap(&c.tm_qkv_st, prec, c.qkv, 3 * kDim, rows, GEMM_BK, GEMM_BM)); // in_proj store
+    VIT_TRY(make_tmap_3d(&c.tm_patches3, prec, c.patches, kDim, e.patches, nb, GEMM_BM));
+    VIT_TRY(make_tmap_3d_f32(&c.tm_x3, c.x, kDim, e.tokens, nb, GEMM_BM));
+    VIT_TRY(make_tmap_3d(&c.tm_xn3, prec, c.xn, kDim, e.tokens, nb, GEMM_BM));
+    VIT_TRY(make_tmap_f32(&c.tm_pos, c.pos, kDim, e.tokens, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_hid32, prec, c.hid, kHidden, rows, GEMM_BK, 32));
+    VIT_TRY(make_tmap(&c.tm_qkv_st32, prec, c.qkv, 3 * kDim, rows, GEMM_BK, 32));
     VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
     VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(e.tokens)));  // Q/K/V boxes
     VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                                   // per-image output tiles
@@ -608,27 +645,39 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     const bool staged = gemm_impl() == 2;
     // conv_proj: patch rows -> GEMM with (+bias, +pos_embedding, row remap) epilogue; class rows aside
     const bool pf = e.profiling;
+    // LayerNorm folded into the GEMMs (default): in_proj / mlp_0 read the operand-precision copy of the raw
+    // residual rows (c.xn) with the per-row statistics (c.pstats) that the previous residual GEMM -- for
+    // layer 0 conv_proj and the class-row kernel -- left behind.  Otherwise: a LayerNorm kernel before each.
+    const bool fused = staged && e.ln_fused;
+    const int stats_rows = static_cast<int>(c.stats_rows);
     {
         ProfScope ps(c, pf, VIT_PROF_PATCHIFY);
         VIT_TRY(launch_patchify(prec, d_images, c.patches, nb, e.img, c.sm_count, st));
-        cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(c.x, c.cls, c.pos, nb, e.tokens);
+        if (fused) {
+            if (prec == VIT_PREC_FP16)
+                cls_rows_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(c.x, static_cast<__half*>(c.xn), c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens);
+            else
+                cls_rows_ln_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, st>>>(c.x, static_cast<__nv_bfloat16*>(c.xn), c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens);
+        } else {
+            cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(c.x, c.cls, c.pos, nb, e.tokens);
+        }
         VIT_TRY(check_launch("cls_rows"));
     }
     {
         ProfScope ps(c, pf, VIT_PROF_EMBED_GEMM);
-        GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
-        VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
+        if (staged) {   // one CTA pair per image; class_token / pos_emb / token layout are pure TMA addressing
+            GemmParams p{nb * ((e.patches + 255) / 256) * 256, kDim, kDim, c.conv_b, c.x, nullptr, e.patches, e.tokens};
+            if (fused) {
+                p.stats_out = c.pstats;
+                p.stats_rows = stats_rows;
+            }
+            VIT_TRY(launch_gemm_embed(prec, fused, c.tm_patches3, c.tm_conv_w, c.tm_x3, c.tm_xn3, c.tm_pos, p, c.sm_count, st));
+        } else {
+            GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
+            VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
+        }
     }
     AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
-    // LayerNorm folded into the GEMMs (default): in_proj / mlp_0 read the operand-precision copy of the raw
-    // residual rows (c.xn) with the per-row statistics (c.pstats) that the previous residual GEMM -- for
-    // layer 0 the rowstats_cast kernel -- left behind.  Otherwise: a LayerNorm kernel before each of them.
-    const bool fused = staged && e.ln_fused;
-    const int stats_rows = static_cast<int>(c.stats_rows);
-    if (fused) {
-        ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
-        VIT_TRY(launch_rowstats_cast(prec, c.x, c.xn, c.pstats, rows, st));
-    }
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
         if (!fused) {
@@ -642,10 +691,10 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
                 p.bias = L.qkv_c;
                 p.colsum = L.qkv_s;
                 p.stats_in = c.pstats;
-                p.stats_parts = l == 0 ? 1 : 6;
+                p.stats_parts = 6;
                 p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
         }
         {
@@ -659,7 +708,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
                 p.stats_out = c.pstats;
                 p.stats_rows = stats_rows;
                 VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, c.tm_x, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
         }
         if (!fused) {
@@ -675,8 +724,8 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
                 p.stats_in = c.pstats;
                 p.stats_parts = 6;
                 p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_wf, c.tm_hid, c.tm_hid, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, c.tm_hid, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_wf, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
         }
         {
@@ -686,7 +735,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
                 p.stats_out = c.pstats;
                 p.stats_rows = stats_rows;
                 VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, p, c.sm_count, st));
+            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, c.tm_x, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
         }
     }
@@ -1085,7 +1134,7 @@ int vit_cuda_op_linear(const float* x, const float* W, const float* b, const flo
         VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * n));
         GemmParams p{m, n, k, db, dy, dy, 0, 0};
         VIT_TRY(make_tmap_f32(&tout, dy, n, m, GEMM_BM));
-        if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(precision, ta, tb, tout, p, sms, nullptr));
+        if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(precision, ta, tb, tout, tout, p, sms, nullptr));
         else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(precision, ta, tb, p, sms, nullptr));
         VIT_TRY(op_end("op_linear"));
         CU_TRY(cudaMemcpy(y, dy, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
@@ -1093,12 +1142,14 @@ int vit_cuda_op_linear(const float* x, const float* W, const float* b, const flo
         void* dy;
         VIT_TRY(s.alloc(&dy, (size_t)m * n * 2, true));
         GemmParams p{m, n, k, db, dy, nullptr, 0, 0};
+        CUtensorMap tout32;
         VIT_TRY(make_tmap(&tout, precision, dy, n, m, GEMM_BK, GEMM_BM));
+        VIT_TRY(make_tmap(&tout32, precision, dy, n, m, GEMM_BK, 32));
         if (epilogue == VIT_EPI_BIAS_GELU) {
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(precision, ta, tb, tout, p, sms, nullptr));
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(precision, ta, tb, tout, tout32, p, sms, nullptr));
             else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(precision, ta, tb, p, sms, nullptr));
         } else if (epilogue == VIT_EPI_BIAS) {
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(precision, ta, tb, tout, p, sms, nullptr));
+            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(precision, ta, tb, tout, tout32, p, sms, nullptr));
             else VIT_TRY(launch_gemm<EPI_BIAS>(precision, ta, tb, p, sms, nullptr));
         } else return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
         VIT_TRY(op_end("op_linear"));
@@ -1134,14 +1185,16 @@ int vit_cuda_op_ln_linear(const float* x, const float* ln_w, const float* ln_b, 
     CUtensorMap ta, tb, tout;
     VIT_TRY(make_tmap(&ta, precision, dxc, kDim, m, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&tb, precision, dwf, kDim, n, GEMM_BK, 128));
+    CUtensorMap tout32;
     VIT_TRY(make_tmap(&tout, precision, dy, n, m, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&tout32, precision, dy, n, m, GEMM_BK, 32));
     GemmParams p{m, n, kDim, dcv, dy, nullptr, 0, 0};
     p.colsum = dcs;
     p.stats_in = dst;
     p.stats_parts = 1;
     p.stats_rows = static_cast<int>(srows);
-    if (epilogue == VIT_EPI_BIAS_GELU) VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(precision, ta, tb, tout, tout, p, sms, nullptr));
-    else VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(precision, ta, tb, tout, tout, p, sms, nullptr));
+    if (epilogue == VIT_EPI_BIAS_GELU) VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(precision, ta, tb, tout, tout32, p, sms, nullptr));
+    else VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(precision, ta, tb, tout, tout32, p, sms, nullptr));
     VIT_TRY(op_end("op_ln_linear"));
     VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
     return op_end("op_ln_linear");
@@ -1280,13 +1333,37 @@ int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w
     VIT_TRY(s.alloc(&dpatch, (size_t)batch * patches * kDim * 2, true));
     VIT_TRY(s.alloc(reinterpret_cast<void**>(&dx), (size_t)batch * tokens * kDim * 4, true));
     CUtensorMap ta, tb;
-    VIT_TRY(make_tmap(&ta, precision, dpatch, kDim, (uint64_t)batch * patches, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&tb, precision, dw, kDim, kDim, GEMM_BK, 128));
     VIT_TRY(launch_patchify(precision, dimg, dpatch, batch, img_size, sms, nullptr));
-    cls_rows_kernel<<<(batch * kDim + 255) / 256, 256>>>(dx, dcls, dpos, batch, tokens);
-    VIT_TRY(check_launch("cls_rows"));
-    GemmParams p{batch * patches, kDim, kDim, dcb, dx, dpos, patches, tokens};
-    VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(precision, ta, tb, p, sms, nullptr));
+    if (gemm_impl() == 2) {
+        // the forward pass's path: conv_proj as the per-image EMBED kernel in its LayerNorm-producer form,
+        // class rows (with their copy and statistics) from cls_rows_ln_kernel
+        void* dxc;
+        float2* dst;
+        const size_t srows = ((size_t)batch * tokens + 255) / 256 * 256;
+        VIT_TRY(s.alloc(&dxc, (size_t)batch * tokens * kDim * 2, true));
+        VIT_TRY(s.alloc(reinterpret_cast<void**>(&dst), 6 * srows * sizeof(float2), true));
+        CUtensorMap tx3, txc3, tpos;
+        VIT_TRY(make_tmap_3d(&ta, precision, dpatch, kDim, patches, batch, GEMM_BM));
+        VIT_TRY(make_tmap_3d_f32(&tx3, dx, kDim, tokens, batch, GEMM_BM));
+        VIT_TRY(make_tmap_3d(&txc3, precision, dxc, kDim, tokens, batch, GEMM_BM));
+        VIT_TRY(make_tmap_f32(&tpos, dpos, kDim, tokens, GEMM_BM));
+        if (precision == VIT_PREC_FP16)
+            cls_rows_ln_kernel<__half><<<(batch + 7) / 8, 256>>>(dx, static_cast<__half*>(dxc), dst, (int)srows, dcls, dpos, batch, tokens);
+        else
+            cls_rows_ln_kernel<__nv_bfloat16><<<(batch + 7) / 8, 256>>>(dx, static_cast<__nv_bfloat16*>(dxc), dst, (int)srows, dcls, dpos, batch, tokens);
+        VIT_TRY(check_launch("cls_rows"));
+        GemmParams p{batch * ((patches + 255) / 256) * 256, kDim, kDim, dcb, dx, nullptr, patches, tokens};
+        p.stats_out = dst;
+        p.stats_rows = (int)srows;
+        VIT_TRY(launch_gemm_embed(precision, true, ta, tb, tx3, txc3, tpos, p, sms, nullptr));
+    } else {
+        VIT_TRY(make_tmap(&ta, precision, dpatch, kDim, (uint64_t)batch * patches, GEMM_BK, GEMM_BM));
+        cls_rows_kernel<<<(batch * kDim + 255) / 256, 256>>>(dx, dcls, dpos, batch, tokens);
+        VIT_TRY(check_launch("cls_rows"));
+        GemmParams p{batch * patches, kDim, kDim, dcb, dx, dpos, patches, tokens};
+        VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(precision, ta, tb, p, sms, nullptr));
+    }
     VIT_TRY(op_end("op_embed"));
     CU_TRY(cudaMemcpy(out, dx, (size_t)batch * tokens * kDim * 4, cudaMemcpyDeviceToHost));
     return 0;

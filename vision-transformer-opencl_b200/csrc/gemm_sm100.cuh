@@ -495,11 +495,22 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // EPI_WARPS: 8 (two warps per TMEM lane quarter) or 16 (four per quarter; for the GELU epilogue, whose
 // ~13 dependent FP32 ops + 2 MUFU per element are latency bound with only two warps per scheduler).
 template <typename T, int STAGES, int SLOTS, int EPI, int EPI_WARPS, bool LN = false, int CAST_BUFS = (LN && EPI == EPI_BIAS_RESIDUAL) ? 2 : 0,
-          bool STAGED = (EPI != EPI_BIAS_RESIDUAL)>
+          bool STAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GEMM_NON_EPI_WARPS + EPI_WARPS) * 32, 1)
 gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_cast,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
+    // EMBED (conv_proj, EPI_BIAS_RESIDUAL): row tiles never straddle images.  A is the patch matrix seen as
+    // [image][patch][768] (3-D map; an image takes ceil(patches / 256) row tiles, rows past p.patches are
+    // zero-filled), the "residual" is pos_embedding rows 1 + patch (tmap_res, 2-D, shared by all images), and
+    // the output goes to token row 1 + patch of the image through 3-D maps [image][token][768] that clip
+    // at the image's last token -- class_token / pos_emb / flatten_transpose of the reference
+    // (ViT_seq.c:52-101) as pure addressing.  p.M = images * tiles per image * 256.
+    static_assert(!EMBED || EPI == EPI_BIAS_RESIDUAL, "EMBED is a residual-epilogue variant");
+    const int embed_tpi = EMBED ? (p.patches + 255) / 256 : 1;  // row tiles per image
+    const uint32_t embed_rank = cluster_ctarank();
+    auto embed_img = [&](int mt) { return mt / embed_tpi; };
+    auto embed_patch0 = [&](int mt) { return (mt % embed_tpi) * 256 + static_cast<int>(embed_rank) * 128; };  // this CTA's first patch
     static_assert((CAST_BUFS > 0) == (LN && EPI == EPI_BIAS_RESIDUAL) && CAST_BUFS <= 2, "staging tiles of the operand-precision copy");
     // STAGED: the tile's parameters are put into shared memory one tile ahead by the loader warp (two buffers);
     // otherwise the epilogue threads load them themselves, from lines they prefetched into L1 a tile earlier.
@@ -550,7 +561,8 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         tma_prefetch_desc(&tmap_out);
-        if constexpr (CAST_BUFS > 0) tma_prefetch_desc(&tmap_cast);
+        if constexpr (CAST_BUFS > 0 || !kResidual) tma_prefetch_desc(&tmap_cast);
+        if constexpr (EMBED) tma_prefetch_desc(&tmap_res);
     }
     if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -592,7 +604,8 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-                    tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+                    if constexpr (EMBED) tma_load_3d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, embed_patch0(tile / tiles_n), embed_img(tile / tiles_n));
+                    else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
                     tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
                 }
                 __syncwarp();
@@ -695,7 +708,10 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const uint32_t slot = k % SLOTS, ph = (k / SLOTS) & 1;
                     mbar_wait(&slot_free[slot], ph ^ 1);
                     mbar_arrive_expect_tx(&res_full[slot], GEMM_SLOT_BYTES);
-                    tma_load_2d(smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, &tmap_out, &res_full[slot], n0 + c * CHUNK_COLS, m0);
+                    if constexpr (EMBED)
+                        tma_load_2d(smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, &tmap_res, &res_full[slot], n0 + c * CHUNK_COLS, 1 + embed_patch0(tile / tiles_n));
+                    else
+                        tma_load_2d(smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, &tmap_out, &res_full[slot], n0 + c * CHUNK_COLS, m0);
                 }
             }
         }
@@ -720,9 +736,9 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             float* sb = s_bias;
             float ln_rstd = 1.f, ln_nm = 0.f;  // LN consumer: this thread's row: rstd and -rstd * mean
             if constexpr (!STAGED) {
-                // Loaded by the epilogue threads themselves.  One buffer is enough: every chunk iteration below
-                // ends with a barrier after its last read of it, so nobody still reads the previous tile's values
-                // here.  The global-memory round trip is short because each thread asked for the NEXT tile's lines
+                // Loaded by the epilogue threads themselves.  One buffer is enough: in the residual kernel every
+                // chunk iteration below ends with a barrier after its last read of it, so nobody still reads the
+                // previous tile's values here (the other kernels regroup explicitly).  The global-memory round trip is short because each thread asked for the NEXT tile's lines
                 // (prefetch.global.L1) one tile ago; TMA traffic bypasses L1, so they are still there.
                 [[maybe_unused]] float2 part[6];
                 if constexpr (LN && !kResidual) {
@@ -732,6 +748,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         part[q] = (row_ok && q < p.stats_parts) ? __ldg(p.stats_in + static_cast<size_t>(q) * p.stats_rows + m0 + row)
                                                                 : make_float2(0.f, 0.f);
                 }
+                if constexpr (!kResidual) epi_bar_sync<EPI_THREADS>();  // the quarters run free in the chunk loop: regroup before the buffer is rewritten
                 if (etid < 256) {
                     const float bv = __ldg(p.bias + n0 + etid);
                     [[maybe_unused]] float cv = 0.f;
@@ -858,17 +875,37 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
                 fence_proxy_async_smem();
-                if (!kResidual && storer) tma_store_wait_read<SLOTS - 2>();  // frees the slot of chunk k + 1
+                if constexpr (!kResidual) {
+                    // Each TMEM lane quarter (two warps, 32 rows) stores its own 32 x 64 piece of the chunk:
+                    // the quarters only ever meet their own partner warp, so they drift apart and the MUFU
+                    // pipe (two ops per GELU: the limiter of the mlp_0 epilogue) is not left idle while all
+                    // eight warps gather at a chunk barrier.
+                    const bool qstorer = half == 0 && lane == 0;
+                    if (qstorer) tma_store_wait_read<SLOTS - 2>();  // frees this quarter's part of the slot of chunk k + 1
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                    if (qstorer) {
+                        tma_store_2d(&tmap_cast /* 32-row boxes of the output */, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES + quarter * 4096,
+                                     n0 + c * CHUNK_COLS, m0 + quarter * 32);
+                        tma_store_commit();
+                    }
+                    continue;
+                }
                 epi_bar_sync<EPI_THREADS>();
                 if (storer) {
-                    tma_store_2d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, m0);
+                    if constexpr (EMBED)
+                        tma_store_3d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, 1 + embed_patch0(tile / tiles_n), embed_img(tile / tiles_n));
+                    else
+                        tma_store_2d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, m0);
                     if constexpr (kResidual && LN) {
                         // Same bulk group as the fp32 chunk, so the wait below also covers the staging tile:
                         // it is rewritten two 64-column blocks later, i.e. after the barriers of chunks c + 1
                         // and c + 2, which this thread only joins after wait_read<1> has seen this group through.
                         // (With a single staging tile the storer simply waits for this group before moving on.)
-                        if (c & 1)
-                            tma_store_2d(&tmap_cast, smem + L::CAST_OFF + ((c >> 1) & (CAST_BUFS - 1)) * GEMM_SLOT_BYTES, n0 + (c >> 1) * 64, m0);
+                        if (c & 1) {
+                            const uint8_t* csrc = smem + L::CAST_OFF + ((c >> 1) & (CAST_BUFS - 1)) * GEMM_SLOT_BYTES;
+                            if constexpr (EMBED) tma_store_3d(&tmap_cast, csrc, n0 + (c >> 1) * 64, 1 + embed_patch0(tile / tiles_n), embed_img(tile / tiles_n));
+                            else tma_store_2d(&tmap_cast, csrc, n0 + (c >> 1) * 64, m0);
+                        }
                     }
                     tma_store_commit();
                     if constexpr (CAST_BUFS == 1) {
@@ -886,7 +923,12 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
             if constexpr (kResidual && LN) {
-                if (m0 + row < p.M)
+                if constexpr (EMBED) {
+                    const int patch = embed_patch0(tile / tiles_n) + row;
+                    if (patch < p.patches)
+                        p.stats_out[static_cast<size_t>(2 * (tile % tiles_n) + half) * p.stats_rows +
+                                    static_cast<size_t>(embed_img(tile / tiles_n)) * p.tokens + 1 + patch] = make_float2(st_sum, st_sq);
+                } else if (m0 + row < p.M)
                     p.stats_out[static_cast<size_t>(2 * (tile % tiles_n) + half) * p.stats_rows + m0 + row] = make_float2(st_sum, st_sq);
             }
             if constexpr (STAGED) {   // all reads of the staged parameters precede the last chunk's barrier
@@ -896,7 +938,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
             if ((acc ^= 1) == 0) acc_phase ^= 1;
         }
-        if (storer) tma_store_wait_all<0>();
+        if (kResidual ? storer : (half == 0 && lane == 0)) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

@@ -150,6 +150,35 @@ __global__ void cls_rows_kernel(float* __restrict__ X, const float* __restrict__
     X[static_cast<size_t>(b) * tokens * kDim + d] = cls[d] + pos[d];
 }
 
+// Same for the LayerNorm-folded forward: also the operand-precision copy of the row and its (sum, sum of
+// squares) as statistics part 0 (parts 1..5 zero), like the conv_proj epilogue emits for the patch rows.
+// One warp per image.
+template <typename T>
+__global__ void __launch_bounds__(256) cls_rows_ln_kernel(float* __restrict__ X, T* __restrict__ Xc, float2* __restrict__ stats,
+                                                          int stats_rows, const float* __restrict__ cls,
+                                                          const float* __restrict__ pos, int batch, int tokens) {
+    const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (img >= batch) return;
+    const int lane = threadIdx.x & 31;
+    const size_t r = static_cast<size_t>(img) * tokens;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float4 a = reinterpret_cast<const float4*>(cls)[lane + 32 * i], b = reinterpret_cast<const float4*>(pos)[lane + 32 * i];
+        const float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        reinterpret_cast<float4*>(X + r * kDim)[lane + 32 * i] = v;
+        uint2 o;
+        o.x = pack2<T>(v.x, v.y);
+        o.y = pack2<T>(v.z, v.w);
+        reinterpret_cast<uint2*>(Xc + r * kDim)[lane + 32 * i] = o;
+        s += (v.x + v.y) + (v.z + v.w);
+        q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane < 6) stats[static_cast<size_t>(lane) * stats_rows + r] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Final LayerNorm on the class rows only (the reference normalises all rows and keeps row 0,
 // ViT_seq.c:429-433), fp32 out.  One warp per image.
