@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""Timeline of the persistent attention kernel: runs it with the debug trace (CTA 0, first 16 items)
-and prints, per item, when each pipeline event happened (SM clock cycles relative to the first event).
-    python tools/attn_trace.py [batch=128] [tokens=197]"""
+"""Timeline of the attention kernel: runs it with the debug trace (CTA 0, first 16 units) and prints when
+each pipeline event happened (SM clock cycles relative to the first event).
+    python tools/attn_trace.py [batch=160] [tokens=197]
+Streaming kernel (default): a unit is one 128-row query tile.  Persistent kernel (VIT_ATTN_IMPL=2): see
+git history of this tool."""
 import sys
 from pathlib import Path
 
@@ -17,15 +19,13 @@ V.attention_trace(qkv, batch, tokens)  # warm-up (module load, L2)
 tr = V.attention_trace(qkv, batch, tokens).astype(np.int64)
 t0 = tr[tr > 0].min()
 rel = np.where(tr > 0, tr - t0, -1)
-n_items = min(16, (batch * 12 + 147) // 148)
-names = {w: ["start", "S_rdy", "P_done", "O_rdy", "O_ld", "end"] for w in range(16)}
-print(f"batch={batch} tokens={tokens}: items traced {n_items}; cycles relative to first event")
-for it in range(n_items):
-    print(f"--- item {it}")
-    print(f"  producer TMA issue {rel[16, it, 0]:7d} | MMA: S0 {rel[17, it, 0]:7d} S1 {rel[18, it, 0]:7d} PV0 {rel[17, it, 1]:7d} PV1 {rel[18, it, 1]:7d}")
-    for w in (0, 3, 4, 8, 12, 14):
-        e = rel[w, it]
-        print(f"  warp {w:2d} (tile {w >> 3} half {"AB"[(w >> 2) & 1]}): " + " ".join(f"{n}={e[i]:7d}" for i, n in enumerate(names[w])) +
-              f" | wait_S {e[1] - e[0]:6d} softmax {e[2] - e[1]:6d} (pass1 {e[6] - e[1]:5d} xchg {e[7] - e[6]:5d} pass2 {e[2] - e[7]:5d}) wait_O {e[3] - e[2]:6d} epi {e[5] - e[3]:6d}")
-per = np.diff(rel[0, 1:n_items, 0])
-print("tile-0 period per item:", per.tolist(), " tile-1:", np.diff(rel[8, 1:n_items, 0]).tolist())
+print(f"batch={batch} tokens={tokens}; cycles relative to first event")
+for u in range(16):
+    print(f"--- unit {u}: producer(item) {rel[16, u, 0]:7d} | issuer: S {rel[17, u, 0]:7d} PV {rel[17, u, 1]:7d}")
+    for w in (0, 3, 4, 8, 10):
+        e = rel[w, u]
+        print(f"  exp warp {w:2d} (part {w >> 2} q{w & 3}): start={e[0]:7d} S_rdy={e[1]:7d} ref={e[6]:7d} P_done={e[2]:7d} | wait_S {e[1]-e[0]:6d} ref {e[6]-e[1]:5d} exp {e[2]-e[6]:6d}")
+    for w in (12, 14):
+        e = rel[w, u]
+        print(f"  out warp {w:2d}: O_rdy={e[3]:7d} O_ld={e[4]:7d} stored={e[5]:7d} | ld {e[4]-e[3]:5d} store {e[5]-e[4]:5d}")
+print("exp warp 0 period per unit:", np.diff(rel[0, 1:16, 0]).tolist())

@@ -474,6 +474,391 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
     }
 }
 
+
+// =============================================================================================
+// Streaming kernel (the one the engine uses for tokens <= 224).
+//
+// The persistent kernel above keeps the two query tiles of an item in two TMEM slots, and each slot is
+// a strictly serial chain  S MMA -> softmax -> PV MMA -> output epilogue -> next S MMA  (the next item's S
+// cannot be computed while P of this one still sits in the slot).  Its timeline (profiles/r1_attention_
+// trace.md, round-1 addendum) shows the softmax threads waiting or doing epilogue work for more than half
+// of every period, and the MUFU pipe -- one ex2 per score, the true floor of this kernel -- busy ~50 %.
+//
+// Here the unit of work is ONE 128-row query tile (an item is two consecutive units), the S accumulator
+// is DOUBLE BUFFERED across units, and the roles are split so that nobody who exponentiates ever waits:
+//
+//   TMEM     S[0] [0,kpad)   S[1] [kpad,2 kpad)   O [2 kpad, 2 kpad + 64)          (kpad <= 224)
+//   warps 0-11   exponentials: warp = part * 4 + lane quarter.  The 16-key chunks of a row are split into
+//                three contiguous ranges (13 chunks: 5 + 4 + 4), one per part, so THREE threads share a row.
+//                P (bf16) is written in place over the first half of the thread's own range.  When a unit
+//                is done they go straight on to the next one, whose S is already waiting in the other buffer.
+//   warps 12-15  output: one per lane quarter; O / row sum -> staging -> one TMA store of 32 rows, while
+//                the exponential warps are already in the next unit.
+//   warp 16      TMA producer (Q, K, V of an item, two stages)     warp 17  MMA issuer, TMEM owner
+//
+// Issue order of the tensor pipe:  S(0) | S(u+1), PV(u) | ...  -- S(u+1) overwrites the buffer that held
+// P(u-1), whose PV(u-1) was issued before it (the pipe executes in order); PV(u) waits for P(u) and for the
+// output warps to have drained O(u-1).
+//
+// Softmax: EXACT as in the persistent kernel (two passes, row maximum exchanged between the three parts),
+// otherwise single pass with the exponent offset m_ref = max of the LAST EIGHT scores of part 0's range --
+// columns that never receive P (a part's P fills only the first half of its range), so all three parts read
+// the same eight scores whatever their relative progress.
+constexpr int ATTN3_THREADS = 18 * 32;
+constexpr int ATTN3_EXP_WARPS = 12, ATTN3_W_OUT = 12, ATTN3_W_PRODUCER = 16, ATTN3_W_ISSUER = 17;
+constexpr int ATTN3_OSTAGE_BYTES = 4 * 2 * 4096;                       // [output warp][2] 32 rows x 128 B
+constexpr int ATTN3_XCH_BYTES = (2 * 3 * 128 + 2 * 3 * 128) * 4;       // sum [unit parity][part][row], max likewise
+__host__ inline int attn3_smem_bytes(int kpad) {
+    return 2 * attn2_stage_bytes(kpad) + ATTN3_OSTAGE_BYTES + ATTN3_XCH_BYTES + 256 + 1024;
+}
+
+template <typename T, bool EXACT>
+__global__ void __launch_bounds__(ATTN3_THREADS, 1)
+attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out32,
+                              const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kv_bytes = attn_kv_bytes(p.kpad);
+    const int stage_bytes = attn2_stage_bytes(p.kpad);
+    uint8_t* sO = smem + 2 * stage_bytes;
+    float* xsum = reinterpret_cast<float*>(sO + ATTN3_OSTAGE_BYTES);  // [unit parity][part][128]
+    float* xmax = xsum + 2 * 3 * 128;                                 // [unit parity][part][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xsum) + ATTN3_XCH_BYTES);
+    uint64_t* kv_full = bars;        // [2 stages] Q, K, V of an item landed (tx)
+    uint64_t* stage_free = bars + 2; // [2 stages] every MMA reading the stage has completed
+    uint64_t* s_full = bars + 4;     // [2 buffers] S in TMEM
+    uint64_t* p_full = bars + 6;     // [2 buffers] P written back (one arrival per exponential warp)
+    uint64_t* o_full = bars + 8;     // O in TMEM
+    uint64_t* o_free = bars + 9;     // O drained (one arrival per output warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = p.batch * 12;
+    const int nqt = p.tokens > 128 ? 2 : 1;
+    const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const int n_units = my_items * nqt;
+    const int nch = p.kpad / 16;
+    // contiguous chunk ranges of the three parts: sizes differ by at most one, larger ones first
+    const int sz = nch / 3, rem = nch - 3 * sz;
+    const int c0_1 = sz + (rem > 0), c0_2 = c0_1 + sz + (rem > 1);   // part 0: [0, c0_1)  part 1: [c0_1, c0_2)  part 2: [c0_2, nch)
+    const uint32_t o_col = 2 * p.kpad;
+
+    if (warp == ATTN3_W_PRODUCER && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_out32);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&stage_free[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], ATTN3_EXP_WARPS);
+        }
+        mbar_init(o_full, 1);
+        mbar_init(o_free, 4);
+        fence_barrier_init();
+    }
+    if (warp == ATTN3_W_ISSUER) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == ATTN3_W_PRODUCER) {
+        // ------------------------------------------------------------ TMA producer (as in the persistent kernel)
+        if (lane == 0) {
+            const int half_rows = p.kpad >> 1, half_bytes = half_rows * 128;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int s = it & 1;
+                const int img = item / 12, head = item - img * 12;
+                const int row0 = img * p.tokens;
+                uint8_t* sQ = smem + s * stage_bytes;
+                uint8_t* sK = sQ + kv_bytes;
+                uint8_t* sV = sK + kv_bytes;
+                mbar_wait(&stage_free[s], ((it >> 1) & 1) ^ 1);
+                ATTN_TRACE(warp, it, 0);
+                mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tma_load_2d(sQ + h * half_bytes, &tmap_qkv, &kv_full[s], head * ATTN_DH, row0 + h * half_rows);
+                    tma_load_2d(sK + h * half_bytes, &tmap_qkv, &kv_full[s], ATTN_DIM + head * ATTN_DH, row0 + h * half_rows);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d(sV + h * half_bytes, &tmap_qkv, &kv_full[s], 2 * ATTN_DIM + head * ATTN_DH, row0 + h * half_rows);
+                const int ahead = item + 2 * static_cast<int>(gridDim.x);
+                if (ahead < n_items) {
+                    const int img2 = ahead / 12, head2 = ahead - img2 * 12;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        tma_prefetch_l2_2d(&tmap_qkv, head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
+                        tma_prefetch_l2_2d(&tmap_qkv, ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
+                        tma_prefetch_l2_2d(&tmap_qkv, 2 * ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
+                    }
+                }
+            }
+        }
+    } else if (warp == ATTN3_W_ISSUER) {
+        // ------------------------------------------------------------ MMA issuer
+        const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
+        const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
+        auto issue_s = [&](int u) {  // S(u) = Q_t K^T into buffer u & 1
+            const int it = u / nqt, t = u - it * nqt, stage = it & 1;
+            if (t == 0) {
+                mbar_wait(&kv_full[stage], (it >> 1) & 1);
+                tc_fence_after();
+            }
+            ATTN_TRACE(warp, u, 0);
+            if (elect_one()) {
+                const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
+                const uint32_t k_addr = q_addr + kv_bytes;
+#pragma unroll
+                for (int k = 0; k < ATTN_DH / 16; ++k)
+                    umma_f16(tmem_base + (u & 1) * p.kpad, desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
+                             desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
+                umma_commit(&s_full[u & 1]);
+            }
+            __syncwarp();
+        };
+        if (n_units > 0) issue_s(0);
+        for (int u = 0; u < n_units; ++u) {
+            if (u + 1 < n_units) issue_s(u + 1);
+            mbar_wait(&p_full[u & 1], (u >> 1) & 1);
+            if (u > 0) mbar_wait(o_free, (u - 1) & 1);
+            tc_fence_after();
+            ATTN_TRACE(warp, u, 1);
+            const int it = u / nqt, t = u - it * nqt, stage = it & 1;
+            if (elect_one()) {
+                const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * kv_bytes;
+                const uint32_t pbase = tmem_base + (u & 1) * p.kpad;
+                for (int ks = 0; ks < nch; ++ks) {  // keys [16 ks, 16 ks + 16): P sits in the first half of its part's range
+                    const int c0 = ks >= c0_2 ? c0_2 : (ks >= c0_1 ? c0_1 : 0);
+                    umma_f16_ts(tmem_base + o_col, pbase + 16 * c0 + 8 * (ks - c0), desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
+                }
+                umma_commit(o_full);
+                if (t == nqt - 1) umma_commit(&stage_free[stage]);  // the item's last unit: Q, K, V no longer needed
+            }
+            __syncwarp();
+        }
+    } else if (warp < ATTN3_EXP_WARPS) {
+        // ------------------------------------------------------------ exponential warps
+        const int part = warp >> 2;
+        const int quarter = warp & 3;       // TMEM lane quarter (warp % 4)
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
+        const int ch0 = part == 0 ? 0 : (part == 1 ? c0_1 : c0_2);
+        const int ch1 = part == 0 ? c0_1 : (part == 1 ? c0_2 : nch);
+        const int nsteps = ch1 - ch0;
+        // reference columns of the single-pass softmax: the last eight of part 0's range (never written with P)
+        const int mcol = (nch == 1 && p.tokens <= 8) ? 0 : 16 * c0_1 - 8;
+        // The stream over this part's chunks:  tcgen05.ld -> FFMA2 -> ex2 -> FADD2 / pack -> tcgen05.st, the next
+        // chunk's load in flight while the current one is processed; `first` already holds (or is about to
+        // receive) chunk ch0.  P is written in place over the first half of the part's own range.  `before_last`
+        // runs just before the last chunk is processed (the other buffer is free by then).  Returns the row sum.
+        auto exp_stream = [&](uint32_t taddr, float moff, uint32_t* first, uint32_t* second, auto before_last) -> float {
+            const float2 sc2 = splat2(p.scale_log2), mo2 = splat2(moff);
+            float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};  // independent chains, packed adds
+            const uint32_t pbase = taddr + 16 * ch0;
+            auto exp_step = [&](const uint32_t* v, int i) {   // chunk ch0 + i of this part, all 16 keys valid
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 a = fma2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, mo2);
+                    const float2 e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+                    acc2[j & 1] = add2(acc2[j & 1], e);
+                    packed[j] = pack2<__nv_bfloat16>(e.x, e.y);
+                }
+                tmem_st_x8p(pbase + 8 * i, packed);   // in place: columns of this part that it has already read
+            };
+            auto exp_step_ragged = [&](const uint32_t* v, int i) {   // the row's last chunk (at 197 tokens: 5 valid keys)
+                const int base = (ch0 + i) * 16;
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k0 = base + 2 * j;
+                    float e0 = 0.f, e1 = 0.f;
+                    if (k0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
+                    if (k0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
+                    acc2[j & 1] = add2(acc2[j & 1], make_float2(e0, e1));
+                    packed[j] = pack2<__nv_bfloat16>(e0, e1);
+                }
+                tmem_st_x8p(pbase + 8 * i, packed);
+            };
+            // only the row's very last chunk can be ragged: it is peeled off the unrolled stream (one or two
+            // instances of the masked code instead of one per step -- the stream must stay instruction-cache friendly)
+            const int nfull = nsteps - ((ch1 == nch && (p.tokens & 15) != 0) ? 1 : 0);
+#pragma unroll
+            for (int i = 0; i < 6; i += 2) {
+                if (i < nfull) {
+                    tmem_ld_wait();
+                    if (i + 1 < nsteps) tmem_ld_x16p(pbase + (i + 1) * 16, second);
+                    else before_last();
+                    exp_step(first, i);
+                }
+                if (i + 1 < nfull) {
+                    tmem_ld_wait();
+                    if (i + 2 < nsteps) tmem_ld_x16p(pbase + (i + 2) * 16, first);
+                    else before_last();
+                    exp_step(second, i + 1);
+                }
+            }
+            if (nfull < nsteps) {
+                tmem_ld_wait();
+                before_last();
+                if (nfull & 1) exp_step_ragged(second, nfull);
+                else exp_step_ragged(first, nfull);
+            }
+            return (acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y);
+        };
+        auto unit_active = [&](int u) { return ((nqt == 2 ? (u & 1) : 0) * 128 + quarter * 32) < p.tokens && nsteps > 0; };
+        if constexpr (EXACT) {
+            for (int u = 0; u < n_units; ++u) {
+                const uint32_t taddr = tmem_base + lane_bits + (u & 1) * p.kpad;
+                float* my_sum = xsum + ((u & 1) * 3 + part) * 128 + row;
+                const bool quarter_active = ((nqt == 2 ? (u & 1) : 0) * 128 + quarter * 32) < p.tokens;
+                ATTN_TRACE(warp, u, 0);
+                mbar_wait(&s_full[u & 1], (u >> 1) & 1);
+                tc_fence_after();
+                ATTN_TRACE(warp, u, 1);
+                if (quarter_active) {   // a part without chunks still takes part in the maximum exchange
+                    uint32_t ra[16], rb[16];
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    for (int c = ch0; c < ch1; ++c) {
+                        uint32_t v[16];
+                        tmem_ld_x16p(taddr + c * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+                    }
+                    if (nsteps > 0) tmem_ld_x16p(taddr + ch0 * 16, ra);  // pass 2's first load flies during the exchange
+                    float* xm = xmax + (u & 1) * 3 * 128 + row;
+                    xm[part * 128] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    attn_bar_sync<96>(1 + quarter);
+                    const float mx = fmaxf(fmaxf(xm[0], xm[128]), xm[256]);
+                    ATTN_TRACE(warp, u, 6);
+                    *my_sum = exp_stream(taddr, -mx * p.scale_log2, ra, rb, [] {});
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
+                ATTN_TRACE(warp, u, 2);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[u & 1]);
+            }
+        } else {
+            // Single pass.  (Requesting the next unit's first loads during the last chunk of this one -- software
+            // pipelining across units -- was tried and LOST 5 %: the kernel is bound by TMEM read bandwidth,
+            // ~64 B/clk/SM for the 142 KB a unit reads, not by the latency of the first round trip.)
+            for (int u = 0; u < n_units; ++u) {
+                ATTN_TRACE(warp, u, 0);
+                mbar_wait(&s_full[u & 1], (u >> 1) & 1);
+                tc_fence_after();
+                ATTN_TRACE(warp, u, 1);
+                if (unit_active(u)) {
+                    uint32_t ra[16], rb[16];
+                    const uint32_t taddr = tmem_base + lane_bits + (u & 1) * p.kpad;
+                    tmem_ld_x8p(taddr + mcol, rb);
+                    tmem_ld_x16p(taddr + ch0 * 16, ra);
+                    tmem_ld_wait();
+                    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (mcol + 8 <= p.tokens) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) m4[j] = fmaxf(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (mcol + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rb[j]));
+                    }
+                    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    ATTN_TRACE(warp, u, 6);
+                    xsum[((u & 1) * 3 + part) * 128 + row] = exp_stream(taddr, fmaf(-mx, p.scale_log2, -ATTN_FAST_SHIFT), ra, rb, [] {});
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else if (((nqt == 2 ? (u & 1) : 0) * 128 + quarter * 32) < p.tokens) {
+                    xsum[((u & 1) * 3 + part) * 128 + row] = 0.f;   // a part without chunks in a live quarter
+                }
+                ATTN_TRACE(warp, u, 2);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[u & 1]);
+            }
+        }
+    } else if (warp < ATTN3_W_PRODUCER) {
+        // ------------------------------------------------------------ output warps
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t oaddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + o_col;
+        uint8_t* my_stage = sO + (warp - ATTN3_W_OUT) * 2 * 4096;
+        uint32_t n_stores = 0;
+        int u = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int img = item / 12, head = item - img * 12;
+            for (int t = 0; t < nqt; ++t, ++u) {
+                const bool warp_active = (t * 128 + quarter * 32) < p.tokens;
+                mbar_wait(o_full, u & 1);
+                tc_fence_after();
+                ATTN_TRACE(warp, u, 3);
+                if (!warp_active) {
+                    if (lane == 0) mbar_arrive(o_free);
+                    continue;
+                }
+                // all three parts' row sums were written before their p_full arrivals, which the PV MMA behind
+                // o_full waited for; read before o_free is released, so unit u + 2 cannot overwrite them earlier
+                const float* ps = xsum + (u & 1) * 3 * 128 + row;
+                const float row_sum = (ps[0] + ps[128]) + ps[256];
+                if constexpr (!EXACT) {
+                    if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN
+                }
+                const float inv_sum = fast_rcp(row_sum);
+                uint32_t r0[32], r1[32];
+                tmem_ld_x32(oaddr, r0);
+                tmem_ld_x32(oaddr + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(o_free);
+                    tma_store_wait_read<1>();   // the store that last used this staging buffer (two units ago) has read it
+                }
+                __syncwarp();
+                ATTN_TRACE(warp, u, 4);
+                uint8_t* sb = my_stage + (n_stores & 1) * 4096;
+                uint8_t* srow = sb + lane * 128;
+                const uint32_t sw = lane & 7;
+                const float2 inv2 = splat2(inv_sum);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t x[4], y[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 a = mul2(make_float2(__uint_as_float(r0[8 * j + 2 * q]), __uint_as_float(r0[8 * j + 2 * q + 1])), inv2);
+                        const float2 b = mul2(make_float2(__uint_as_float(r1[8 * j + 2 * q]), __uint_as_float(r1[8 * j + 2 * q + 1])), inv2);
+                        x[q] = pack2<T>(a.x, a.y);
+                        y[q] = pack2<T>(b.x, b.y);
+                    }
+                    *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<uint4*>(srow + (((4 + j) ^ sw) << 4)) = make_uint4(y[0], y[1], y[2], y[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {   // rows past the image's last token are clipped by the 3-D map
+                    tma_store_3d(&tmap_out32, sb, head * ATTN_DH, t * 128 + quarter * 32, img);
+                    tma_store_commit();
+                }
+                ++n_stores;
+                ATTN_TRACE(warp, u, 5);
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == ATTN3_W_ISSUER) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 }  // namespace vit
 
 namespace vit {

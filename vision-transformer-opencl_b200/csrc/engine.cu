@@ -299,6 +299,22 @@ int launch_attention_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const A
     kern<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem, st>>>(tqkv, tout, p);
     return check_launch("attention");
 }
+template <typename T, bool EXACT>
+int launch_attention_stream_t(const CUtensorMap& tqkv, const CUtensorMap& tout32, const AttnParams& p, int sm_count, cudaStream_t st) {
+    auto kern = attention_sm100_stream_kernel<T, EXACT>;
+    const int smem = attn3_smem_bytes(p.kpad);
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<std::min(p.batch * kHeads, sm_count), ATTN3_THREADS, smem, st>>>(tqkv, tout32, p);
+    return check_launch("attention_stream");
+}
+int attn_impl() {  // VIT_ATTN_IMPL=2: the two-slot persistent kernel instead of the streaming one (A/B testing)
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("VIT_ATTN_IMPL");
+        v = (s && atoi(s) == 2) ? 2 : 3;
+    }
+    return v;
+}
 template <typename T>
 int launch_attention_blocked_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count, cudaStream_t st) {
     auto kern = attention_sm100_blocked_kernel<T>;
@@ -315,18 +331,23 @@ int attention_load_box_rows(int tokens) {
 // tqkv: load map of the packed QKV activation with attention_load_box_rows(tokens) rows per box,
 // tout: 3-D store map of the output (make_tmap_3d, 128 rows per box)
 // exact: two-pass softmax (exact row maximum); otherwise the single-pass variant, which raises
-// g_attn_range_flag when a row left its exponent window (the caller then repeats with exact = true)
-int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count,
-                     cudaStream_t st, bool exact) {
+// g_attn_range_flag when a row left its exponent window (the caller then repeats with exact = true).
+// tout: 3-D store map of the output with 128-row boxes (persistent and key-blocked kernels), tout32: the same
+// with 32-row boxes (streaming kernel, one store per output warp).
+int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const CUtensorMap& tout32, const AttnParams& p,
+                     int sm_count, cudaStream_t st, bool exact) {
     if (p.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", p.tokens, ATTNL_MAX_TOKENS);
+    const bool h = prec == VIT_PREC_FP16;
     if (p.tokens > kAttnSingleBlockMaxTokens)
-        return prec == VIT_PREC_FP16 ? launch_attention_blocked_t<__half>(tqkv, tout, p, sm_count, st)
-                                     : launch_attention_blocked_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
-    if (exact)
-        return prec == VIT_PREC_FP16 ? launch_attention_t<__half, true>(tqkv, tout, p, sm_count, st)
-                                     : launch_attention_t<__nv_bfloat16, true>(tqkv, tout, p, sm_count, st);
-    return prec == VIT_PREC_FP16 ? launch_attention_t<__half, false>(tqkv, tout, p, sm_count, st)
-                                 : launch_attention_t<__nv_bfloat16, false>(tqkv, tout, p, sm_count, st);
+        return h ? launch_attention_blocked_t<__half>(tqkv, tout, p, sm_count, st) : launch_attention_blocked_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
+    if (attn_impl() == 3) {
+        if (exact) return h ? launch_attention_stream_t<__half, true>(tqkv, tout32, p, sm_count, st)
+                            : launch_attention_stream_t<__nv_bfloat16, true>(tqkv, tout32, p, sm_count, st);
+        return h ? launch_attention_stream_t<__half, false>(tqkv, tout32, p, sm_count, st)
+                 : launch_attention_stream_t<__nv_bfloat16, false>(tqkv, tout32, p, sm_count, st);
+    }
+    if (exact) return h ? launch_attention_t<__half, true>(tqkv, tout, p, sm_count, st) : launch_attention_t<__nv_bfloat16, true>(tqkv, tout, p, sm_count, st);
+    return h ? launch_attention_t<__half, false>(tqkv, tout, p, sm_count, st) : launch_attention_t<__nv_bfloat16, false>(tqkv, tout, p, sm_count, st);
 }
 // Reads and clears the current device's range flag (after the stream has been synchronised).
 int take_attn_range_flag(bool* was_set) {
@@ -445,7 +466,7 @@ struct DeviceCtx {
     // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
     // use, so TMA zero-fills loads and clips stores past the last image
     int maps_nb = -1;
-    CUtensorMap tm_patches3, tm_x3, tm_xn3 /* per-image 3-D views for conv_proj */, tm_pos, tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_hid32, tm_qkv_st32 /* 32-row store boxes */, tm_x, tm_q /* attention loads */, tm_kv /* attention store */;
+    CUtensorMap tm_patches3, tm_x3, tm_xn3 /* per-image 3-D views for conv_proj */, tm_pos, tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_hid32, tm_qkv_st32 /* 32-row store boxes */, tm_x, tm_q /* attention loads */, tm_kv /* attention store */, tm_kv32 /* attention store, 32-row boxes */;
     size_t ws_bytes = 0;
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
@@ -609,6 +630,7 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
     VIT_TRY(make_tmap(&c.tm_q, prec, c.qkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(e.tokens)));  // Q/K/V boxes
     VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                                   // per-image output tiles
+    VIT_TRY(make_tmap_3d(&c.tm_kv32, prec, c.ao, kDim, e.tokens, nb, 32));
     c.maps_nb = nb;
     return 0;
 }
@@ -699,7 +721,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
         }
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
-            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, ap, c.sm_count, st, e.attn_exact));
+            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, c.tm_kv32, ap, c.sm_count, st, e.attn_exact));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
@@ -1279,21 +1301,22 @@ static int op_attention_impl(const float* qkv, float* out, int batch, int tokens
         CU_TRY(cudaDeviceSynchronize());
     }
     VIT_TRY(s.alloc(&dout, rows * kDim * 2, true));
-    CUtensorMap tq, tkv;
+    CUtensorMap tq, tkv, tkv32;
     VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(tokens)));
     VIT_TRY(make_tmap_3d(&tkv, precision, dout, kDim, tokens, batch, 128));
+    VIT_TRY(make_tmap_3d(&tkv32, precision, dout, kDim, tokens, batch, 32));
     AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
     constexpr size_t kTraceLen = static_cast<size_t>(ATTN_TRACE_WARPS) * ATTN_TRACE_ITEMS * ATTN_TRACE_EVENTS;
     if (trace_out) VIT_TRY(s.alloc(reinterpret_cast<void**>(&p.trace), kTraceLen * 8, true));
     const char* ex = getenv("VIT_ATTN_EXACT");
     bool exact = ex && atoi(ex) != 0;
-    VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr, exact));
+    VIT_TRY(launch_attention(precision, tq, tkv, tkv32, p, sms, nullptr, exact));
     VIT_TRY(op_end("op_attention"));
     if (!exact && !trace_out) {  // same contract as vit_cuda_forward: repeat with the exact softmax when flagged
         bool flagged = false;
         VIT_TRY(take_attn_range_flag(&flagged));
         if (flagged) {
-            VIT_TRY(launch_attention(precision, tq, tkv, p, sms, nullptr, true));
+            VIT_TRY(launch_attention(precision, tq, tkv, tkv32, p, sms, nullptr, true));
             VIT_TRY(op_end("op_attention"));
         }
     }
