@@ -26,6 +26,8 @@ import numpy as np
 
 FLOP_PER_IMAGE_224 = 35_127_656_448  # matmul-only, 2 FLOP/MAC, un-padded 197 tokens
 # per-launch algorithmic FLOPs of one GEMM over `rows` token rows
+# DRAM bytes of one launch at B = 1024 from the ncu --set full capture committed under profiles/ (r1_ncu_layer_final.txt)
+NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_199_038_000, "out_gemm": 1_812_138_000, "fc1_gemm": 1_527_691_000, "fc2_gemm": 2_864_615_000}
 GEMM_FLOP_PER_ROW = {"qkv_gemm": 2 * 768 * 2304, "out_gemm": 2 * 768 * 768, "fc1_gemm": 2 * 768 * 3072, "fc2_gemm": 2 * 3072 * 768}
 
 
@@ -265,13 +267,16 @@ def run_ours(args):
             "model_tflops": FLOP_PER_IMAGE_224 * value / 1e12,
             "model_frac_of_peak": {"burst": FLOP_PER_IMAGE_224 * value / n_gpus / 1e12 / peaks["bf16_tflops"],
                                    "sustained": FLOP_PER_IMAGE_224 * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
-            "roofline": {"kernel": f"gemm_sm100_kernel ({dom})", "bound": "tensor", "achieved": dom_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": dom_tflops / peak, "traffic": None, "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
+            "roofline": {"kernel": f"gemm_sm100_staged_kernel ({dom})", "bound": "tensor", "achieved": dom_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": dom_tflops / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom) if B == 1024 else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_layer_final.txt" if B == 1024 else None,
+                         "algorithmic_flop_per_launch": GEMM_FLOP_PER_ROW[dom] * rows,
+                         "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
                          "ms_per_launch": dom_ms, "launches": prof[dom]["launches"]},
             "step_breakdown_ms": step_ms_by_cat,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h_imgs.nbytes), "d2h_bytes_per_step": int(h_logits.nbytes),
                     "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": int(launches), "clocks": clocks, "engine": info, "top1_checksum": int(top1.sum()),
+            "gpu_launches": int(launches), "clocks": clocks, "engine": eng.info(), "top1_checksum": int(top1.sum()),
         }
         if lat:
             out["batch1_latency"] = lat

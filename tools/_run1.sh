@@ -1,5 +1,8 @@
-timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "attention" > gpurun_out/t16_attn.log 2>&1; echo "attn rc=$?"; tail -2 gpurun_out/t16_attn.log
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/t16_bench.json 2> gpurun_out/t16_bench.err; echo "bench rc=$?"
+python -m pytest tests -m gpu -x -q > gpurun_out/t17_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t17_pytest.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/t17_bench.json 2> gpurun_out/t17_bench.err; echo "bench rc=$?"
 python -c "
-import json;d=json.load(open('gpurun_out/t16_bench.json'));print(d['value'],d['ms_per_step'],{k:round(v,2) for k,v in d['step_breakdown_ms'].items()},d['clocks']['sm_mhz'])"
-python tools/attn_trace.py 160 197 > gpurun_out/t16_trace_stream.log 2>&1; tail -1 gpurun_out/t16_trace_stream.log; sed -n 40,48p gpurun_out/t16_trace_stream.log
+import json;d=json.load(open('gpurun_out/t17_bench.json'));print(d['value'],d['ms_per_step'],{k:round(v,2) for k,v in d['step_breakdown_ms'].items()},d['e2e'],d['clocks'],d['batch1_latency'],d['roofline'],d['cpu_baseline'])"
+python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/t17_bench_ref.json 2>gpurun_out/t17_ref.err; cat gpurun_out/t17_bench_ref.json
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/t17_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/t17_smoke.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches_b1024_final.csv python tools/profile_one.py 1024 > gpurun_out/t17_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gemm_sm100_staged|attention_sm100" -s 5 -c 5 -o gpurun_out/t17_layer python tools/profile_one.py 1024 > gpurun_out/t17_ncu2.log 2>&1; tail -1 gpurun_out/t17_ncu2.log

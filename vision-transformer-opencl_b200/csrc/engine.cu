@@ -937,19 +937,27 @@ static int forward_host_once(const float* images_nchw, int n, float* logits_out,
     const int G = static_cast<int>(e.ctx.size());
     const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
     const int per_gpu = (n + G - 1) / G;  // contiguous shards
-    // Pass size: a shard is cut into >= 4 passes when it is large enough, so that the H2D copy of
-    // pass i+1 (copy stream, second image buffer) hides under the compute of pass i.
-    const int pass_size = std::min(e.max_batch, std::max(32, (per_gpu + 3) / 4));
-    const int max_passes = (per_gpu + pass_size - 1) / pass_size;
+    // Pass schedule of a shard: the H2D copy of pass i+1 (copy stream, second image buffer) hides under the
+    // kernels of pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB), and
+    // every later pass may be three times the previous one (PCIe Gen5 moves images ~3.4x faster than
+    // the kernels consume them) up to the workspace size.  1024 images: 32 + 96 + 288 + 608.
+    std::vector<int> pass_first, pass_count;
+    for (int done = 0, sz = 32; done < per_gpu; sz = std::min(e.max_batch, 3 * sz)) {
+        const int nb = std::min(std::min(sz, e.max_batch), per_gpu - done);
+        pass_first.push_back(done);
+        pass_count.push_back(nb);
+        done += nb;
+    }
+    const int max_passes = static_cast<int>(pass_first.size());
     // pass-major issue order so that all GPUs are fed before any host-side wait
     for (int pass = 0; pass < max_passes; ++pass) {
         for (int g = 0; g < G; ++g) {
             DeviceCtx& c = e.ctx[g];
             int lo, hi;
             vit_cuda_shard_range(n, G, g, &lo, &hi);
-            const int first = lo + pass * pass_size;
+            const int first = lo + pass_first[pass];
             if (first >= hi) continue;
-            const int nb = std::min(pass_size, hi - first);
+            const int nb = std::min(pass_count[pass], hi - first);
             const int buf = pass & 1;
             CU_TRY(cudaSetDevice(c.device));
             // H2D of this pass overlaps the previous pass's compute (other image buffer)
