@@ -472,6 +472,15 @@ struct DeviceCtx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
     size_t prof_used[VIT_PROF_NCAT] = {};
     timerEvents_t timer;
+    struct Graph {   // captured launch sequence of one small pass
+        int nb = 0;
+        const float* images = nullptr;
+        float* logits = nullptr;
+        bool attn_exact = false, ln_fused = true;
+        long long launches = 0;
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<Graph> graphs;
 };
 
 struct Engine {
@@ -519,6 +528,9 @@ void destroy_ctx(DeviceCtx& c) {
     if (c.device < 0) return;
     cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
+    for (auto& g : c.graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c.graphs.clear();
     for (void* p : c.allocs) cudaFree(p);
     c.allocs.clear();
     for (int i = 0; i < 2; ++i) {
@@ -659,7 +671,7 @@ struct ProfScope {
 };
 
 // Enqueue the whole forward for nb images already resident in d_images (fp32 NCHW) on c.stream.
-int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
+int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
     cudaStream_t st = c.stream;
     const int prec = e.prec;
     const int rows = nb * e.tokens;
@@ -767,6 +779,56 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     head_gemm_kernel<<<dim3((kClasses + 63) / 64, (nb + 63) / 64), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
                                                                                 kClasses);
     return check_launch("head_gemm");
+}
+
+// Small passes (batch-1 latency, BASELINE.json configs[1]) are launch bound: ~65 kernels of 5-20 us each.  Their
+// launch sequence is captured once per (pass size, buffers, softmax mode) into a CUDA graph and replayed with a
+// single launch.  VIT_GRAPHS=0 disables this.
+constexpr int kGraphMaxBatch = 8;
+bool graphs_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("VIT_GRAPHS");
+        v = (s && atoi(s) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
+    if (nb > kGraphMaxBatch || e.profiling || !graphs_enabled() || gemm_impl() != 2)
+        return enqueue_forward_kernels(c, e, d_images, nb, d_logits);
+    for (auto& g : c.graphs)
+        if (g.nb == nb && g.images == d_images && g.logits == d_logits && g.attn_exact == e.attn_exact && g.ln_fused == e.ln_fused) {
+            CU_TRY(cudaGraphLaunch(g.exec, c.stream));
+            g_launches.fetch_add(g.launches, std::memory_order_relaxed);
+            return 0;
+        }
+    // first time: run it once the ordinary way (sets the kernels' attributes, builds the tensor maps), then capture
+    VIT_TRY(enqueue_forward_kernels(c, e, d_images, nb, d_logits));
+    if (c.graphs.size() >= 16) return 0;   // a caller cycling through many buffers: stay with plain launches
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches.load();
+    CU_TRY(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_forward_kernels(c, e, d_images, nb, d_logits);
+    const cudaError_t ce = cudaStreamEndCapture(c.stream, &graph);
+    const long long captured = g_launches.load() - before;
+    g_launches.fetch_sub(captured, std::memory_order_relaxed);   // captured, not launched
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return set_err(VIT_E_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+    DeviceCtx::Graph g;
+    g.nb = nb;
+    g.images = d_images;
+    g.logits = d_logits;
+    g.attn_exact = e.attn_exact;
+    g.ln_fused = e.ln_fused;
+    g.launches = captured;
+    const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return set_err(VIT_E_CUDA, "graph instantiate: %s", cudaGetErrorString(ie));
+    c.graphs.push_back(g);
+    return 0;
 }
 
 size_t tensor_numel(int idx, int img) {
