@@ -79,6 +79,13 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
  * Pure host arithmetic (usable without a device); returns VIT_E_ARG on bad arguments. */
 int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi);
 
+/* The pass schedule vit_cuda_forward uses for a shard of n_images on one GPU: pass i covers images
+ * [first[i], first[i] + count[i]) of the shard.  The first pass is small (32 images) because its
+ * host-to-device copy is the only one not hidden under kernels; each later pass may be three times
+ * the previous one, up to max_batch.  Pure host arithmetic.  Returns the number of passes (<= cap)
+ * or a negative status. */
+int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, int cap);
+
 /* Device-resident variant for one GPU slot (0 <= gpu_slot < n_gpus): d_images and d_logits
  * are device pointers on that GPU, n <= max_batch_per_gpu.  Work is enqueued on the
  * engine's stream for that slot and the call returns after it has completed. */

@@ -105,3 +105,23 @@ def test_synthetic_assets_are_deterministic(vit):
     assert w384[3].size == 577 * 768 and np.array_equal(w384[6], a[6])
     net = vit.as_network(a)
     assert vit.lib.vit_validate_weights(net, 152, 224) == 0
+
+
+def test_pass_schedule_covers_the_shard_with_a_small_first_pass(vit):
+    """vit_cuda_forward's pass schedule (pure host arithmetic): contiguous, complete, first pass <= 32 images (its
+    H2D copy is the only exposed one), growth <= 3x per pass, never above the workspace size."""
+    for n, mb in [(1, 1), (1, 1024), (31, 64), (32, 32), (33, 1024), (100, 16), (1024, 1024), (1024, 256), (8192, 1024), (5000, 999)]:
+        sched = vit.pass_schedule(n, mb)
+        assert sum(c for _, c in sched) == n
+        pos = 0
+        for i, (f, c) in enumerate(sched):
+            assert f == pos and 0 < c <= mb
+            if i == 0:
+                assert c <= 32
+            else:
+                assert c <= 3 * sched[i - 1][1]
+            pos += c
+    assert vit.pass_schedule(0, 8) == []
+    assert vit.pass_schedule(1024, 1024) == [(0, 32), (32, 96), (128, 288), (416, 608)]
+    with pytest.raises(vit.VitCudaError):
+        vit.pass_schedule(100000, 1)   # more than 64 passes

@@ -955,6 +955,21 @@ int vit_cuda_forward_device(int gpu_slot, const float* d_images, int n, float* d
     return vit_cuda_sync(gpu_slot);
 }
 
+int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, int cap) {
+    if (n_images < 0 || max_batch <= 0 || !first || !count || cap <= 0) return set_err(VIT_E_ARG, "bad schedule arguments");
+    int n = 0;
+    for (int done = 0, sz = 32; done < n_images; sz = std::min(max_batch, 3 * sz)) {
+        // more passes than `cap` (a tiny max_batch): the last entry takes max_batch-sized steps
+        const int nb = std::min(std::min(sz, max_batch), n_images - done);
+        if (n == cap) return set_err(VIT_E_ARG, "pass schedule of %d images with max_batch %d needs more than %d passes", n_images, max_batch, cap);
+        first[n] = done;
+        count[n] = nb;
+        done += nb;
+        ++n;
+    }
+    return n;
+}
+
 int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi) {
     if (n < 0 || n_gpus <= 0 || g < 0 || g >= n_gpus || !lo || !hi) return set_err(VIT_E_ARG, "bad shard arguments");
     const int per_gpu = (n + n_gpus - 1) / n_gpus;
@@ -1003,13 +1018,11 @@ static int forward_host_once(const float* images_nchw, int n, float* logits_out,
     // kernels of pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB), and
     // every later pass may be three times the previous one (PCIe Gen5 moves images ~3.4x faster than
     // the kernels consume them) up to the workspace size.  1024 images: 32 + 96 + 288 + 608.
-    std::vector<int> pass_first, pass_count;
-    for (int done = 0, sz = 32; done < per_gpu; sz = std::min(e.max_batch, 3 * sz)) {
-        const int nb = std::min(std::min(sz, e.max_batch), per_gpu - done);
-        pass_first.push_back(done);
-        pass_count.push_back(nb);
-        done += nb;
-    }
+    std::vector<int> pass_first(64), pass_count(64);
+    const int n_sched = vit_cuda_pass_schedule(per_gpu, e.max_batch, pass_first.data(), pass_count.data(), 64);
+    if (n_sched < 0) return n_sched;
+    pass_first.resize(n_sched);
+    pass_count.resize(n_sched);
     const int max_passes = static_cast<int>(pass_first.size());
     // pass-major issue order so that all GPUs are fed before any host-side wait
     for (int pass = 0; pass < max_passes; ++pass) {

@@ -56,6 +56,7 @@ _sig("vit_cuda_init", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c
 _sig("vit_cuda_init_ex", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int)
 _sig("vit_cuda_forward", C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 _sig("vit_cuda_shard_range", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p)
+_sig("vit_cuda_pass_schedule", C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_forward_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_enqueue_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_sync", C.c_int, C.c_int)
@@ -242,6 +243,14 @@ def shard_range(n: int, n_gpus: int, g: int) -> tuple[int, int]:
     lo, hi = C.c_int(), C.c_int()
     _check(lib.vit_cuda_shard_range(n, n_gpus, g, C.byref(lo), C.byref(hi)))
     return lo.value, hi.value
+
+
+def pass_schedule(n_images: int, max_batch: int) -> list[tuple[int, int]]:
+    first, count = (C.c_int * 64)(), (C.c_int * 64)()
+    n = lib.vit_cuda_pass_schedule(n_images, max_batch, first, count, 64)
+    if n < 0:
+        _check(n)
+    return [(first[i], count[i]) for i in range(n)]
 
 
 def dev_alloc(slot: int, nbytes: int) -> int:
