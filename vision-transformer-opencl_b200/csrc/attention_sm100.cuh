@@ -562,6 +562,8 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();     // the set-up above overlaps the previous kernel's tail (programmatic dependent launch)
+    griddep_launch();
 
     if (warp == ATTN3_W_PRODUCER) {
         // ------------------------------------------------------------ TMA producer (as in the persistent kernel)

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "attention_sm100.cuh"
@@ -133,6 +134,31 @@ int check_launch(const char* what) {
     return 0;
 }
 
+// Launch with programmatic stream serialization (the kernel must call griddep_wait() before it touches anything
+// its predecessor wrote).  VIT_PDL=0: ordinary launches.
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("VIT_PDL");
+        v = (s && atoi(s) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 int attn_no_pingpong() {  // VIT_ATTN_NO_PINGPONG=1: tuning switch of the attention kernel (A/B testing)
     static int v = -1;
     if (v < 0) {
@@ -173,13 +199,12 @@ constexpr int kStagedStages = 5, kStagedSlots = 4;
 // LN = true: LayerNorm folded into the GEMM (consumer for EPI_BIAS / EPI_BIAS_GELU, producer for
 // EPI_BIAS_RESIDUAL, see gemm_sm100.cuh).  The producer gives one operand stage up for the two
 // staging tiles of the operand-precision copy.
-template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false>
+template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false, int kEpiWarps = 8>
 int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
                            const GemmParams& p, int sm_count, cudaStream_t st, const CUtensorMap* tres = nullptr) {
     constexpr int kPreFloats = !PSTAGED ? 0 : (LN ? 256 + 256 + 2 * 128 : 256);
     using L = GemmStagedSmem<STAGES, SLOTS, CAST, kPreFloats * 4>;
     static_assert(L::DYN_BYTES <= 232448, "shared memory budget");
-    constexpr int kEpiWarps = 8;  // 16 was measured no faster for the GELU epilogue (issue bound, not latency bound)
     auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED, EMBED>;
     static int configured_dev_mask = 0;
     int dev = 0;
@@ -194,7 +219,7 @@ int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const C
         return set_err(VIT_E_ARG, "LayerNorm-folded gemm: bad statistics arguments (N=%d K=%d)", p.N, p.K);
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int grid = 2 * std::min(tiles, sm_count / 2);
-    kern<<<grid, (GEMM_NON_EPI_WARPS + kEpiWarps) * 32, L::DYN_BYTES, st>>>(ta, tb, tout, tcast, tres ? *tres : tout, p);
+    CU_TRY(launch_pdl(kern, dim3(grid), dim3((GEMM_NON_EPI_WARPS + kEpiWarps) * 32), L::DYN_BYTES, st, ta, tb, tout, tcast, tres ? *tres : tout, p));
     return check_launch("gemm_staged");
 }
 int res_cfg() {  // VIT_RES_CFG: A/B switch of the residual GEMM's shared-memory split (tuning)
@@ -223,6 +248,9 @@ int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
         // 6 KB of staged parameters cost one output slot; loading them in the epilogue threads instead (4 slots)
         // measured 7 % slower on mlp_0
         if (res_cfg() == 4) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, false>(ta, tb, tout, tcast, p, sm_count, st);
+        if constexpr (EPI == EPI_BIAS_GELU) {
+            if (res_cfg() == 6) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, 3, 0, true, false, 16>(ta, tb, tout, tcast, p, sm_count, st);
+        }
         return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, 3, 0, true>(ta, tb, tout, tcast, p, sm_count, st);
     } else {
         if (res_cfg() == 5) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, false>(ta, tb, tout, tcast, p, sm_count, st);
@@ -304,7 +332,7 @@ int launch_attention_stream_t(const CUtensorMap& tqkv, const CUtensorMap& tout32
     auto kern = attention_sm100_stream_kernel<T, EXACT>;
     const int smem = attn3_smem_bytes(p.kpad);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<std::min(p.batch * kHeads, sm_count), ATTN3_THREADS, smem, st>>>(tqkv, tout32, p);
+    CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN3_THREADS), smem, st, tqkv, tout32, p));
     return check_launch("attention_stream");
 }
 int attn_impl() {  // VIT_ATTN_IMPL=2: the two-slot persistent kernel instead of the streaming one (A/B testing)
@@ -776,7 +804,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
     ProfScope ps(c, pf, VIT_PROF_HEAD);
     head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
     VIT_TRY(check_launch("head_ln"));
-    head_gemm_kernel<<<dim3((kClasses + 63) / 64, (nb + 63) / 64), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
+    head_gemm_kernel<<<dim3((kClasses + 7) / 8, std::min((nb + HEAD_IMGS - 1) / HEAD_IMGS, 16)), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
                                                                                 kClasses);
     return check_launch("head_gemm");
 }
@@ -1490,7 +1518,7 @@ int vit_cuda_op_head(const float* x, const float* ln_w, const float* ln_b, const
     VIT_TRY(s.alloc(reinterpret_cast<void**>(&dlog), (size_t)batch * kClasses * 4));
     head_ln_kernel<<<(batch + 7) / 8, 256>>>(dx, dlw, dlb, dcls, batch, tokens);
     VIT_TRY(check_launch("head_ln"));
-    head_gemm_kernel<<<dim3((kClasses + 63) / 64, (batch + 63) / 64), 256>>>(dcls, dhw, dhb, dlog, batch, kClasses);
+    head_gemm_kernel<<<dim3((kClasses + 7) / 8, std::min((batch + HEAD_IMGS - 1) / HEAD_IMGS, 16)), 256>>>(dcls, dhw, dhb, dlog, batch, kClasses);
     VIT_TRY(check_launch("head_gemm"));
     VIT_TRY(op_end("op_head"));
     CU_TRY(cudaMemcpy(logits, dlog, (size_t)batch * kClasses * 4, cudaMemcpyDeviceToHost));

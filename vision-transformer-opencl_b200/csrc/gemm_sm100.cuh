@@ -517,7 +517,6 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     static_assert(!(STAGED && EPI == EPI_BIAS_RESIDUAL), "the residual kernel's loader warp is busy");
     constexpr int PRE_FLOATS = !STAGED ? 0 : (LN ? 256 + 256 + 2 * 128 : 256);  // bias | colsum | (rstd, nm) per row
     using L = GemmStagedSmem<STAGES, SLOTS, CAST_BUFS, PRE_FLOATS * 4>;
-    static_assert(!LN || EPI_WARPS == 8, "LN variants use 8 epilogue warps");
     static_assert(EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESIDUAL, "staged epilogues");
     constexpr bool kResidual = EPI == EPI_BIAS_RESIDUAL;
     constexpr int BN = 256;
@@ -589,6 +588,8 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();     // everything above overlaps the previous kernel's tail; nothing below may
+    griddep_launch();
 
     if (warp == W_PRODUCER) {
         // ------------------------------------------------------------ operand producer (both CTAs)
@@ -882,7 +883,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     // eight warps gather at a chunk barrier.
                     const bool qstorer = half == 0 && lane == 0;
                     if (qstorer) tma_store_wait_read<SLOTS - 2>();  // frees this quarter's part of the slot of chunk k + 1
-                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(2 + quarter), "n"(PARTS * 32) : "memory");
                     if (qstorer) {
                         tma_store_2d(&tmap_cast /* 32-row boxes of the output */, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES + quarter * 4096,
                                      n0 + c * CHUNK_COLS, m0 + quarter * 32);

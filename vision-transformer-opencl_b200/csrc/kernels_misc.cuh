@@ -214,42 +214,44 @@ __global__ void __launch_bounds__(256) head_ln_kernel(const float* __restrict__ 
 }
 
 // Classifier head in fp32 on the CUDA cores: logits[b][c] = bias[c] + sum_k xn[b][k] * W[c][k]
-// (linear_layer with tokens = 1, ViT_seq.c:435).  0.002 % of the model's FLOPs; fp32 keeps the
-// logits free of operand rounding.  64x64 output tile, 4x4 per thread, K chunks of 16.
+// (linear_layer with tokens = 1, ViT_seq.c:435).  0.002 % of the model's FLOPs; fp32 keeps the logits free of
+// operand rounding.  One warp per class keeps its W row in registers (24 values per lane) and walks the images,
+// which a block of 8 warps stages through shared memory 8 at a time.  Per output the summation order is fixed
+// (lane-strided partial sums in ascending k, then a butterfly), so a logit does not depend on the batch size or
+// the image's position in it; and a batch of ONE image still spreads over 125 blocks (the previous 64x64-tiled
+// kernel ran 16 blocks for 134 us at batch 1).
+constexpr int HEAD_IMGS = 16;   // 48 KB of shared memory per block
 __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ xn, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ logits,
                                                         int batch, int classes) {
-    __shared__ float sA[16][64 + 4];
-    __shared__ float sW[16][64 + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int b0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < kDim; k0 += 16) {
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-            const int r = i >> 4, k = i & 15;
-            sA[k][r] = (b0 + r < batch) ? xn[static_cast<size_t>(b0 + r) * kDim + k0 + k] : 0.f;
-            sW[k][r] = (c0 + r < classes) ? W[static_cast<size_t>(c0 + r) * kDim + k0 + k] : 0.f;
-        }
+    __shared__ float4 sx[HEAD_IMGS][kDim / 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;
+    float4 w[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        w[i] = c < classes ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * kDim) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float bc = c < classes ? bias[c] : 0.f;
+    for (int b0 = blockIdx.y * HEAD_IMGS; b0 < batch; b0 += gridDim.y * HEAD_IMGS) {
+        const int nb = min(HEAD_IMGS, batch - b0);
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            float a[4], w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; w[i] = sW[k][tx * 4 + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
-        }
+        for (int i = threadIdx.x; i < nb * (kDim / 4); i += 256)
+            sx[i / (kDim / 4)][i % (kDim / 4)] = reinterpret_cast<const float4*>(xn + static_cast<size_t>(b0) * kDim)[i];
         __syncthreads();
+        for (int j = 0; j < nb; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const float4 x = sx[j][lane + 32 * i];
+                acc = fmaf(x.x, w[i].x, acc);
+                acc = fmaf(x.y, w[i].y, acc);
+                acc = fmaf(x.z, w[i].z, acc);
+                acc = fmaf(x.w, w[i].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && c < classes) logits[static_cast<size_t>(b0 + j) * classes + c] = acc + bc;
+        }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int b = b0 + ty * 4 + i, c = c0 + tx * 4 + j;
-            if (b < batch && c < classes) logits[static_cast<size_t>(b) * classes + c] = acc[i][j] + bias[c];
-        }
 }
 
 // fp32 -> operand precision (weights at init, test inputs), and back (test outputs).

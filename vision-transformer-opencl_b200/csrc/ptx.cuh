@@ -27,6 +27,12 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still
+// draining; griddep_wait() blocks until the predecessor has completed and its writes are visible (a no-op for an
+// ordinary launch), griddep_launch() lets the successor's CTAs be scheduled as this grid's CTAs retire.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
