@@ -74,6 +74,12 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size,
  * overlapped.  Synchronous: everything is on the host when the call returns. */
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out);
 
+/* Same for n separately allocated images (images[i] -> [3][S][S] fp32), the form the reference's
+ * loader produces (one malloc per image, Network.c:75-93) and ViT_opencl() receives: every pass is
+ * gathered into pinned staging buffers owned by the engine while the GPU works on the previous
+ * pass.  ViT_cuda() goes through this. */
+int vit_cuda_forward_scattered(const float* const* images, int n, float* logits_out, int* top1_out);
+
 /* The contiguous shard [*lo, *hi) of n images that GPU slot g of n_gpus processes in
  * vit_cuda_forward: ceil(n / n_gpus) images per slot, the last ones possibly fewer or none.
  * Pure host arithmetic (usable without a device); returns VIT_E_ARG on bad arguments. */

@@ -144,6 +144,25 @@ def test_single_pass_softmax_matches_exact_and_falls_back(vit, weights224, ref16
     assert np.array_equal(out, want)
 
 
+def test_scattered_images_and_pinned_logits_paths(vit, weights224, ref16):
+    """vit_cuda_forward_scattered (one allocation per image, as the reference's loader produces them) and the
+    pinned / pageable result paths of vit_cuda_forward all return the same bits."""
+    imgs, _ = ref16
+    with vit.Engine(weights224, 224, max_batch=8) as eng:     # 16 images: passes of 8
+        base = eng.forward(imgs)                                # pageable logits -> pinned staging inside the engine
+        parts = [np.ascontiguousarray(imgs[i]).copy() for i in range(len(imgs))]
+        scat, top1 = eng.forward_scattered(parts, want_top1=True)
+        h_logits, h_ptr = vit.pinned_empty((len(imgs), 1000))
+        h_imgs, h_imgs_ptr = vit.pinned_empty(imgs.shape)
+        h_imgs[...] = imgs
+        eng.forward_raw(h_imgs_ptr, len(imgs), h_ptr)           # pinned in, pinned out: direct copies
+        pinned = h_logits.copy()
+        vit.pinned_free(h_ptr)
+        vit.pinned_free(h_imgs_ptr)
+    assert np.array_equal(base, scat) and np.array_equal(base, pinned)
+    assert np.array_equal(top1, base.argmax(1))
+
+
 def test_reference_signature_adaptor(vit, weights224, ref16, oracle, tmp_path):
     """ViT_cuda(ImageData*, Network*, float**) + result file + comparator, the Main.c flow."""
     imgs, ref = ref16

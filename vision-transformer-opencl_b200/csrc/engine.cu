@@ -489,6 +489,11 @@ struct DeviceCtx {
     float* images[2] = {nullptr, nullptr};
     void *patches = nullptr, *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr;
     float *x = nullptr, *cls_ln = nullptr, *logits = nullptr;
+    float* h_stage[2] = {nullptr, nullptr};  // pinned staging for scattered host images (vit_cuda_forward_scattered), lazily allocated
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};   // the H2D copy out of h_stage[i] has completed
+    float* h_logits[2] = {nullptr, nullptr};        // pinned staging for logits when the caller's buffer is pageable
+    cudaEvent_t ev_logits[2] = {nullptr, nullptr};
+    int pend_first[2] = {0, 0}, pend_count[2] = {0, 0};  // logits waiting in h_logits[i] for their copy to the caller
     float2* pstats = nullptr;  // [6][max rows] partial (sum, sum of squares) of the residual rows (LN folding)
     size_t stats_rows = 0;
     // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
@@ -556,6 +561,12 @@ void destroy_ctx(DeviceCtx& c) {
     if (c.device < 0) return;
     cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c.h_stage[i]) cudaFreeHost(c.h_stage[i]);
+        if (c.ev_stage[i]) cudaEventDestroy(c.ev_stage[i]);
+        if (c.h_logits[i]) cudaFreeHost(c.h_logits[i]);
+        if (c.ev_logits[i]) cudaEventDestroy(c.ev_logits[i]);
+    }
     for (auto& g : c.graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     c.graphs.clear();
@@ -1006,21 +1017,43 @@ int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi) {
     return 0;
 }
 
-static int forward_host_once(const float* images_nchw, int n, float* logits_out, bool* range_flag);
+static int forward_host_once(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, bool* range_flag);
+
+static int forward_host(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, int* top1_out);
+// hand the logits parked in pinned staging buffer `buf` (if any) over to the caller's (pageable) array
+static int drain_logits(DeviceCtx& c, int buf, float* logits_out) {
+    if (c.pend_count[buf] == 0) return 0;
+    CU_TRY(cudaEventSynchronize(c.ev_logits[buf]));
+    memcpy(logits_out + static_cast<size_t>(c.pend_first[buf]) * kClasses, c.h_logits[buf], static_cast<size_t>(c.pend_count[buf]) * kClasses * sizeof(float));
+    c.pend_count[buf] = 0;
+    return 0;
+}
 
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out) {
+    if (!images_nchw) return set_err(VIT_E_ARG, "bad arguments");
+    return forward_host(images_nchw, nullptr, n, logits_out, top1_out);
+}
+
+int vit_cuda_forward_scattered(const float* const* images, int n, float* logits_out, int* top1_out) {
+    if (!images) return set_err(VIT_E_ARG, "bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!images[i]) return set_err(VIT_E_ARG, "image %d is NULL", i);
+    return forward_host(nullptr, images, n, logits_out, top1_out);
+}
+
+static int forward_host(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, int* top1_out) {
     Engine& e = g_eng;
     if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
-    if (!images_nchw || !logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (!logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
     if (n == 0) return 0;
     bool flagged = false;
-    VIT_TRY(forward_host_once(images_nchw, n, logits_out, &flagged));
+    VIT_TRY(forward_host_once(images_nchw, image_ptrs, n, logits_out, &flagged));
     if (flagged) {
         // some row left the single-pass softmax's exponent window: repeat with the exact two-pass softmax
         // (and stay there once this has happened three times -- the data evidently does it regularly)
         ++e.attn_fallbacks;
         e.attn_exact = true;
-        const int rc = forward_host_once(images_nchw, n, logits_out, &flagged);
+        const int rc = forward_host_once(images_nchw, image_ptrs, n, logits_out, &flagged);
         if (e.attn_fallbacks < 3) e.attn_exact = false;
         VIT_TRY(rc);
     }
@@ -1035,7 +1068,7 @@ int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* to
     return 0;
 }
 
-static int forward_host_once(const float* images_nchw, int n, float* logits_out, bool* range_flag) {
+static int forward_host_once(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, bool* range_flag) {
     Engine& e = g_eng;
     *range_flag = false;
     if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
@@ -1046,6 +1079,9 @@ static int forward_host_once(const float* images_nchw, int n, float* logits_out,
     // kernels of pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB), and
     // every later pass may be three times the previous one (PCIe Gen5 moves images ~3.4x faster than
     // the kernels consume them) up to the workspace size.  1024 images: 32 + 96 + 288 + 608.
+    cudaPointerAttributes pa;
+    const bool logits_pinned = cudaPointerGetAttributes(&pa, logits_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
     std::vector<int> pass_first(64), pass_count(64);
     const int n_sched = vit_cuda_pass_schedule(per_gpu, e.max_batch, pass_first.data(), pass_count.data(), 64);
     if (n_sched < 0) return n_sched;
@@ -1065,14 +1101,44 @@ static int forward_host_once(const float* images_nchw, int n, float* logits_out,
             CU_TRY(cudaSetDevice(c.device));
             // H2D of this pass overlaps the previous pass's compute (other image buffer)
             if (pass >= 2) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_done[buf], 0));
-            CU_TRY(cudaMemcpyAsync(c.images[buf], images_nchw + static_cast<size_t>(first) * img_elems,
-                                   static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+            const float* src = nullptr;
+            if (image_ptrs) {
+                // separately allocated images (the reference's loader, Network.c:75-93): gather this pass into the
+                // slot's pinned staging buffer while the GPU works on the previous pass
+                if (!c.h_stage[buf]) {
+                    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_stage[buf]), static_cast<size_t>(e.max_batch) * img_elems * sizeof(float), cudaHostAllocPortable));
+                    CU_TRY(cudaEventCreateWithFlags(&c.ev_stage[buf], cudaEventDisableTiming));
+                } else {
+                    CU_TRY(cudaEventSynchronize(c.ev_stage[buf]));   // its previous copy has left the buffer
+                }
+                for (int i = 0; i < nb; ++i)
+                    memcpy(c.h_stage[buf] + static_cast<size_t>(i) * img_elems, image_ptrs[first + i], img_elems * sizeof(float));
+                src = c.h_stage[buf];
+            } else {
+                src = images_nchw + static_cast<size_t>(first) * img_elems;
+            }
+            CU_TRY(cudaMemcpyAsync(c.images[buf], src, static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+            if (image_ptrs) CU_TRY(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
             CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
             CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
             VIT_TRY(enqueue_forward(c, e, c.images[buf], nb, c.logits));
             CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
-            CU_TRY(cudaMemcpyAsync(logits_out + static_cast<size_t>(first) * kClasses, c.logits,
-                                   static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+            if (logits_pinned) {
+                CU_TRY(cudaMemcpyAsync(logits_out + static_cast<size_t>(first) * kClasses, c.logits,
+                                       static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+            } else {
+                // a device-to-pageable copy would block the host until this pass is through, and with it the
+                // enqueueing (and gathering) of the next one: go through pinned staging, hand over later
+                if (!c.h_logits[buf]) {
+                    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_logits[buf]), static_cast<size_t>(e.max_batch) * kClasses * sizeof(float), cudaHostAllocPortable));
+                    CU_TRY(cudaEventCreateWithFlags(&c.ev_logits[buf], cudaEventDisableTiming));
+                }
+                VIT_TRY(drain_logits(c, buf, logits_out));
+                CU_TRY(cudaMemcpyAsync(c.h_logits[buf], c.logits, static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaEventRecord(c.ev_logits[buf], c.stream));
+                c.pend_first[buf] = first;
+                c.pend_count[buf] = nb;
+            }
         }
     }
     for (int g = 0; g < G; ++g) {
@@ -1080,6 +1146,7 @@ static int forward_host_once(const float* images_nchw, int n, float* logits_out,
         CU_TRY(cudaSetDevice(c.device));
         const cudaError_t se = cudaStreamSynchronize(c.stream);
         if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
+        for (int buf = 0; buf < 2; ++buf) VIT_TRY(drain_logits(c, buf, logits_out));
         if (!e.attn_exact) {
             bool f = false;
             VIT_TRY(take_attn_range_flag(&f));

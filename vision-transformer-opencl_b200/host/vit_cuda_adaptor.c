@@ -58,7 +58,6 @@ void ViT_cuda(ImageData* image, Network* networks, float** prb) {
     config_from_env();
     const int n = image[0].n;
     const int img = image[0].h;
-    const size_t per = (size_t)image[0].c * image[0].h * image[0].w;
     g_status = VIT_E_ARG;
     if (n <= 0 || image[0].c != 3 || image[0].h != image[0].w) {
         fprintf(stderr, "ViT_cuda: unsupported image batch %d x %d x %d x %d\n", n, image[0].c, image[0].h, image[0].w);
@@ -77,20 +76,21 @@ void ViT_cuda(ImageData* image, Network* networks, float** prb) {
         g_engine_img = img;
         g_engine_weights = networks;
     }
-    /* image[i].data are separate allocations (Network.c:80): gather into pinned staging */
-    float* staging = NULL;
-    float* logits = NULL;
-    int pinned = vit_cuda_host_alloc_pinned(((size_t)n * per + (size_t)n * VIT_NUM_CLASSES) * sizeof(float), (void**)&staging) == 0;
-    if (!pinned) staging = (float*)malloc(((size_t)n * per + (size_t)n * VIT_NUM_CLASSES) * sizeof(float));
-    if (!staging) {
+    /* image[i].data are separate allocations (Network.c:80): the engine gathers them pass by pass into its own
+     * pinned staging buffers, overlapped with the kernels of the previous pass */
+    const float** ptrs = (const float**)malloc((size_t)n * sizeof(*ptrs));
+    float* logits = (float*)malloc((size_t)n * VIT_NUM_CLASSES * sizeof(float));
+    if (!ptrs || !logits) {
+        free(ptrs);
+        free(logits);
         g_status = VIT_E_NOMEM;
         return;
     }
-    logits = staging + (size_t)n * per;
-    for (int i = 0; i < n; ++i) memcpy(staging + (size_t)i * per, image[i].data, per * sizeof(float));
-    g_status = vit_cuda_forward(staging, n, logits, NULL);
+    for (int i = 0; i < n; ++i) ptrs[i] = image[i].data;
+    g_status = vit_cuda_forward_scattered(ptrs, n, logits, NULL);
     if (g_status != 0) fail(prb, n, "forward");
     else
         for (int i = 0; i < n; ++i) vit_softmax(logits + (size_t)i * VIT_NUM_CLASSES, prb[i], VIT_NUM_CLASSES);
-    if (pinned) vit_cuda_host_free_pinned(staging); else free(staging);
+    free(ptrs);
+    free(logits);
 }

@@ -56,6 +56,7 @@ _sig("vit_cuda_init", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c
 _sig("vit_cuda_init_ex", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int)
 _sig("vit_cuda_forward", C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 _sig("vit_cuda_shard_range", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p)
+_sig("vit_cuda_forward_scattered", C.c_int, C.POINTER(_f32p), C.c_int, C.c_void_p, C.c_void_p)
 _sig("vit_cuda_pass_schedule", C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_forward_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_enqueue_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
@@ -187,6 +188,15 @@ class Engine:
         logits = np.empty((n, NUM_CLASSES), dtype=np.float32)
         top1 = np.empty(n, dtype=np.int32) if want_top1 else None
         _check(lib.vit_cuda_forward(images.ctypes.data, n, logits.ctypes.data, top1.ctypes.data if want_top1 else None))
+        return (logits, top1) if want_top1 else logits
+
+    def forward_scattered(self, images: list[np.ndarray], want_top1: bool = False):
+        """vit_cuda_forward_scattered: one separately allocated [3][S][S] array per image (the reference loader's form)."""
+        n = len(images)
+        ptrs = (_f32p * n)(*[fptr(a) for a in images])
+        logits = np.empty((n, NUM_CLASSES), dtype=np.float32)
+        top1 = np.empty(n, dtype=np.int32)
+        _check(lib.vit_cuda_forward_scattered(ptrs, n, logits.ctypes.data, top1.ctypes.data if want_top1 else None))
         return (logits, top1) if want_top1 else logits
 
     def forward_raw(self, images_ptr: int, n: int, logits_ptr: int):
