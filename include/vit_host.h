@@ -56,6 +56,12 @@ int vit_validate_weights(const Network network[], int count, int img_size);
 /* Writers for the two file formats (used by the synthetic-asset tools and the tests). */
 int save_image_data(const char* filename, const float* nchw, int n, int c, int h, int w);
 int save_weights(const char* directory, const Network network[], int count, int img_size);
+/* Weight cache: all tensors (as load_weights returns them, i.e. after its 1e-6 rounding) in ONE
+ * checksummed file, so a restart reads 330 MB sequentially instead of opening 152 files and
+ * re-rounding them (Network.c:119-194).  load_weights_blob validates magic, the tensor sizes for
+ * the stored image size and the checksum; on any failure nothing is returned (-1).  0 = ok. */
+int save_weights_blob(const char* path, const Network network[], int count, int img_size);
+int load_weights_blob(const char* path, Network network[], int count, int* img_size_out);
 
 /* ---- engine lifecycle with the reference's shape --------------------------------------- */
 

@@ -125,3 +125,32 @@ def test_pass_schedule_covers_the_shard_with_a_small_first_pass(vit):
     assert vit.pass_schedule(1024, 1024) == [(0, 32), (32, 96), (128, 288), (416, 608)]
     with pytest.raises(vit.VitCudaError):
         vit.pass_schedule(100000, 1)   # more than 64 passes
+
+
+def test_weight_cache_blob_round_trip_and_damage_detection(vit, tmp_path):
+    """The single-file weight cache: bit-exact round trip of all 152 tensors, and a flipped byte, a
+    truncated file or a foreign file are refused."""
+    w = vit.synth_weights(224, 42)
+    path = tmp_path / "weights.vitw"
+    assert vit.lib.save_weights_blob(str(path).encode(), vit.as_network(w), 152, 224) == 0
+    assert path.stat().st_size == 8 + 8 + 152 * 8 + sum(a.size for a in w) * 4 + 8
+    back = (vit.Tensor * 152)()
+    img = C.c_int(0)
+    assert vit.lib.load_weights_blob(str(path).encode(), back, 152, C.byref(img)) == 0 and img.value == 224
+    for i in range(152):
+        got = np.ctypeslib.as_array(back[i].data, shape=(back[i].size,))
+        assert np.array_equal(got, w[i]), i
+    vit.lib.free_weights(back, 152)
+    raw = bytearray(path.read_bytes())
+    raw[len(raw) // 2] ^= 0x40
+    bad = tmp_path / "damaged.vitw"
+    bad.write_bytes(raw)
+    assert vit.lib.load_weights_blob(str(bad).encode(), back, 152, None) != 0
+    bad.write_bytes(path.read_bytes()[:-100])
+    assert vit.lib.load_weights_blob(str(bad).encode(), back, 152, None) != 0
+    bad.write_bytes(b"not a cache")
+    assert vit.lib.load_weights_blob(str(bad).encode(), back, 152, None) != 0
+    # a tensor of the wrong size is refused at save time
+    short = [a for a in w]
+    short[6] = short[6][:-1].copy()
+    assert vit.lib.save_weights_blob(str(bad).encode(), vit.as_network(short), 152, 224) != 0

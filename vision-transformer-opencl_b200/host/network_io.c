@@ -226,3 +226,93 @@ int save_weights(const char* directory, const Network network[], int count, int 
     }
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight cache: the 152 tensors AFTER load_weights' 1e-6 rounding in ONE file,
+ * so a restart is a single sequential read instead of 152 opens + a rounding pass over 330 MB
+ * (Network.c:119-194).  Layout, little endian:
+ *     char magic[8] = "VITW0001";  uint32 img_size, count;  uint64 numel[count];
+ *     float data[sum numel];       uint64 fnv1a64(over everything before it)
+ * load_weights_blob verifies magic, tensor sizes for img_size and the checksum before handing
+ * anything out.
+ */
+static uint64_t fnv1a64(uint64_t h, const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) {
+        h ^= b[i];
+        h *= 0x100000001b3ull;
+    }
+    return h;
+}
+
+int save_weights_blob(const char* path, const Network network[], int count, int img_size) {
+    if (!path || !network || count != VIT_NUM_TENSORS) return -1;
+    if (vit_validate_weights(network, count, img_size) != 0) return -1;
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        fprintf(stderr, "save_weights_blob: cannot create %s: %s\n", path, strerror(errno));
+        return -1;
+    }
+    uint64_t h = 0xcbf29ce484222325ull;
+    const char magic[8] = {'V', 'I', 'T', 'W', '0', '0', '0', '1'};
+    const uint32_t head[2] = {(uint32_t)img_size, (uint32_t)count};
+    int ok = fwrite(magic, 1, 8, f) == 8 && fwrite(head, sizeof(uint32_t), 2, f) == 2;
+    h = fnv1a64(fnv1a64(h, magic, 8), head, sizeof(head));
+    for (int i = 0; ok && i < count; ++i) {
+        const uint64_t n = network[i].size;
+        ok = fwrite(&n, sizeof(n), 1, f) == 1;
+        h = fnv1a64(h, &n, sizeof(n));
+    }
+    for (int i = 0; ok && i < count; ++i) {
+        ok = fwrite(network[i].data, sizeof(float), network[i].size, f) == network[i].size;
+        h = fnv1a64(h, network[i].data, network[i].size * sizeof(float));
+    }
+    ok = ok && fwrite(&h, sizeof(h), 1, f) == 1;
+    if (fclose(f) != 0) ok = 0;
+    if (!ok) fprintf(stderr, "save_weights_blob: short write to %s\n", path);
+    return ok ? 0 : -1;
+}
+
+int load_weights_blob(const char* path, Network network[], int count, int* img_size_out) {
+    if (!path || !network || count != VIT_NUM_TENSORS) return -1;
+    for (int i = 0; i < count; ++i) {
+        network[i].data = NULL;
+        network[i].size = 0;
+    }
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        fprintf(stderr, "load_weights_blob: cannot open %s: %s\n", path, strerror(errno));
+        return -1;
+    }
+    char magic[8];
+    uint32_t head[2];
+    uint64_t h = 0xcbf29ce484222325ull, stored = 0;
+    int ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "VITW0001", 8) == 0 && fread(head, sizeof(uint32_t), 2, f) == 2 &&
+             head[1] == (uint32_t)count && head[0] % PATCH == 0 && head[0] > 0 && head[0] <= 1024;
+    if (!ok) fprintf(stderr, "load_weights_blob: %s is not a VITW0001 weight cache for %d tensors\n", path, count);
+    if (ok) h = fnv1a64(fnv1a64(h, magic, 8), head, sizeof(head));
+    for (int i = 0; ok && i < count; ++i) {
+        uint64_t n = 0;
+        ok = fread(&n, sizeof(n), 1, f) == 1 && n == vit_tensor_numel(i, (int)head[0]);
+        if (!ok) fprintf(stderr, "load_weights_blob: %s: tensor %d has the wrong size for img_size %u\n", path, i, head[0]);
+        h = fnv1a64(h, &n, sizeof(n));
+        network[i].size = (size_t)n;
+    }
+    for (int i = 0; ok && i < count; ++i) {
+        network[i].data = (float*)malloc(network[i].size * sizeof(float));
+        ok = network[i].data && fread(network[i].data, sizeof(float), network[i].size, f) == network[i].size;
+        if (!ok) fprintf(stderr, "load_weights_blob: %s: tensor %d unreadable\n", path, i);
+        else h = fnv1a64(h, network[i].data, network[i].size * sizeof(float));
+    }
+    if (ok) {
+        ok = fread(&stored, sizeof(stored), 1, f) == 1 && stored == h;
+        if (!ok) fprintf(stderr, "load_weights_blob: %s: checksum mismatch (file damaged or truncated)\n", path);
+    }
+    fclose(f);
+    if (!ok) {
+        free_weights(network, count);
+        return -1;
+    }
+    if (img_size_out) *img_size_out = (int)head[0];
+    return 0;
+}

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
 
 #include "vit_host.h"
@@ -22,7 +23,7 @@ static double now_s(void) {
 }
 
 int main(int argc, char** argv) {
-    const char *images_path = NULL, *weights_dir = NULL, *result_path = "cuda_result.txt", *answer_path = NULL;
+    const char *images_path = NULL, *weights_dir = NULL, *result_path = "cuda_result.txt", *answer_path = NULL, *cache_out = NULL;
     int n_limit = 0, synthetic = 0, img = 224;
     vit_host_config cfg = {1, 256, VIT_PREC_BF16};
     for (int i = 1; i < argc; ++i) {
@@ -30,6 +31,7 @@ int main(int argc, char** argv) {
         const char* v = (i + 1 < argc) ? argv[i + 1] : NULL;
         if (!strcmp(a, "--images") && v) images_path = v, ++i;
         else if (!strcmp(a, "--weights") && v) weights_dir = v, ++i;
+        else if (!strcmp(a, "--save-weight-cache") && v) cache_out = v, ++i;
         else if (!strcmp(a, "--result") && v) result_path = v, ++i;
         else if (!strcmp(a, "--answer") && v) answer_path = v, ++i;
         else if (!strcmp(a, "--n") && v) n_limit = atoi(v), ++i;
@@ -39,8 +41,8 @@ int main(int argc, char** argv) {
         else if (!strcmp(a, "--img") && v) img = atoi(v), ++i;
         else if (!strcmp(a, "--precision") && v) cfg.precision = strcmp(v, "fp16") ? VIT_PREC_BF16 : VIT_PREC_FP16, ++i;
         else {
-            fprintf(stderr, "usage: %s (--images FILE --weights DIR | --synthetic N [--img S]) [--n N] [--gpus G] "
-                            "[--max-batch B] [--precision bf16|fp16] [--result FILE] [--answer FILE]\n", argv[0]);
+            fprintf(stderr, "usage: %s (--images FILE --weights DIR|CACHEFILE | --synthetic N [--img S]) [--n N] [--gpus G] "
+                            "[--max-batch B] [--precision bf16|fp16] [--result FILE] [--answer FILE] [--save-weight-cache FILE]\n", argv[0]);
             return 2;
         }
     }
@@ -66,11 +68,22 @@ int main(int argc, char** argv) {
         images = load_image_data(images_path);
         if (!images) return 1;
         img = images[0].h;
-        const int loaded = load_weights(weights_dir, network, VIT_NUM_TENSORS);
-        if (loaded < 0) return 1;
-        printf("loaded %d / %d weight tensors from %s\n", loaded, VIT_NUM_TENSORS, weights_dir);
+        struct stat sb;
+        if (stat(weights_dir, &sb) == 0 && S_ISREG(sb.st_mode)) {   /* a weight cache written by --save-weight-cache */
+            int cached_img = 0;
+            if (load_weights_blob(weights_dir, network, VIT_NUM_TENSORS, &cached_img) != 0) return 1;
+            printf("loaded %d weight tensors (img_size %d) from cache %s\n", VIT_NUM_TENSORS, cached_img, weights_dir);
+        } else {
+            const int loaded = load_weights(weights_dir, network, VIT_NUM_TENSORS);
+            if (loaded < 0) return 1;
+            printf("loaded %d / %d weight tensors from %s\n", loaded, VIT_NUM_TENSORS, weights_dir);
+        }
     }
     if (vit_validate_weights(network, VIT_NUM_TENSORS, img) != 0) return 1;
+    if (cache_out) {
+        if (save_weights_blob(cache_out, network, VIT_NUM_TENSORS, img) != 0) return 1;
+        printf("wrote weight cache %s\n", cache_out);
+    }
 
     int n = images[0].n;
     if (n_limit > 0 && n_limit < n) {

@@ -95,6 +95,8 @@ _sig("vit_tensor_name", C.c_char_p, C.c_int, C.c_char_p, C.c_size_t)
 _sig("vit_validate_weights", C.c_int, C.POINTER(Tensor), C.c_int, C.c_int)
 _sig("save_image_data", C.c_int, C.c_char_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int)
 _sig("save_weights", C.c_int, C.c_char_p, C.POINTER(Tensor), C.c_int, C.c_int)
+_sig("save_weights_blob", C.c_int, C.c_char_p, C.POINTER(Tensor), C.c_int, C.c_int)
+_sig("load_weights_blob", C.c_int, C.c_char_p, C.POINTER(Tensor), C.c_int, _i32p)
 _sig("initialize_cuda", C.c_int)
 _sig("ViT_cuda", None, C.POINTER(ImageData), C.POINTER(Tensor), C.POINTER(_f32p))
 _sig("ViT_cuda_status", C.c_int)
