@@ -25,6 +25,7 @@ sys.path.insert(0, str(ROOT / "vision-transformer-opencl_b200"))
 import numpy as np
 
 FLOP_PER_IMAGE_224 = 35_127_656_448  # matmul-only, 2 FLOP/MAC, un-padded 197 tokens
+FLOP_PER_IMAGE = {224: FLOP_PER_IMAGE_224, 384: 110_968_700_928}  # 384: BASELINE.json configs[4] (577 tokens)
 # per-launch algorithmic FLOPs of one GEMM over `rows` token rows
 # DRAM bytes of one launch at B = 1024 from the ncu --set full capture committed under profiles/ (r1_ncu_layer_final.txt)
 NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_199_038_000, "out_gemm": 1_812_138_000, "fc1_gemm": 1_527_691_000, "fc2_gemm": 2_864_615_000}
@@ -175,13 +176,16 @@ def run_ours(args):
     prec = V.PREC_FP16 if args.precision == "fp16" else V.PREC_BF16
     B = args.batch
     peaks = load_peaks()
-    weights = V.synth_weights(224, 42)
-    eng = V.Engine(weights, 224, max_batch=B, n_gpus=1, device_ids=[local_rank], precision=prec)
+    S = args.img_size
+    T = (S // 16) ** 2 + 1
+    flop_per_image = FLOP_PER_IMAGE[S]
+    weights = V.synth_weights(S, 42)
+    eng = V.Engine(weights, S, max_batch=B, n_gpus=1, device_ids=[local_rank], precision=prec)
     info = eng.info()
 
     # synthetic batch (seed 7), distinct images per rank; pinned host copy for the end-to-end leg
-    h_imgs, h_imgs_ptr = V.pinned_empty((B, 3, 224, 224))
-    V.synth_images(B, 224, 7, first_index=rank * B, out=h_imgs)
+    h_imgs, h_imgs_ptr = V.pinned_empty((B, 3, S, S))
+    V.synth_images(B, S, 7, first_index=rank * B, out=h_imgs)
     h_logits, h_logits_ptr = V.pinned_empty((B, 1000))
     d_imgs = V.dev_alloc(0, h_imgs.nbytes)
     d_logits = V.dev_alloc(0, h_logits.nbytes)
@@ -252,24 +256,24 @@ def run_ours(args):
                "host_to_host_ms_median": float(np.median(host_ms)), "host_to_host_ms_p99": float(np.percentile(host_ms, 99)), "runs": 200}
 
     if rank == 0:
-        rows = B * 197
+        rows = B * T
         step_ms_by_cat = {k: v["ms"] / args.steps for k, v in prof.items()}
         dom = max(GEMM_FLOP_PER_ROW, key=lambda k: step_ms_by_cat[k])  # dominant kernel of the step
         dom_ms = prof[dom]["ms"] / max(prof[dom]["launches"], 1)
         dom_tflops = GEMM_FLOP_PER_ROW[dom] * rows / (dom_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]  # kernel timed inside a long step
         out = {
-            "metric": "ViT-B/16 224x224 inference throughput", "value": value, "unit": "images/s", "n_gpus": n_gpus,
+            "metric": f"ViT-B/16 {S}x{S} inference throughput", "value": value, "unit": "images/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"ViT-B/16 224x224 synthetic batch {B} per GPU ({n_gpus * B} total), 197 tokens, 12 layers, random-init weights (seed 42), fp32 residual stream",
-                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "l2": "inputs (617 MB/batch) and activations larger than the 126 MB L2"},
-            "model_tflops": FLOP_PER_IMAGE_224 * value / 1e12,
-            "model_frac_of_peak": {"burst": FLOP_PER_IMAGE_224 * value / n_gpus / 1e12 / peaks["bf16_tflops"],
-                                   "sustained": FLOP_PER_IMAGE_224 * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
+            "config": {"workload": f"ViT-B/16 {S}x{S} synthetic batch {B} per GPU ({n_gpus * B} total), {T} tokens, 12 layers, random-init weights (seed 42), fp32 residual stream",
+                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "l2": f"inputs ({h_imgs.nbytes // 1000000} MB/batch) and activations larger than the 126 MB L2"},
+            "model_tflops": flop_per_image * value / 1e12,
+            "model_frac_of_peak": {"burst": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops"],
+                                   "sustained": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
             "roofline": {"kernel": f"gemm_sm100_staged_kernel ({dom})", "bound": "tensor", "achieved": dom_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": dom_tflops / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom) if B == 1024 else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_layer_final.txt" if B == 1024 else None,
+                         "frac": dom_tflops / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom) if (B, S) == (1024, 224) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_layer_final.txt" if (B, S) == (1024, 224) else None,
                          "algorithmic_flop_per_launch": GEMM_FLOP_PER_ROW[dom] * rows,
                          "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
                          "ms_per_launch": dom_ms, "launches": prof[dom]["launches"]},
@@ -297,6 +301,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--img-size", type=int, choices=[224, 384], default=224, help="384: BASELINE.json configs[4] (use --batch 512)")
     ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-threads", type=int, default=0)

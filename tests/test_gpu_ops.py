@@ -130,7 +130,7 @@ def test_layernorm(vit, oracle, prec, rows):
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("batch,tokens", [(1, 197), (3, 197), (2, 64), (2, 128), (1, 224), (2, 130), (2, 17), (40, 197), (70, 100),
-                                          (1, 225), (1, 256), (2, 300), (2, 577), (1, 640), (30, 577)])
+                                          (1, 225), (1, 256), (2, 257), (2, 272), (2, 288), (2, 300), (1, 384), (2, 400), (2, 577), (1, 640), (30, 577)])
 def test_attention(vit, oracle, prec, batch, tokens):
     qkv = _round_qkv(_rand((batch * tokens, 2304), 14 + tokens), prec)
     got = vit.op_attention(qkv, batch, tokens, precision=prec)
@@ -144,13 +144,15 @@ def test_attention(vit, oracle, prec, batch, tokens):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-def test_attention_dominant_late_key(vit, oracle, prec):
-    """A key far down the row whose score exceeds everything in the first 32 columns by > 2^60 in the
-    softmax's exponent: the single-pass kernel must take its exact power-of-two repair path."""
-    batch, tokens = 2, 197
+@pytest.mark.parametrize("tokens,late_key", [(197, 150), (577, 500), (300, 290)])
+def test_attention_dominant_late_key(vit, oracle, prec, tokens, late_key):
+    """A key far down the row whose score exceeds the reference scores of the single-pass softmax by > 2^1000 in
+    the exponent: the kernel must flag the row and the operator must come back with the exact kernel's result
+    (single-block and key-blocked paths)."""
+    batch = 2
     qkv = _rand((batch * tokens, 2304), 77)
     qkv[:, :768] *= 4.0
-    qkv[150::tokens, 768:1536] = 6.0 * qkv[3::tokens, :768]   # key 150 of each image is aligned with query 3
+    qkv[late_key::tokens, 768:1536] = 6.0 * qkv[3::tokens, :768]   # that key of each image is aligned with query 3
     qkv = _round_qkv(qkv, prec)
     got = vit.op_attention(qkv, batch, tokens, precision=prec)
     ref = np.empty((batch * tokens, 768), dtype=np.float32)

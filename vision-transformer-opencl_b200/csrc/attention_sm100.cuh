@@ -1146,3 +1146,342 @@ attention_sm100_blocked_kernel(const __grid_constant__ CUtensorMap tmap_qkv /* b
 }
 
 }  // namespace vit
+
+namespace vit {
+
+// =============================================================================================
+// Streaming kernel for longer sequences (224 < tokens <= 640; ViT-B/16 at 384^2: 577 tokens), the
+// key-blocked sibling of attention_sm100_stream_kernel and the engine's default for that range.
+//
+// With the single-pass softmax the exponent offset of a row is FIXED once it has been read from the row's
+// first key block (eight scores of columns that never receive P), so the row's P blocks need no rescaling
+// and O simply accumulates over the key blocks: one pass over the keys, Q K^T computed once -- the exact
+// two-pass kernel above computes it twice and reads every S block twice.  Same roles as the single-block
+// streaming kernel: 12 exponential warps (three threads per row, contiguous chunk ranges inside each
+// key block, P in place), 4 output warps, TMA producer, one MMA issuer; S is double buffered per KEY
+// BLOCK (2 x up to 224 columns), O (64 columns) accumulates over a unit's blocks.  The head's whole K and V stay in
+// shared memory for all of its query tiles.
+//
+//   issue order:  S(g+1) | PV(g)  per key block g of the unit stream (S(g+1) overwrites the buffer whose P
+//   was consumed by PV(g-1), already issued); at a head boundary K/V are single buffered, so the next head's
+//   first S waits for this head's last PV.
+//
+// Rows whose scores leave the exponent window raise g_attn_range_flag exactly as in the single-block kernel;
+// the host then repeats the call with attention_sm100_blocked_kernel (exact).
+constexpr int ATTN4_THREADS = 18 * 32;
+// keys per S block: the row is cut into the fewest blocks of at most 224 keys (2 S buffers + O fit the 512 TMEM
+// columns), equally sized up to the 16-key chunk (577 tokens: 208 + 208 + 161)
+// -- and K, V of the head (rounded up to the 64-row TMA boxes) must fit 640 rows of shared memory each
+// (640 tokens: four blocks of 160 rather than three of 224)
+__host__ __device__ inline int attn4_kb_for(int tokens, int nkb) { return ((tokens + nkb - 1) / nkb + 15) / 16 * 16; }
+__host__ __device__ inline int attn4_blocks(int tokens) {
+    int nkb = (tokens + 223) / 224;
+    while ((nkb * attn4_kb_for(tokens, nkb) + 63) / 64 * 64 > 640) ++nkb;
+    return nkb;
+}
+__host__ __device__ inline int attn4_kb(int tokens) { return attn4_kb_for(tokens, attn4_blocks(tokens)); }
+constexpr int ATTN4_OSTAGE_BYTES = 4 * 4096;          // [output warp] 32 rows x 128 B
+constexpr int ATTN4_XCH_BYTES = 2 * 3 * 128 * 4;      // row sums [unit parity][part][row]
+__host__ __device__ inline int attn4_kv_rows(int tokens) { return (attn4_blocks(tokens) * attn4_kb(tokens) + 63) / 64 * 64; }  // 64-row TMA boxes
+__host__ inline int attn4_smem_bytes(int tokens) {
+    return 2 * attn4_kv_rows(tokens) * 128 + 2 * ATTN_Q_TILE_BYTES + ATTN4_OSTAGE_BYTES + ATTN4_XCH_BYTES + 256 + 1024;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ATTN4_THREADS, 1)
+attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_qkv /* box {64, 64 rows} */,
+                                      const __grid_constant__ CUtensorMap tmap_out32 /* 3-D, box {64, 32, 1} */, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nkb = attn4_blocks(p.tokens);          // key blocks per head
+    const int nq = (p.tokens + 127) / 128;           // query tiles (units) per head
+    const int kb = attn4_kb(p.tokens);               // keys per block
+    const int last_cols = ((p.tokens - (nkb - 1) * kb) + 15) & ~15;  // S columns of the last key block
+    const int kv_boxes = attn4_kv_rows(p.tokens) / 64;
+    const int kv_bytes = kv_boxes * 64 * 128;
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + kv_bytes;
+    uint8_t* sQ = sV + kv_bytes;                     // [2] 128 x 128 B
+    uint8_t* sO = sQ + 2 * ATTN_Q_TILE_BYTES;        // [output warp] staging
+    float* xsum = reinterpret_cast<float*>(sO + ATTN4_OSTAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xsum) + ATTN4_XCH_BYTES);
+    uint64_t* kv_full = bars;        // K, V of a head landed (tx)
+    uint64_t* kv_free = bars + 1;    // every MMA reading them has completed
+    uint64_t* q_full = bars + 2;     // [2] Q tile landed (tx)
+    uint64_t* q_free = bars + 4;     // [2] every S MMA of the unit has completed
+    uint64_t* s_full = bars + 6;     // [2] S block in TMEM
+    uint64_t* p_full = bars + 8;     // [2] P written back (one arrival per exponential warp)
+    uint64_t* o_full = bars + 10;    // O of a unit complete
+    uint64_t* o_free = bars + 11;    // O drained (one arrival per output warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_items = p.batch * 12;
+    const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const int n_units = my_items * nq;
+    const uint32_t o_col = 2 * kb;
+    // chunk ranges of the three parts inside a key block of `nch` 16-key chunks: sizes differ by at most one
+    auto part_lo = [](int nch, int part) {
+        const int sz = nch / 3, rem = nch - 3 * sz;
+        return part == 0 ? 0 : (part == 1 ? sz + (rem > 0) : 2 * sz + (rem > 0) + (rem > 1));
+    };
+
+    if (warp == ATTN3_W_PRODUCER && lane == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_out32);
+        mbar_init(kv_full, 1);
+        mbar_init(kv_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_free[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], ATTN3_EXP_WARPS);
+        }
+        mbar_init(o_full, 1);
+        mbar_init(o_free, 4);
+        fence_barrier_init();
+    }
+    if (warp == ATTN3_W_ISSUER) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();
+    griddep_launch();
+
+    if (warp == ATTN3_W_PRODUCER) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0, uq = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int img = item / 12, head = item - img * 12;
+                const int row0 = img * p.tokens;
+                mbar_wait(kv_free, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full, 2 * kv_bytes);
+                for (int j = 0; j < kv_boxes; ++j)
+                    tma_load_2d(sK + j * 64 * 128, &tmap_qkv, kv_full, ATTN_DIM + head * ATTN_DH, row0 + j * 64);
+                for (int j = 0; j < kv_boxes; ++j)
+                    tma_load_2d(sV + j * 64 * 128, &tmap_qkv, kv_full, 2 * ATTN_DIM + head * ATTN_DH, row0 + j * 64);
+                for (int t = 0; t < nq; ++t, ++uq) {
+                    const int b = uq & 1;
+                    mbar_wait(&q_free[b], ((uq >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&q_full[b], ATTN_Q_TILE_BYTES);
+                    tma_load_2d(sQ + b * ATTN_Q_TILE_BYTES, &tmap_qkv, &q_full[b], head * ATTN_DH, row0 + t * 128);
+                    tma_load_2d(sQ + b * ATTN_Q_TILE_BYTES + 64 * 128, &tmap_qkv, &q_full[b], head * ATTN_DH, row0 + t * 128 + 64);
+                }
+                const int next = item + static_cast<int>(gridDim.x);  // pull the next head's K, V towards L2
+                if (next < n_items) {
+                    const int img2 = next / 12, head2 = next - img2 * 12;
+                    for (int j = 0; j < kv_boxes; ++j) {
+                        tma_prefetch_l2_2d(&tmap_qkv, ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + j * 64);
+                        tma_prefetch_l2_2d(&tmap_qkv, 2 * ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + j * 64);
+                    }
+                }
+            }
+        }
+    } else if (warp == ATTN3_W_ISSUER) {
+        // ------------------------------------------------------------ MMA issuer
+        const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
+        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        const int n_blocks = n_units * nkb;
+        auto issue_s = [&](int g) {   // S block g of the stream: unit g / nkb, key block g % nkb, buffer g & 1
+            const int u = g / nkb, j = g - u * nkb;
+            if (j == 0) {
+                if (u % nq == 0) mbar_wait(kv_full, (u / nq) & 1);
+                mbar_wait(&q_full[u & 1], (u >> 1) & 1);
+                tc_fence_after();
+            }
+            if (elect_one()) {
+                const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(j == nkb - 1 ? last_cols : kb), 0, 0);
+                const uint32_t q_addr = smem_u32(sQ + (u & 1) * ATTN_Q_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < ATTN_DH / 16; ++k)
+                    umma_f16(tmem_base + (g & 1) * kb, desc_kmajor_sw128(q_addr, k), desc_kmajor_sw128(k_addr + j * kb * 128, k), idesc_s, k != 0);
+                umma_commit(&s_full[g & 1]);
+                if (j == nkb - 1) umma_commit(&q_free[u & 1]);   // the unit's last S: its Q tile may be replaced
+            }
+            __syncwarp();
+        };
+        if (n_blocks > 0) issue_s(0);
+        for (int g = 0; g < n_blocks; ++g) {
+            const int u = g / nkb, j = g - u * nkb;
+            const bool head_ends = j == nkb - 1 && (u % nq) == nq - 1;   // K, V are single buffered: no look-ahead across heads
+            if (g + 1 < n_blocks && !head_ends) issue_s(g + 1);
+            mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+            if (j == 0 && u > 0) mbar_wait(o_free, (u - 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const int nch = (j == nkb - 1 ? last_cols : kb) / 16;
+                const int lo1 = part_lo(nch, 1), lo2 = part_lo(nch, 2);
+                const uint32_t pbase = tmem_base + (g & 1) * kb;
+                for (int ks = 0; ks < nch; ++ks) {
+                    const int c0 = ks >= lo2 ? lo2 : (ks >= lo1 ? lo1 : 0);
+                    umma_f16_ts(tmem_base + o_col, pbase + 16 * c0 + 8 * (ks - c0), desc_mnmajor_sw128(v_addr + j * kb * 128, ks), idesc_o,
+                                (j | ks) != 0);
+                }
+                if (j == nkb - 1) {
+                    umma_commit(o_full);
+                    if (head_ends) umma_commit(kv_free);
+                }
+            }
+            __syncwarp();
+            if (g + 1 < n_blocks && head_ends) issue_s(g + 1);
+        }
+    } else if (warp < ATTN3_EXP_WARPS) {
+        // ------------------------------------------------------------ exponential warps
+        const int part = warp >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
+        const int mcol = 16 * part_lo(nkb > 1 ? kb / 16 : last_cols / 16, 1) - 8;  // last eight columns of part 0's range in block 0
+        int g = 0;
+        for (int u = 0; u < n_units; ++u) {
+            const int t = u % nq;
+            const bool warp_active = (t * 128 + quarter * 32) < p.tokens;
+            float moff = 0.f;
+            float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            for (int j = 0; j < nkb; ++j, ++g) {
+                const int nch = (j == nkb - 1 ? last_cols : kb) / 16;
+                const int ch0 = part_lo(nch, part), ch1 = part == 2 ? nch : part_lo(nch, part + 1);
+                const int nsteps = ch1 - ch0;
+                const int key0 = j * kb;
+                const uint32_t taddr = tmem_base + lane_bits + (g & 1) * kb;
+                mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                if (warp_active) {
+                    uint32_t ra[16], rb[16];
+                    if (j == 0) {
+                        tmem_ld_x8p(taddr + mcol, rb);
+                        if (nsteps > 0) tmem_ld_x16p(taddr + ch0 * 16, ra);
+                        tmem_ld_wait();
+                        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (mcol + i < p.tokens) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(rb[i]));
+                        moff = fmaf(-fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), p.scale_log2, -ATTN_FAST_SHIFT);
+                    } else if (nsteps > 0) {
+                        tmem_ld_x16p(taddr + ch0 * 16, ra);
+                    }
+                    const float2 sc2 = splat2(p.scale_log2), mo2 = splat2(moff);
+                    const uint32_t pbase = taddr + 16 * ch0;
+                    auto exp_step = [&](const uint32_t* v, int i) {
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float2 a = fma2(make_float2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), sc2, mo2);
+                            const float2 e = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+                            acc2[q & 1] = add2(acc2[q & 1], e);
+                            packed[q] = pack2<__nv_bfloat16>(e.x, e.y);
+                        }
+                        tmem_st_x8p(pbase + 8 * i, packed);
+                    };
+                    auto exp_step_ragged = [&](const uint32_t* v, int i) {   // the row's last chunk: keys past `tokens` get P = 0
+                        const int base = key0 + (ch0 + i) * 16;
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int k0 = base + 2 * q;
+                            float e0 = 0.f, e1 = 0.f;
+                            if (k0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * q]), p.scale_log2, moff));
+                            if (k0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * q + 1]), p.scale_log2, moff));
+                            acc2[q & 1] = add2(acc2[q & 1], make_float2(e0, e1));
+                            packed[q] = pack2<__nv_bfloat16>(e0, e1);
+                        }
+                        tmem_st_x8p(pbase + 8 * i, packed);
+                    };
+                    const int nfull = nsteps - ((j == nkb - 1 && ch1 == nch && (p.tokens & 15) != 0 && nsteps > 0) ? 1 : 0);
+#pragma unroll
+                    for (int i = 0; i < 6; i += 2) {
+                        if (i < nfull) {
+                            tmem_ld_wait();
+                            if (i + 1 < nsteps) tmem_ld_x16p(pbase + (i + 1) * 16, rb);
+                            exp_step(ra, i);
+                        }
+                        if (i + 1 < nfull) {
+                            tmem_ld_wait();
+                            if (i + 2 < nsteps) tmem_ld_x16p(pbase + (i + 2) * 16, ra);
+                            exp_step(rb, i + 1);
+                        }
+                    }
+                    if (nfull < nsteps) {
+                        tmem_ld_wait();
+                        if (nfull & 1) exp_step_ragged(rb, nfull);
+                        else exp_step_ragged(ra, nfull);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
+                if (j == nkb - 1 && warp_active) xsum[((u & 1) * 3 + part) * 128 + row] = (acc2[0].x + acc2[0].y) + (acc2[1].x + acc2[1].y);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g & 1]);
+            }
+        }
+    } else if (warp < ATTN3_W_PRODUCER) {
+        // ------------------------------------------------------------ output warps
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t oaddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + o_col;
+        uint8_t* sb = sO + (warp - ATTN3_W_OUT) * 4096;
+        int u = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int img = item / 12, head = item - img * 12;
+            for (int t = 0; t < nq; ++t, ++u) {
+                const bool warp_active = (t * 128 + quarter * 32) < p.tokens;
+                mbar_wait(o_full, u & 1);
+                tc_fence_after();
+                if (!warp_active) {
+                    if (lane == 0) mbar_arrive(o_free);
+                    continue;
+                }
+                const float* ps = xsum + (u & 1) * 3 * 128 + row;
+                const float row_sum = (ps[0] + ps[128]) + ps[256];
+                if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN
+                const float inv_sum = fast_rcp(row_sum);
+                uint32_t r0[32], r1[32];
+                tmem_ld_x32(oaddr, r0);
+                tmem_ld_x32(oaddr + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(o_free);
+                    tma_store_wait_read<0>();   // the previous store has left the staging tile
+                }
+                __syncwarp();
+                uint8_t* srow = sb + lane * 128;
+                const uint32_t sw = lane & 7;
+                const float2 inv2 = splat2(inv_sum);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint32_t x[4], y[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 a = mul2(make_float2(__uint_as_float(r0[8 * jj + 2 * q]), __uint_as_float(r0[8 * jj + 2 * q + 1])), inv2);
+                        const float2 b = mul2(make_float2(__uint_as_float(r1[8 * jj + 2 * q]), __uint_as_float(r1[8 * jj + 2 * q + 1])), inv2);
+                        x[q] = pack2<T>(a.x, a.y);
+                        y[q] = pack2<T>(b.x, b.y);
+                    }
+                    *reinterpret_cast<uint4*>(srow + ((jj ^ sw) << 4)) = make_uint4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<uint4*>(srow + (((4 + jj) ^ sw) << 4)) = make_uint4(y[0], y[1], y[2], y[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tmap_out32, sb, head * ATTN_DH, t * 128 + quarter * 32, img);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == ATTN3_W_ISSUER) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace vit

@@ -335,6 +335,14 @@ int launch_attention_stream_t(const CUtensorMap& tqkv, const CUtensorMap& tout32
     CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN3_THREADS), smem, st, tqkv, tout32, p));
     return check_launch("attention_stream");
 }
+template <typename T>
+int launch_attention_stream_blocked_t(const CUtensorMap& tqkv, const CUtensorMap& tout32, const AttnParams& p, int sm_count, cudaStream_t st) {
+    auto kern = attention_sm100_stream_blocked_kernel<T>;
+    const int smem = attn4_smem_bytes(p.tokens);
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN4_THREADS), smem, st, tqkv, tout32, p));
+    return check_launch("attention_stream_blocked");
+}
 int attn_impl() {  // VIT_ATTN_IMPL=2: the two-slot persistent kernel instead of the streaming one (A/B testing)
     static int v = -1;
     if (v < 0) {
@@ -366,8 +374,13 @@ int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout,
                      int sm_count, cudaStream_t st, bool exact) {
     if (p.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", p.tokens, ATTNL_MAX_TOKENS);
     const bool h = prec == VIT_PREC_FP16;
-    if (p.tokens > kAttnSingleBlockMaxTokens)
+    if (p.tokens > kAttnSingleBlockMaxTokens) {
+        // key-blocked: single-pass streaming kernel unless the exact softmax is asked for (or after a range flag)
+        if (!exact && attn_impl() == 3)
+            return h ? launch_attention_stream_blocked_t<__half>(tqkv, tout32, p, sm_count, st)
+                     : launch_attention_stream_blocked_t<__nv_bfloat16>(tqkv, tout32, p, sm_count, st);
         return h ? launch_attention_blocked_t<__half>(tqkv, tout, p, sm_count, st) : launch_attention_blocked_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
+    }
     if (attn_impl() == 3) {
         if (exact) return h ? launch_attention_stream_t<__half, true>(tqkv, tout32, p, sm_count, st)
                             : launch_attention_stream_t<__nv_bfloat16, true>(tqkv, tout32, p, sm_count, st);
