@@ -168,6 +168,8 @@ def run_ours(args):
     import vit_b200 as V
     rank, local_rank, world = dist_env()
     if world > 1:
+        # NCCL writes its version / debug lines to stdout; the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
