@@ -88,6 +88,38 @@ def test_forward_384_key_blocked_attention(vit, oracle):
             assert (err <= ATOL + RTOL * np.abs(ref)).mean() >= 0.99 and np.all(err <= 2 * ATOL + RTOL * np.abs(ref)), _report(got, ref)
 
 
+@pytest.mark.parametrize("img_size,n", [(32, 5), (64, 3), (208, 2), (240, 2)])
+def test_forward_odd_image_sizes(vit, oracle, img_size, n):
+    """Edge geometries: 32x32 (5 tokens: one 16-key chunk, one row quarter), 64x64 (17 tokens), 208x208 (170 tokens,
+    a second query tile of 42 rows) and 240x240 (226 tokens: the smallest size that takes the key-blocked attention
+    kernel, with a one-chunk last key block).  FP16 operands against the oracle within the stated tolerance."""
+    w = vit.synth_weights(img_size, 42)
+    imgs = vit.synth_images(n, img_size, 7)
+    ref = oracle.forward(w, imgs, img_size)
+    with vit.Engine(w, img_size, max_batch=2, precision=vit.PREC_FP16) as eng:
+        got, top1 = eng.forward(imgs, want_top1=True)
+        assert eng.info()["attention_fallbacks"] == 0
+    print(img_size, _report(got, ref))
+    _assert_top1(top1, ref, f"fp16 {img_size}")
+    assert np.all(np.abs(got - ref) <= ATOL + RTOL * np.abs(ref)), _report(got, ref)
+
+
+def test_empty_and_oversized_requests(vit, weights224):
+    with vit.Engine(weights224, 224, max_batch=2) as eng:
+        out = eng.forward(np.empty((0, 3, 224, 224), dtype=np.float32))
+        assert out.shape == (0, 1000)
+        d = vit.dev_alloc(0, 3 * 3 * 224 * 224 * 4)
+        with pytest.raises(vit.VitCudaError):
+            eng.enqueue_device(d, 3, d)          # more than max_batch on the device-resident path
+        vit.dev_free(0, d)
+    w640 = None
+    with pytest.raises(vit.VitCudaError) as ei:     # 26x26 patches + 1 = 677 tokens > 640
+        bad = vit.synth_weights(416, 42)
+        with vit.Engine(bad, 416, max_batch=1) as eng:
+            eng.forward(vit.synth_images(1, 416, 7))
+    assert "tokens" in str(ei.value)
+
+
 def test_batch_position_independence(vit, weights224, ref16):
     """An image's logits must not depend on its position in the batch or on the pass size
     (needed for bit-identical results across GPU counts)."""

@@ -12,9 +12,10 @@ import vit_b200 as V
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-w = V.synth_weights(224, 42)
-eng = V.Engine(w, 224, max_batch=B)
-imgs = V.synth_images(min(B, 64), 224, 7)
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 224
+w = V.synth_weights(S, 42)
+eng = V.Engine(w, S, max_batch=B)
+imgs = V.synth_images(min(B, 64), S, 7)
 imgs = np.ascontiguousarray(np.tile(imgs, ((B + imgs.shape[0] - 1) // imgs.shape[0], 1, 1, 1))[:B])
 d_imgs = V.dev_alloc(0, imgs.nbytes)
 d_logits = V.dev_alloc(0, B * 1000 * 4)

@@ -1043,11 +1043,13 @@ static int drain_logits(DeviceCtx& c, int buf, float* logits_out) {
 }
 
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out) {
+    if (n == 0 && g_eng.up) return 0;   // nothing to do, whatever the pointers are
     if (!images_nchw) return set_err(VIT_E_ARG, "bad arguments");
     return forward_host(images_nchw, nullptr, n, logits_out, top1_out);
 }
 
 int vit_cuda_forward_scattered(const float* const* images, int n, float* logits_out, int* top1_out) {
+    if (n == 0 && g_eng.up) return 0;
     if (!images) return set_err(VIT_E_ARG, "bad arguments");
     for (int i = 0; i < n; ++i)
         if (!images[i]) return set_err(VIT_E_ARG, "image %d is NULL", i);
@@ -1095,6 +1097,8 @@ static int forward_host_once(const float* images_nchw, const float* const* image
     cudaPointerAttributes pa;
     const bool logits_pinned = cudaPointerGetAttributes(&pa, logits_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    const bool images_pinned = images_nchw && cudaPointerGetAttributes(&pa, images_nchw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
     std::vector<int> pass_first(64), pass_count(64);
     const int n_sched = vit_cuda_pass_schedule(per_gpu, e.max_batch, pass_first.data(), pass_count.data(), 64);
     if (n_sched < 0) return n_sched;
@@ -1115,23 +1119,27 @@ static int forward_host_once(const float* images_nchw, const float* const* image
             // H2D of this pass overlaps the previous pass's compute (other image buffer)
             if (pass >= 2) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_done[buf], 0));
             const float* src = nullptr;
-            if (image_ptrs) {
-                // separately allocated images (the reference's loader, Network.c:75-93): gather this pass into the
-                // slot's pinned staging buffer while the GPU works on the previous pass
+            if (image_ptrs || !images_pinned) {
+                // separately allocated images (the reference's loader, Network.c:75-93) or pageable memory: gather this
+                // pass into the slot's pinned staging buffer while the GPU works on the previous pass
                 if (!c.h_stage[buf]) {
                     CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_stage[buf]), static_cast<size_t>(e.max_batch) * img_elems * sizeof(float), cudaHostAllocPortable));
                     CU_TRY(cudaEventCreateWithFlags(&c.ev_stage[buf], cudaEventDisableTiming));
                 } else {
                     CU_TRY(cudaEventSynchronize(c.ev_stage[buf]));   // its previous copy has left the buffer
                 }
-                for (int i = 0; i < nb; ++i)
-                    memcpy(c.h_stage[buf] + static_cast<size_t>(i) * img_elems, image_ptrs[first + i], img_elems * sizeof(float));
+                if (image_ptrs) {
+                    for (int i = 0; i < nb; ++i)
+                        memcpy(c.h_stage[buf] + static_cast<size_t>(i) * img_elems, image_ptrs[first + i], img_elems * sizeof(float));
+                } else {   // contiguous but pageable: a direct copy would be staged by the driver synchronously
+                    memcpy(c.h_stage[buf], images_nchw + static_cast<size_t>(first) * img_elems, static_cast<size_t>(nb) * img_elems * sizeof(float));
+                }
                 src = c.h_stage[buf];
             } else {
                 src = images_nchw + static_cast<size_t>(first) * img_elems;
             }
             CU_TRY(cudaMemcpyAsync(c.images[buf], src, static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
-            if (image_ptrs) CU_TRY(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
+            if (src == c.h_stage[buf]) CU_TRY(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
             CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
             CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
             VIT_TRY(enqueue_forward(c, e, c.images[buf], nb, c.logits));
