@@ -239,6 +239,25 @@ def run_ours(args):
     e2e_value = n_gpus * B * args.steps / e2e_s
     top1 = h_logits.argmax(1)
 
+    # ---- optional logit gather over NCCL (the path itself needs no collective: this only shows what gathering
+    #      the [B, 1000] fp32 logits of every rank onto every rank costs over NVLink)
+    gather_ms = None
+    if world > 1:
+        t_log = torch.empty((B, 1000), dtype=torch.float32, device="cuda")
+        t_all = torch.empty((world * B, 1000), dtype=torch.float32, device="cuda")
+        t_log.copy_(torch.from_numpy(h_logits))
+        for _ in range(3):
+            dist.all_gather_into_tensor(t_all, t_log)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_gather_into_tensor(t_all, t_log)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1) / 10)
+        assert torch.equal(t_all[rank * B:(rank + 1) * B], t_log)
+
     # ---- batch-1 latency (BASELINE.json configs[1]), device resident and host-to-host
     lat = None
     if rank == 0 and not args.no_latency:
@@ -284,6 +303,8 @@ def run_ours(args):
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "engine": eng.info(), "top1_checksum": int(top1.sum()),
         }
+        if gather_ms is not None:
+            out["nccl_logit_allgather_ms"] = gather_ms
         if lat:
             out["batch1_latency"] = lat
         if n_gpus == 1 and not args.no_cpu_baseline:
