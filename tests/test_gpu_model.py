@@ -120,6 +120,45 @@ def test_empty_and_oversized_requests(vit, weights224):
     assert "tokens" in str(ei.value)
 
 
+def test_against_committed_reference_golden_vectors(vit, weights224):
+    """The CUDA path against tests/golden/vit_seq_probs.npz -- outputs of the reference's OWN compiled ViT_seq()
+    (tests/golden/make_golden.py), without the oracle in between: same top-1, top-8 probabilities within the
+    reference comparator's 0.01 (comparator.c:70) and within what the stated logit tolerance allows."""
+    from pathlib import Path
+    gold = np.load(Path(__file__).resolve().parent / "golden" / "vit_seq_probs.npz")
+    imgs = vit.synth_images(3, 224, int(gold["images_seed"]))
+    for prec in (vit.PREC_FP16, vit.PREC_BF16):
+        with vit.Engine(weights224, 224, max_batch=4, precision=prec) as eng:
+            logits = eng.forward(imgs)
+        probs = np.empty_like(logits)
+        for i in range(3):
+            vit.lib.vit_softmax(vit.fptr(logits[i]), vit.fptr(probs[i]), 1000)
+        got = np.take_along_axis(probs, gold["top_idx"].astype(np.int64), 1)
+        assert np.abs(got - gold["top_prob"]).max() <= 0.01
+        assert np.allclose(got, gold["top_prob"], rtol=0.06, atol=1e-5)        # |dlogit| <= ~0.03 => |dp|/p <= ~0.06
+        assert np.array_equal(probs.argmax(1), gold["top_idx"][:, 0]) or np.all(
+            gold["top_prob"][:, 0] - gold["top_prob"][:, 1] < 0.06 * gold["top_prob"][:, 0])
+
+
+def test_full_size_batch_1024_properties(vit, weights224):
+    """BASELINE.json configs[2] size (1024 images, 201 728 token rows, every kernel at its full grid) through
+    size-independent properties: the batch is 64 distinct images repeated 16 times, so (1) all 16 copies of an
+    image must give bit-identical logits wherever they sit in the batch, (2) they must equal the logits of the
+    same image in a 64-image forward (different pass sizes, tile boundaries and row positions), and (3) the
+    checksum of the per-image checksums is reproducible run to run."""
+    base = vit.synth_images(64, 224, 7)
+    big = np.ascontiguousarray(np.tile(base, (16, 1, 1, 1)))
+    with vit.Engine(weights224, 224, max_batch=1024) as eng:
+        small = eng.forward(base)
+        out1 = eng.forward(big)
+        out2 = eng.forward(big)
+        assert eng.info()["attention_fallbacks"] == 0
+    assert np.isfinite(out1).all()
+    assert np.array_equal(out1, out2)
+    assert np.array_equal(out1.reshape(16, 64, 1000), np.broadcast_to(small, (16, 64, 1000)))
+    assert float(out1.astype(np.float64).sum(1).sum()) == float(out2.astype(np.float64).sum(1).sum())
+
+
 def test_batch_position_independence(vit, weights224, ref16):
     """An image's logits must not depend on its position in the batch or on the pass size
     (needed for bit-identical results across GPU counts)."""
