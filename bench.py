@@ -204,6 +204,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # The headline numbers (value, e2e, roofline, step breakdown) are measured with the FULL last layer -- every
+    # multiply-add of the reference's forward (FLOP_PER_IMAGE).  The engine's default (class-row pruning of the last
+    # layer, same logits, 6.3 % fewer multiply-adds) is measured separately below and reported under its own key.
+    eng.set_class_row_pruning(False)
+
     # ---- device-resident throughput (inputs in HBM, 617 MB per batch >> 126 MB L2)
     for _ in range(max(args.warmup, 3)):
         eng.enqueue_device(d_imgs, B, d_logits)
@@ -238,6 +243,27 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_gpus * B * args.steps / e2e_s
     top1 = h_logits.argmax(1)
+
+    # ---- the engine's default configuration: last layer pruned to the class rows (same logits)
+    eng.set_class_row_pruning(True)
+    for _ in range(3):
+        eng.enqueue_device(d_imgs, B, d_logits)
+    eng.sync()
+    barrier()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.enqueue_device(d_imgs, B, d_logits)
+    ms_pruned = max_over_ranks(eng.timer_stop())
+    eng.sync()
+    for _ in range(2):
+        eng.forward_raw(h_imgs_ptr, B, h_logits_ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.forward_raw(h_imgs_ptr, B, h_logits_ptr)
+    e2e_pruned_s = max_over_ranks(time.perf_counter() - t0)
+    top1_pruned = h_logits.argmax(1)
+    eng.set_class_row_pruning(False)
 
     # ---- optional logit gather over NCCL (the path itself needs no collective: this only shows what gathering
     #      the [B, 1000] fp32 logits of every rank onto every rank costs over NVLink)
@@ -288,7 +314,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"ViT-B/16 {S}x{S} synthetic batch {B} per GPU ({n_gpus * B} total), {T} tokens, 12 layers, random-init weights (seed 42), fp32 residual stream",
-                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "l2": f"inputs ({h_imgs.nbytes // 1000000} MB/batch) and activations larger than the 126 MB L2"},
+                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "last_layer": "all rows (class-row pruning off)", "l2": f"inputs ({h_imgs.nbytes // 1000000} MB/batch) and activations larger than the 126 MB L2"},
             "model_tflops": flop_per_image * value / 1e12,
             "model_frac_of_peak": {"burst": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops"],
                                    "sustained": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
@@ -303,6 +329,12 @@ def run_ours(args):
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "engine": eng.info(), "top1_checksum": int(top1.sum()),
         }
+        out["class_row_pruning"] = {
+            "note": "engine default: last encoder layer computes out_proj / LayerNorm / MLP for the class rows only (the head reads nothing else); "
+                    "same logits, 6.3 % of the multiply-adds not executed; NOT used for value / e2e / roofline above",
+            "value": n_gpus * B * args.steps / (ms_pruned * 1e-3), "unit": "images/s", "ms_per_step": ms_pruned / args.steps,
+            "e2e_value": n_gpus * B * args.steps / e2e_pruned_s, "executed_flop_per_image": flop_per_image - (2_199_515_136 if S == 224 else 0) if S == 224 else None,
+            "top1_equal_to_full": bool((top1_pruned == top1).all())}
         if gather_ms is not None:
             out["nccl_logit_allgather_ms"] = gather_ms
         if lat:

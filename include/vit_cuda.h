@@ -122,9 +122,17 @@ long long vit_cuda_launch_count(void);
  * The environment variable VIT_ATTN_EXACT=1 selects it at init. */
 int vit_cuda_set_attention_exact(int on);
 
+/* Last-layer pruning (default on; VIT_PRUNE_LAST=0 at init or this call with 0 turns it off).  The
+ * head reads only the class token of the last encoder layer (the reference computes all 197 rows and
+ * keeps row 0, ViT_seq.c:429-433), and after the last attention no token reads another one: with
+ * pruning the last layer runs in_proj for all rows (keys and values), attention for the class query
+ * only, and out_proj / LayerNorm / MLP on the [n][768] class rows.  The logits are the same
+ * function of the input; 6.3 % of the model's multiply-adds are never executed. */
+int vit_cuda_set_class_row_pruning(int on);
+
 /* Facts about the engine/device, for logs: fills up to n entries of
  * {sm_count, cc_major, cc_minor, max_batch, tokens, precision, n_gpus, ws_bytes>>20,
- *  attention_exact, attention_fallbacks}. */
+ *  attention_exact, attention_fallbacks, class_row_pruning}. */
 int vit_cuda_info(long long* out, int n);
 
 /* CUDA-event stopwatch on a slot's stream: start records an event, stop records a second one,

@@ -159,6 +159,33 @@ def test_full_size_batch_1024_properties(vit, weights224):
     assert float(out1.astype(np.float64).sum(1).sum()) == float(out2.astype(np.float64).sum(1).sum())
 
 
+def test_class_row_pruning_of_the_last_layer_keeps_the_logits(vit, oracle, weights224, ref16):
+    """Default engine: the last layer runs out_proj / LayerNorm / MLP only for the class rows (the only ones the head
+    reads).  Against the all-rows computation the logits differ only by the class-row attention's fp32 softmax
+    (instead of bf16 P on the tensor cores), i.e. far less than either differs from the oracle."""
+    imgs, ref = ref16
+    for prec in (vit.PREC_FP16, vit.PREC_BF16):
+        with vit.Engine(weights224, 224, max_batch=16, precision=prec) as eng:
+            assert eng.info()["class_row_pruning"] == 1
+            pruned = eng.forward(imgs)
+            eng.set_class_row_pruning(False)
+            full = eng.forward(imgs)
+            one = eng.forward(np.ascontiguousarray(imgs[3:4]))
+            eng.set_class_row_pruning(True)
+            one_p = eng.forward(np.ascontiguousarray(imgs[3:4]))
+        print("pruned vs full", np.abs(pruned - full).max(), "| pruned", _report(pruned, ref), "| full", _report(full, ref))
+        assert np.abs(pruned - full).max() < 5e-3
+        assert np.abs(pruned - ref).mean() <= 1.05 * np.abs(full - ref).mean() + 1e-5
+        assert np.array_equal(full[3:4], one) and np.array_equal(pruned[3:4], one_p)   # position independence in both modes
+    # 384x384 (key-blocked attention in the other layers)
+    w = vit.synth_weights(384, 42)
+    im = vit.synth_images(2, 384, 7)
+    r = oracle.forward(w, im, 384)
+    with vit.Engine(w, 384, max_batch=2, precision=vit.PREC_FP16) as eng:
+        got = eng.forward(im)
+    assert np.all(np.abs(got - r) <= ATOL + RTOL * np.abs(r)), _report(got, r)
+
+
 def test_batch_position_independence(vit, weights224, ref16):
     """An image's logits must not depend on its position in the batch or on the pass size
     (needed for bit-identical results across GPU counts)."""

@@ -507,6 +507,12 @@ struct DeviceCtx {
     float* h_logits[2] = {nullptr, nullptr};        // pinned staging for logits when the caller's buffer is pageable
     cudaEvent_t ev_logits[2] = {nullptr, nullptr};
     int pend_first[2] = {0, 0}, pend_count[2] = {0, 0};  // logits waiting in h_logits[i] for their copy to the caller
+    // compact [batch]-row buffers of the pruned last-layer tail (class rows only)
+    void *ao_c = nullptr, *xn_c = nullptr, *hid_c = nullptr;
+    float* x_c = nullptr;
+    float2* pstats_c = nullptr;
+    size_t stats_rows_c = 0;
+    CUtensorMap tm_ao_c, tm_x_c, tm_xn_c, tm_hid_c, tm_hid_c32;
     float2* pstats = nullptr;  // [6][max rows] partial (sum, sum of squares) of the residual rows (LN folding)
     size_t stats_rows = 0;
     // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
@@ -522,7 +528,7 @@ struct DeviceCtx {
         int nb = 0;
         const float* images = nullptr;
         float* logits = nullptr;
-        bool attn_exact = false, ln_fused = true;
+        bool attn_exact = false, ln_fused = true, prune_last = true;
         long long launches = 0;
         cudaGraphExec_t exec = nullptr;
     };
@@ -532,6 +538,7 @@ struct DeviceCtx {
 struct Engine {
     bool up = false;
     bool profiling = false;
+    bool prune_last = true;       // last layer: everything behind the attention for the class rows only (VIT_PRUNE_LAST=0: all rows)
     bool ln_fused = true;         // LayerNorm folded into the GEMMs (VIT_LN_FUSED=0: separate LayerNorm kernels)
     bool attn_exact = false;      // two-pass softmax (VIT_ATTN_EXACT=1, vit_cuda_set_attention_exact, or after a range flag)
     long long attn_fallbacks = 0; // forwards repeated with the exact softmax
@@ -669,6 +676,12 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
     VIT_TRY(dev_alloc(c, &c.ao, rows * kDim * 2, true));
     VIT_TRY(dev_alloc(c, &c.hid, rows * kHidden * 2, true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.cls_ln), B * kDim * 4, true));
+    VIT_TRY(dev_alloc(c, &c.ao_c, B * kDim * 2, true));
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.x_c), B * kDim * 4, true));
+    VIT_TRY(dev_alloc(c, &c.xn_c, B * kDim * 2, true));
+    VIT_TRY(dev_alloc(c, &c.hid_c, B * kHidden * 2, true));
+    c.stats_rows_c = (B + 255) / 256 * 256;
+    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.pstats_c), 6 * c.stats_rows_c * sizeof(float2), true));
     c.stats_rows = (rows + 255) / 256 * 256;
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.pstats), 6 * c.stats_rows * sizeof(float2), true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.logits), B * kClasses * 4, true));
@@ -689,6 +702,11 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap_3d_f32(&c.tm_x3, c.x, kDim, e.tokens, nb, GEMM_BM));
     VIT_TRY(make_tmap_3d(&c.tm_xn3, prec, c.xn, kDim, e.tokens, nb, GEMM_BM));
     VIT_TRY(make_tmap_f32(&c.tm_pos, c.pos, kDim, e.tokens, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_ao_c, prec, c.ao_c, kDim, nb, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap_f32(&c.tm_x_c, c.x_c, kDim, nb, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_xn_c, prec, c.xn_c, kDim, nb, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_hid_c, prec, c.hid_c, kHidden, nb, GEMM_BK, GEMM_BM));
+    VIT_TRY(make_tmap(&c.tm_hid_c32, prec, c.hid_c, kHidden, nb, GEMM_BK, 32));
     VIT_TRY(make_tmap(&c.tm_hid32, prec, c.hid, kHidden, rows, GEMM_BK, 32));
     VIT_TRY(make_tmap(&c.tm_qkv_st32, prec, c.qkv, 3 * kDim, rows, GEMM_BK, 32));
     VIT_TRY(make_tmap_f32(&c.tm_x, c.x, kDim, rows, GEMM_BM));                       // residual load + store
@@ -764,6 +782,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
         }
     }
     AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
+    bool pruned_tail = false;
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
         if (!fused) {
@@ -782,6 +801,43 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
                 VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
             } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
             else VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
+        }
+        if (l == kDepth - 1 && fused && e.prune_last) {
+            // Last layer: only the class token reaches the head, and no token reads another one after the attention.
+            // Attention for the class query alone (all keys and values), then out_proj / LayerNorm / MLP on the compact
+            // [nb][768] class rows: 1/197 of the rows of the other layers.
+            {
+                ProfScope ps(c, pf, VIT_PROF_ATTENTION);
+                if (prec == VIT_PREC_FP16)
+                    cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__half*>(c.ao_c), c.x_c, e.tokens);
+                else
+                    cls_attention_kernel<__nv_bfloat16><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__nv_bfloat16*>(c.ao_c), c.x_c, e.tokens);
+                VIT_TRY(check_launch("cls_attention"));
+            }
+            const int srows_c = static_cast<int>(c.stats_rows_c);
+            {
+                ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
+                GemmParams p{nb, kDim, kDim, L.out_b, c.x_c, c.x_c, 0, 0};
+                p.stats_out = c.pstats_c;
+                p.stats_rows = srows_c;
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao_c, L.tm_out_w, c.tm_x_c, c.tm_xn_c, p, c.sm_count, st));
+            }
+            {
+                ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
+                GemmParams p{nb, kHidden, kDim, L.fc1_c, c.hid_c, nullptr, 0, 0};
+                p.colsum = L.fc1_s;
+                p.stats_in = c.pstats_c;
+                p.stats_parts = 6;
+                p.stats_rows = srows_c;
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn_c, L.tm_fc1_wf, c.tm_hid_c, c.tm_hid_c32, p, c.sm_count, st));
+            }
+            {
+                ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
+                GemmParams p{nb, kDim, kHidden, L.fc2_b, c.x_c, c.x_c, 0, 0};
+                VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid_c, L.tm_fc2_w, c.tm_x_c, c.tm_x_c, p, c.sm_count, st));
+            }
+            pruned_tail = true;
+            break;
         }
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
@@ -826,7 +882,8 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
         }
     }
     ProfScope ps(c, pf, VIT_PROF_HEAD);
-    head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
+    if (pruned_tail) head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);
+    else head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
     VIT_TRY(check_launch("head_ln"));
     head_gemm_kernel<<<dim3((kClasses + 7) / 8, std::min((nb + HEAD_IMGS - 1) / HEAD_IMGS, 16)), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
                                                                                 kClasses);
@@ -849,7 +906,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     if (nb > kGraphMaxBatch || e.profiling || !graphs_enabled() || gemm_impl() != 2)
         return enqueue_forward_kernels(c, e, d_images, nb, d_logits);
     for (auto& g : c.graphs)
-        if (g.nb == nb && g.images == d_images && g.logits == d_logits && g.attn_exact == e.attn_exact && g.ln_fused == e.ln_fused) {
+        if (g.nb == nb && g.images == d_images && g.logits == d_logits && g.attn_exact == e.attn_exact && g.ln_fused == e.ln_fused && g.prune_last == e.prune_last) {
             CU_TRY(cudaGraphLaunch(g.exec, c.stream));
             g_launches.fetch_add(g.launches, std::memory_order_relaxed);
             return 0;
@@ -875,6 +932,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     g.logits = d_logits;
     g.attn_exact = e.attn_exact;
     g.ln_fused = e.ln_fused;
+    g.prune_last = e.prune_last;
     g.launches = captured;
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -940,6 +998,8 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size, in
         e.attn_fallbacks = 0;
         const char* lf = getenv("VIT_LN_FUSED");
         e.ln_fused = !(lf && atoi(lf) == 0);
+        const char* pl = getenv("VIT_PRUNE_LAST");
+        e.prune_last = !(pl && atoi(pl) == 0);
     }
     e.ctx.assign(n_gpus, DeviceCtx());
     for (int g = 0; g < n_gpus; ++g) {
@@ -988,6 +1048,12 @@ int vit_cuda_sync(int gpu_slot) {
                                         "this pass are invalid.  The engine has switched to the exact two-pass softmax: enqueue again");
         }
     }
+    return 0;
+}
+
+int vit_cuda_set_class_row_pruning(int on) {
+    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
+    g_eng.prune_last = on != 0;
     return 0;
 }
 
@@ -1182,10 +1248,10 @@ int vit_cuda_info(long long* out, int n) {
     const DeviceCtx& c = g_eng.ctx[0];
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, c.device));
-    const long long v[10] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
+    const long long v[11] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
                              (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20), g_eng.attn_exact ? 1 : 0,
-                             g_eng.attn_fallbacks};
-    for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+                             g_eng.attn_fallbacks, g_eng.prune_last ? 1 : 0};
+    for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
     return 0;
 }
 

@@ -180,6 +180,75 @@ __global__ void __launch_bounds__(256) cls_rows_ln_kernel(float* __restrict__ X,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Class-row attention for the LAST encoder layer.  Only the class token of the last layer reaches the
+// head (ViT_seq.c:429-435 normalises all rows and keeps row 0), and after the last attention no token reads
+// another one, so everything behind it -- out_proj, LayerNorm, the MLP -- is needed for ONE row per image.  The
+// query is that row; keys and values are still all of the image's tokens.
+// One block per image, one warp per head:  s_j = q . k_j / 8 (lanes over keys), softmax in fp32 (exact maximum,
+// as ViT_seq.c:178-191), o = sum_j p_j v_j (lanes over the 64 output columns).  Also gathers the image's fp32
+// class row of the residual stream into the compact [batch][768] buffer the pruned layer tail works on.
+template <typename T>
+__global__ void __launch_bounds__(384) cls_attention_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ X,
+                                                           T* __restrict__ ao_c, float* __restrict__ x_c, int tokens) {
+    __shared__ float sp[12][640];           // one row of scores / probabilities per head
+    const int img = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t row0 = static_cast<size_t>(img) * tokens;
+    if (threadIdx.x < kDim / 4)
+        reinterpret_cast<float4*>(x_c + static_cast<size_t>(img) * kDim)[threadIdx.x] = reinterpret_cast<const float4*>(X + row0 * kDim)[threadIdx.x];
+    const uint16_t* qrow = qkv + row0 * 2304 + head * 64;
+    float q[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {       // the whole query in every lane (uniform loads, 8 x 16 B)
+        const uint4 v = *reinterpret_cast<const uint4*>(qrow + 8 * i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            q[8 * i + 2 * k] = to_float<T>(reinterpret_cast<const T*>(&w[k])[0]);
+            q[8 * i + 2 * k + 1] = to_float<T>(reinterpret_cast<const T*>(&w[k])[1]);
+        }
+    }
+    float* p = sp[head];
+    float mx = -INFINITY;
+    for (int j = lane; j < tokens; j += 32) {
+        const uint16_t* krow = qkv + (row0 + j) * 2304 + 768 + head * 64;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(krow + 8 * i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc = fmaf(q[8 * i + 2 * k], to_float<T>(reinterpret_cast<const T*>(&w[k])[0]), acc);
+                acc = fmaf(q[8 * i + 2 * k + 1], to_float<T>(reinterpret_cast<const T*>(&w[k])[1]), acc);
+            }
+        }
+        acc *= 0.125f;
+        p[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < tokens; j += 32) {
+        const float e = __expf(p[j] - mx);
+        p[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    // o[d] for d = 2 lane, 2 lane + 1: V rows are always bf16 (the in_proj epilogue stores them so)
+    float o0 = 0.f, o1 = 0.f;
+    const __nv_bfloat162* vcol = reinterpret_cast<const __nv_bfloat162*>(qkv + row0 * 2304 + 1536 + head * 64) + lane;
+    for (int j = 0; j < tokens; ++j) {
+        const float2 v = __bfloat1622float2(vcol[static_cast<size_t>(j) * (2304 / 2)]);
+        o0 = fmaf(p[j], v.x, o0);
+        o1 = fmaf(p[j], v.y, o1);
+    }
+    const float inv = 1.0f / sum;
+    reinterpret_cast<uint32_t*>(ao_c + static_cast<size_t>(img) * kDim + head * 64)[lane] = pack2<T>(o0 * inv, o1 * inv);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Final LayerNorm on the class rows only (the reference normalises all rows and keeps row 0,
 // ViT_seq.c:429-433), fp32 out.  One warp per image.
 __global__ void __launch_bounds__(256) head_ln_kernel(const float* __restrict__ X, const float* __restrict__ w,

@@ -67,6 +67,7 @@ _sig("vit_cuda_last_error", C.c_char_p)
 _sig("vit_cuda_launch_count", C.c_longlong)
 _sig("vit_cuda_info", C.c_int, C.POINTER(C.c_longlong), C.c_int)
 _sig("vit_cuda_set_attention_exact", C.c_int, C.c_int)
+_sig("vit_cuda_set_class_row_pruning", C.c_int, C.c_int)
 _sig("vit_cuda_timer_start", C.c_int, C.c_int)
 _sig("vit_cuda_timer_stop", C.c_int, C.c_int, _f32p)
 _sig("vit_cuda_profile_enable", C.c_int, C.c_int)
@@ -229,11 +230,15 @@ class Engine:
         return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(PROF_CATEGORIES)}
 
     def info(self) -> dict:
-        v = (C.c_longlong * 10)()
-        _check(lib.vit_cuda_info(v, 10))
+        v = (C.c_longlong * 11)()
+        _check(lib.vit_cuda_info(v, 11))
         keys = ["sm_count", "cc_major", "cc_minor", "max_batch", "tokens", "precision", "n_gpus", "workspace_mib",
-                "attention_exact", "attention_fallbacks"]
+                "attention_exact", "attention_fallbacks", "class_row_pruning"]
         return dict(zip(keys, [int(x) for x in v]))
+
+    def set_class_row_pruning(self, on: bool):
+        """Last layer: everything behind the attention for the class rows only (default on)."""
+        _check(lib.vit_cuda_set_class_row_pruning(1 if on else 0))
 
     def set_attention_exact(self, on: bool):
         """Two-pass (exact row maximum) softmax instead of the default single-pass one."""
