@@ -507,7 +507,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
 constexpr int ATTN3_THREADS = 18 * 32;
 constexpr int ATTN3_EXP_WARPS = 12, ATTN3_W_OUT = 12, ATTN3_W_PRODUCER = 16, ATTN3_W_ISSUER = 17;
 constexpr int ATTN3_OSTAGE_BYTES = 4 * 2 * 4096;                       // [output warp][2] 32 rows x 128 B
-constexpr int ATTN3_XCH_BYTES = (2 * 3 * 128 + 2 * 3 * 128) * 4;       // sum [unit parity][part][row], max likewise
+constexpr int ATTN3_XCH_BYTES = (3 * 3 * 128 + 2 * 3 * 128) * 4;       // sum [unit % 3][part][row], max [unit parity][part][row]
 __host__ inline int attn3_smem_bytes(int kpad) {
     return 2 * attn2_stage_bytes(kpad) + ATTN3_OSTAGE_BYTES + ATTN3_XCH_BYTES + 256 + 1024;
 }
@@ -521,8 +521,11 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
     const int kv_bytes = attn_kv_bytes(p.kpad);
     const int stage_bytes = attn2_stage_bytes(p.kpad);
     uint8_t* sO = smem + 2 * stage_bytes;
-    float* xsum = reinterpret_cast<float*>(sO + ATTN3_OSTAGE_BYTES);  // [unit parity][part][128]
-    float* xmax = xsum + 2 * 3 * 128;                                 // [unit parity][part][128]
+    // Row sums are TRIPLE buffered: the exponential warps may write the sums of unit u + 2 before the output warps
+    // have read those of unit u (nothing orders the two), but never those of unit u + 3 -- S(u + 3) is issued after
+    // PV(u + 1), which waits for o_free(u), which the output warps give only after reading the sums of unit u.
+    float* xsum = reinterpret_cast<float*>(sO + ATTN3_OSTAGE_BYTES);  // [unit % 3][part][128]
+    float* xmax = xsum + 3 * 3 * 128;                                 // [unit parity][part][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xsum) + ATTN3_XCH_BYTES);
     uint64_t* kv_full = bars;        // [2 stages] Q, K, V of an item landed (tx)
     uint64_t* stage_free = bars + 2; // [2 stages] every MMA reading the stage has completed
@@ -716,7 +719,7 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
         if constexpr (EXACT) {
             for (int u = 0; u < n_units; ++u) {
                 const uint32_t taddr = tmem_base + lane_bits + (u & 1) * p.kpad;
-                float* my_sum = xsum + ((u & 1) * 3 + part) * 128 + row;
+                float* my_sum = xsum + ((u % 3) * 3 + part) * 128 + row;
                 const bool quarter_active = ((nqt == 2 ? (u & 1) : 0) * 128 + quarter * 32) < p.tokens;
                 ATTN_TRACE(warp, u, 0);
                 mbar_wait(&s_full[u & 1], (u >> 1) & 1);
@@ -773,11 +776,11 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
                     }
                     const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                     ATTN_TRACE(warp, u, 6);
-                    xsum[((u & 1) * 3 + part) * 128 + row] = exp_stream(taddr, fmaf(-mx, p.scale_log2, -ATTN_FAST_SHIFT), ra, rb, [] {});
+                    xsum[((u % 3) * 3 + part) * 128 + row] = exp_stream(taddr, fmaf(-mx, p.scale_log2, -ATTN_FAST_SHIFT), ra, rb, [] {});
                     tmem_st_wait();
                     tc_fence_before();
                 } else if (((nqt == 2 ? (u & 1) : 0) * 128 + quarter * 32) < p.tokens) {
-                    xsum[((u & 1) * 3 + part) * 128 + row] = 0.f;   // a part without chunks in a live quarter
+                    xsum[((u % 3) * 3 + part) * 128 + row] = 0.f;   // a part without chunks in a live quarter
                 }
                 ATTN_TRACE(warp, u, 2);
                 __syncwarp();
@@ -804,8 +807,8 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
                     continue;
                 }
                 // all three parts' row sums were written before their p_full arrivals, which the PV MMA behind
-                // o_full waited for; read before o_free is released, so unit u + 2 cannot overwrite them earlier
-                const float* ps = xsum + (u & 1) * 3 * 128 + row;
+                // o_full waited for; read before o_free is released, so unit u + 3 cannot overwrite them earlier
+                const float* ps = xsum + (u % 3) * 3 * 128 + row;
                 const float row_sum = (ps[0] + ps[128]) + ps[256];
                 if constexpr (!EXACT) {
                     if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN

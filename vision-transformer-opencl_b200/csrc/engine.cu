@@ -426,11 +426,17 @@ int launch_fold_ln(int prec, const float* W, const float* ln_w, const float* ln_
     return check_launch("fold_ln_weights");
 }
 
+template <typename T>
+void launch_patchify_t(const float* img, T* patches, int batch, int S, cudaStream_t st) {
+    const dim3 grid((S * (S / 4) + 511) / 512, 3 * batch);
+    if (S == 224) patchify_kernel<T, 224><<<grid, 256, 0, st>>>(img, patches, batch, S);
+    else if (S == 384) patchify_kernel<T, 384><<<grid, 256, 0, st>>>(img, patches, batch, S);
+    else patchify_kernel<T, 0><<<grid, 256, 0, st>>>(img, patches, batch, S);
+}
 int launch_patchify(int prec, const float* img, void* patches, int batch, int S, int sm_count, cudaStream_t st) {
-    const size_t total4 = static_cast<size_t>(batch) * 3 * S * S / 4;
-    const int grid = static_cast<int>(std::min<size_t>((total4 + 255) / 256, static_cast<size_t>(sm_count) * 16));
-    if (prec == VIT_PREC_FP16) patchify_kernel<__half><<<grid, 256, 0, st>>>(img, static_cast<__half*>(patches), batch, S);
-    else patchify_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, static_cast<__nv_bfloat16*>(patches), batch, S);
+    (void)sm_count;
+    if (prec == VIT_PREC_FP16) launch_patchify_t(img, static_cast<__half*>(patches), batch, S, st);
+    else launch_patchify_t(img, static_cast<__nv_bfloat16*>(patches), batch, S, st);
     return check_launch("patchify");
 }
 
@@ -885,7 +891,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
     if (pruned_tail) head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);
     else head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
     VIT_TRY(check_launch("head_ln"));
-    head_gemm_kernel<<<dim3((kClasses + 7) / 8, std::min((nb + HEAD_IMGS - 1) / HEAD_IMGS, 16)), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
+    head_gemm_kernel<<<dim3((kClasses + HEAD_CLASSES - 1) / HEAD_CLASSES, std::min((nb + HEAD_IMGS - 1) / HEAD_IMGS, 32)), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
                                                                                 kClasses);
     return check_launch("head_gemm");
 }
@@ -1672,7 +1678,7 @@ int vit_cuda_op_head(const float* x, const float* ln_w, const float* ln_b, const
     VIT_TRY(s.alloc(reinterpret_cast<void**>(&dlog), (size_t)batch * kClasses * 4));
     head_ln_kernel<<<(batch + 7) / 8, 256>>>(dx, dlw, dlb, dcls, batch, tokens);
     VIT_TRY(check_launch("head_ln"));
-    head_gemm_kernel<<<dim3((kClasses + 7) / 8, std::min((batch + HEAD_IMGS - 1) / HEAD_IMGS, 16)), 256>>>(dcls, dhw, dhb, dlog, batch, kClasses);
+    head_gemm_kernel<<<dim3((kClasses + HEAD_CLASSES - 1) / HEAD_CLASSES, std::min((batch + HEAD_IMGS - 1) / HEAD_IMGS, 32)), 256>>>(dcls, dhw, dhb, dlog, batch, kClasses);
     VIT_TRY(check_launch("head_gemm"));
     VIT_TRY(op_end("op_head"));
     CU_TRY(cudaMemcpy(logits, dlog, (size_t)batch * kClasses * 4, cudaMemcpyDeviceToHost));

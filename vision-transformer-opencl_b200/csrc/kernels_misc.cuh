@@ -115,28 +115,32 @@ __global__ void __launch_bounds__(256) fold_ln_weights_kernel(const float* __res
 // K order (ic, kh, kw) = the flattened conv_proj.weight row order (Conv2d, ViT_seq.c:33-41), patch
 // index oh*G+ow (flatten_transpose, ViT_seq.c:57-65).  One thread per float4 of the image, reads
 // fully coalesced, writes 8-byte pieces.
-template <typename T>
+template <typename T, int S_CT>   // S_CT: image size known at compile time (224, 384), or 0 for any size
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, T* __restrict__ patches,
-                                                       int batch, int S) {
-    const int G = S / 16;
-    const size_t per_img4 = static_cast<size_t>(3) * S * S / 4;
-    const size_t total = per_img4 * batch;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const size_t bimg = i / per_img4;
-        size_t rem = i - bimg * per_img4;           // float4 index inside the image
-        const int x4 = static_cast<int>(rem % (S / 4));
-        rem /= (S / 4);
-        const int yy = static_cast<int>(rem % S);
-        const int c = static_cast<int>(rem / S);
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(img) + i);
-        const int x = x4 * 4;
+                                                       int batch, int S_rt) {
+    const int S = S_CT ? S_CT : S_rt;
+    const int G = S / 16, S4 = S / 4;
+    // blockIdx.y = image * 3 + channel; two float4 per thread (two loads in flight), no 64-bit divisions
+    const int plane = blockIdx.y;
+    const int bimg = plane / 3, c = plane - bimg * 3;
+    const float4* src = reinterpret_cast<const float4*>(img) + static_cast<size_t>(plane) * S * S4;
+    T* dst_img = patches + static_cast<size_t>(bimg) * G * G * kDim + c * 256;
+    const int n4 = S * S4;
+    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 2;
+    float4 v[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (i0 + k < n4) v[k] = __ldcs(src + i0 + k);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = i0 + k;
+        if (i >= n4) break;
+        const int yy = i / S4, x = (i - yy * S4) * 4;
         const int ph = yy >> 4, kh = yy & 15, pw = x >> 4, kw = x & 15;
-        const size_t prow = bimg * (G * G) + ph * G + pw;
         uint2 o;
-        o.x = pack2<T>(v.x, v.y);
-        o.y = pack2<T>(v.z, v.w);
-        *reinterpret_cast<uint2*>(patches + prow * kDim + c * 256 + kh * 16 + kw) = o;
+        o.x = pack2<T>(v[k].x, v[k].y);
+        o.y = pack2<T>(v[k].z, v[k].w);
+        *reinterpret_cast<uint2*>(dst_img + static_cast<size_t>(ph * G + pw) * kDim + kh * 16 + kw) = o;
     }
 }
 
@@ -287,20 +291,23 @@ __global__ void __launch_bounds__(256) head_ln_kernel(const float* __restrict__ 
 // operand rounding.  One warp per class keeps its W row in registers (24 values per lane) and walks the images,
 // which a block of 8 warps stages through shared memory 8 at a time.  Per output the summation order is fixed
 // (lane-strided partial sums in ascending k, then a butterfly), so a logit does not depend on the batch size or
-// the image's position in it; and a batch of ONE image still spreads over 125 blocks (the previous 64x64-tiled
+// the image's position in it; and a batch of ONE image still spreads over 63 blocks (the previous 64x64-tiled
 // kernel ran 16 blocks for 134 us at batch 1).
 constexpr int HEAD_IMGS = 16;   // 48 KB of shared memory per block
+constexpr int HEAD_CLASSES = 16;   // per block: two per warp, so that every staged image row is read once per two classes
 __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict__ xn, const float* __restrict__ W,
                                                         const float* __restrict__ bias, float* __restrict__ logits,
                                                         int batch, int classes) {
     __shared__ float4 sx[HEAD_IMGS][kDim / 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * 8 + warp;
-    float4 w[6];
+    const int c0 = blockIdx.x * HEAD_CLASSES + 2 * warp, c1 = c0 + 1;
+    float4 w0[6], w1[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-        w[i] = c < classes ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * kDim) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float bc = c < classes ? bias[c] : 0.f;
+    for (int i = 0; i < 6; ++i) {
+        w0[i] = c0 < classes ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(c0) * kDim) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        w1[i] = c1 < classes ? __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(c1) * kDim) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float b0v = c0 < classes ? bias[c0] : 0.f, b1v = c1 < classes ? bias[c1] : 0.f;
     for (int b0 = blockIdx.y * HEAD_IMGS; b0 < batch; b0 += gridDim.y * HEAD_IMGS) {
         const int nb = min(HEAD_IMGS, batch - b0);
         __syncthreads();
@@ -308,17 +315,21 @@ __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict_
             sx[i / (kDim / 4)][i % (kDim / 4)] = reinterpret_cast<const float4*>(xn + static_cast<size_t>(b0) * kDim)[i];
         __syncthreads();
         for (int j = 0; j < nb; ++j) {
-            float acc = 0.f;
+            float a0 = 0.f, a1 = 0.f;   // per output: lane-strided partial sums in ascending k, then a butterfly
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 const float4 x = sx[j][lane + 32 * i];
-                acc = fmaf(x.x, w[i].x, acc);
-                acc = fmaf(x.y, w[i].y, acc);
-                acc = fmaf(x.z, w[i].z, acc);
-                acc = fmaf(x.w, w[i].w, acc);
+                a0 = fmaf(x.x, w0[i].x, a0); a1 = fmaf(x.x, w1[i].x, a1);
+                a0 = fmaf(x.y, w0[i].y, a0); a1 = fmaf(x.y, w1[i].y, a1);
+                a0 = fmaf(x.z, w0[i].z, a0); a1 = fmaf(x.z, w1[i].z, a1);
+                a0 = fmaf(x.w, w0[i].w, a0); a1 = fmaf(x.w, w1[i].w, a1);
             }
-            acc = warp_sum(acc);
-            if (lane == 0 && c < classes) logits[static_cast<size_t>(b0 + j) * classes + c] = acc + bc;
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+            if (lane == 0) {
+                if (c0 < classes) logits[static_cast<size_t>(b0 + j) * classes + c0] = a0 + b0v;
+                if (c1 < classes) logits[static_cast<size_t>(b0 + j) * classes + c1] = a1 + b1v;
+            }
         }
     }
 }
