@@ -171,9 +171,12 @@ def cpu_baseline(seconds_hint=20):
 def run_ours(args):
     import vit_b200 as V
     rank, local_rank, world = dist_env()
+    # The contract is ONE JSON line on stdout.  NCCL prints its version banner there (NCCL_DEBUG=VERSION in this image),
+    # other libraries may too: everything but the final line is routed to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout; the contract is ONE JSON line there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -345,7 +348,8 @@ def run_ours(args):
             out["batch1_latency"] = lat
         if n_gpus == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
     V.dev_free(0, d_imgs)
     V.dev_free(0, d_logits)
