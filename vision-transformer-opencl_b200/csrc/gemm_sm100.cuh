@@ -5,13 +5,15 @@
 // token-flattened batch: M = images * tokens.  W is the PyTorch [out,in] layout, i.e. already
 // the K-major "B^T" operand.
 //
-// Structure (one persistent CTA per SM, warp specialised):
-//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 (128B swizzle) per stage
-//   warp 1      one thread issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16, fp32 accumulate
-//               in TMEM); tcgen05.commit releases smem stages and publishes accumulators
-//   warp 2      TMEM allocator (2 accumulator stages x BN columns = 512 columns)
-//   warps 4..   epilogue: tcgen05.ld -> registers -> bias / GELU / residual -> global,
-//               overlapped with the next tile's main loop through the second TMEM stage
+// Three kernels live here.  The engine runs everything on the LAST one:
+//   gemm_sm100_kernel         single-CTA 128 x 256 tiles, epilogue straight to global memory   (VIT_GEMM_IMPL=1, A/B reference)
+//   gemm_sm100_pair_kernel    CTA pair (cta_group::2) 256 x 256 tiles, same epilogue            (ditto)
+//   gemm_sm100_staged_kernel  CTA pair, staged TMA-store epilogue, fused bias / exact-erf GELU / fp32 residual, LayerNorm
+//                             folded in (producer + consumer forms), per-image EMBED addressing for conv_proj
+// Common structure (one persistent CTA per SM, warp specialised): a TMA producer (A tile 128x64 and W tile per
+// stage, 128B swizzle), ONE thread issuing tcgen05.mma (kind::f16, fp32 accumulators in TMEM, two accumulator
+// stages), tcgen05.commit releasing shared-memory stages and publishing accumulators, and epilogue warps reading
+// the accumulators with tcgen05.ld while the next tile's main loop runs in the other TMEM stage.
 #pragma once
 
 #include "ptx.cuh"

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 // LayerNorm folded into the GEMMs (gemm_sm100_staged_kernel, LN = true): the two helpers around it.
 //
-// rowstats_cast: for the rows entering layer 0 (written by the patch-embedding epilogue) -- the
+// rowstats_cast (operator tests; the forward gets the same from the conv_proj epilogue and the class-row kernel) -- the
 // operand-precision copy of the raw fp32 row plus its (sum, sum of squares), i.e. what the residual
 // GEMMs emit for every later LayerNorm.  One warp per row, 128-bit loads.
 template <typename T>
