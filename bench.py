@@ -140,7 +140,10 @@ def run_reference(args):
     }), flush=True)
 
 
-def cpu_baseline(seconds_hint=20):
+def cpu_baseline(gpu_logits=None):
+    """The reference's ViT_seq on the host cores (one image per thread), timed; and -- BASELINE.md section 4 -- the GPU's
+    answers for the same images checked against it in the same run (top-1, reference comparator rule on the top-1
+    probability, comparator.c:64-74)."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle_py as O
     import vit_b200 as V
@@ -151,20 +154,33 @@ def cpu_baseline(seconds_hint=20):
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
     os.dup2(devnull, 1)
+    probs = np.zeros((cores, 1000), dtype=np.float32)
     t0 = time.perf_counter()
     try:
         if kind == "reference":
-            ths = [threading.Thread(target=O.ref_vit_seq, args=(w, imgs[i:i + 1])) for i in range(cores)]
+            def one(i):
+                probs[i] = O.ref_vit_seq(w, imgs[i:i + 1])[0]
+            ths = [threading.Thread(target=one, args=(i,)) for i in range(cores)]
             [t.start() for t in ths]
             [t.join() for t in ths]
         else:
-            O.forward(w, imgs, 224, n_threads=cores)
+            probs = O.softmax(O.forward(w, imgs, 224, n_threads=cores))
     finally:
         os.dup2(saved, 1)
     dt = time.perf_counter() - t0
-    return {"value": cores / dt, "unit": "images/s", "cores": cores, "kind": kind,
-            "sample": f"{cores} images of the same synthetic batch (seed 7), one image per host thread through "
-                      f"{'the reference ViT_seq() compiled from its own source (oracle/_ref)' if kind == 'reference' else 'the oracle port'}, {dt:.1f} s"}
+    out = {"value": cores / dt, "unit": "images/s", "cores": cores, "kind": kind,
+           "sample": f"{cores} images of the same synthetic batch (seed 7), one image per host thread through "
+                     f"{'the reference ViT_seq() compiled from its own source (oracle/_ref)' if kind == 'reference' else 'the oracle port'}, {dt:.1f} s"}
+    if gpu_logits is not None and len(gpu_logits) >= cores:
+        g = O.softmax(np.ascontiguousarray(gpu_logits[:cores]))
+        top_c, top_g = probs.argmax(1), g.argmax(1)
+        srt = np.sort(probs, 1)
+        decisive = srt[:, -1] - srt[:, -2] > 0.06 * srt[:, -1]          # beyond what the stated logit tolerance can flip
+        out["gpu_vs_cpu"] = {"images": int(cores), "top1_equal": int((top_c == top_g).sum()), "decisive_images": int(decisive.sum()),
+                             "top1_equal_on_decisive": bool((top_c[decisive] == top_g[decisive]).all()),
+                             "max_abs_dprob_top1": float(np.abs(g[np.arange(cores), top_c] - probs[np.arange(cores), top_c]).max()),
+                             "comparator_rule_0.01": bool((np.abs(g[np.arange(cores), top_c] - probs[np.arange(cores), top_c]) <= 0.01).all())}
+    return out
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -250,6 +266,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_gpus * B * args.steps / e2e_s
     top1 = h_logits.argmax(1)
+    logits_first = h_logits[:64].copy()   # rank 0: images 0.. of the seeded stream, checked against the CPU reference below
 
     # ---- the engine's default configuration: last layer pruned to the class rows (same logits)
     eng.set_class_row_pruning(True)
@@ -347,7 +364,7 @@ def run_ours(args):
         if lat:
             out["batch1_latency"] = lat
         if n_gpus == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline()
+            out["cpu_baseline"] = cpu_baseline(logits_first if S == 224 else None)
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
