@@ -1166,8 +1166,9 @@ namespace vit {
 // shared memory for all of its query tiles.
 //
 //   issue order:  S(g+1) | PV(g)  per key block g of the unit stream (S(g+1) overwrites the buffer whose P
-//   was consumed by PV(g-1), already issued); at a head boundary K/V are single buffered, so the next head's
-//   first S waits for this head's last PV.
+//   was consumed by PV(g-1), already issued).  K and V are single buffered but released separately: K once the
+//   head's last S has completed (its reload for the next head runs under the head's last exponentials and PVs),
+//   V once its last PV has (its reload runs under the next head's first block of exponentials).
 //
 // Rows whose scores leave the exponent window raise g_attn_range_flag exactly as in the single-block kernel;
 // the host then repeats the call with attention_sm100_blocked_kernel (exact).
@@ -1208,15 +1209,17 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
     uint8_t* sO = sQ + 2 * ATTN_Q_TILE_BYTES;        // [output warp] staging
     float* xsum = reinterpret_cast<float*>(sO + ATTN4_OSTAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xsum) + ATTN4_XCH_BYTES);
-    uint64_t* kv_full = bars;        // K, V of a head landed (tx)
-    uint64_t* kv_free = bars + 1;    // every MMA reading them has completed
+    uint64_t* k_full = bars;         // K of a head landed (tx)
+    uint64_t* k_free = bars + 1;     // every S MMA of the head has completed
     uint64_t* q_full = bars + 2;     // [2] Q tile landed (tx)
     uint64_t* q_free = bars + 4;     // [2] every S MMA of the unit has completed
     uint64_t* s_full = bars + 6;     // [2] S block in TMEM
     uint64_t* p_full = bars + 8;     // [2] P written back (one arrival per exponential warp)
     uint64_t* o_full = bars + 10;    // O of a unit complete
     uint64_t* o_free = bars + 11;    // O drained (one arrival per output warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* v_full = bars + 12;    // V of a head landed (tx)
+    uint64_t* v_free = bars + 13;    // every PV MMA of the head has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -1233,8 +1236,10 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
     if (warp == ATTN3_W_PRODUCER && lane == 0) {
         tma_prefetch_desc(&tmap_qkv);
         tma_prefetch_desc(&tmap_out32);
-        mbar_init(kv_full, 1);
-        mbar_init(kv_free, 1);
+        mbar_init(k_full, 1);
+        mbar_init(k_free, 1);
+        mbar_init(v_full, 1);
+        mbar_init(v_free, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&q_free[i], 1);
@@ -1260,19 +1265,26 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int img = item / 12, head = item - img * 12;
                 const int row0 = img * p.tokens;
-                mbar_wait(kv_free, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(kv_full, 2 * kv_bytes);
-                for (int j = 0; j < kv_boxes; ++j)
-                    tma_load_2d(sK + j * 64 * 128, &tmap_qkv, kv_full, ATTN_DIM + head * ATTN_DH, row0 + j * 64);
-                for (int j = 0; j < kv_boxes; ++j)
-                    tma_load_2d(sV + j * 64 * 128, &tmap_qkv, kv_full, 2 * ATTN_DIM + head * ATTN_DH, row0 + j * 64);
-                for (int t = 0; t < nq; ++t, ++uq) {
+                auto load_q = [&](int t) {
                     const int b = uq & 1;
                     mbar_wait(&q_free[b], ((uq >> 1) & 1) ^ 1);
                     mbar_arrive_expect_tx(&q_full[b], ATTN_Q_TILE_BYTES);
                     tma_load_2d(sQ + b * ATTN_Q_TILE_BYTES, &tmap_qkv, &q_full[b], head * ATTN_DH, row0 + t * 128);
                     tma_load_2d(sQ + b * ATTN_Q_TILE_BYTES + 64 * 128, &tmap_qkv, &q_full[b], head * ATTN_DH, row0 + t * 128 + 64);
-                }
+                    ++uq;
+                };
+                // K first (free since the previous head's last S), then the first Q tile, so that the head's first S can be
+                // issued without waiting for V, whose buffer the previous head's last PVs are still reading
+                mbar_wait(k_free, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full, kv_bytes);
+                for (int j = 0; j < kv_boxes; ++j)
+                    tma_load_2d(sK + j * 64 * 128, &tmap_qkv, k_full, ATTN_DIM + head * ATTN_DH, row0 + j * 64);
+                load_q(0);
+                mbar_wait(v_free, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, kv_bytes);
+                for (int j = 0; j < kv_boxes; ++j)
+                    tma_load_2d(sV + j * 64 * 128, &tmap_qkv, v_full, 2 * ATTN_DIM + head * ATTN_DH, row0 + j * 64);
+                for (int t = 1; t < nq; ++t) load_q(t);
                 const int next = item + static_cast<int>(gridDim.x);  // pull the next head's K, V towards L2
                 if (next < n_items) {
                     const int img2 = next / 12, head2 = next - img2 * 12;
@@ -1291,7 +1303,7 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
         auto issue_s = [&](int g) {   // S block g of the stream: unit g / nkb, key block g % nkb, buffer g & 1
             const int u = g / nkb, j = g - u * nkb;
             if (j == 0) {
-                if (u % nq == 0) mbar_wait(kv_full, (u / nq) & 1);
+                if (u % nq == 0) mbar_wait(k_full, (u / nq) & 1);
                 mbar_wait(&q_full[u & 1], (u >> 1) & 1);
                 tc_fence_after();
             }
@@ -1302,17 +1314,23 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
                 for (int k = 0; k < ATTN_DH / 16; ++k)
                     umma_f16(tmem_base + (g & 1) * kb, desc_kmajor_sw128(q_addr, k), desc_kmajor_sw128(k_addr + j * kb * 128, k), idesc_s, k != 0);
                 umma_commit(&s_full[g & 1]);
-                if (j == nkb - 1) umma_commit(&q_free[u & 1]);   // the unit's last S: its Q tile may be replaced
+                if (j == nkb - 1) {
+                    umma_commit(&q_free[u & 1]);                 // the unit's last S: its Q tile may be replaced
+                    if (u % nq == nq - 1) umma_commit(k_free);   // ... and the head's last: so may K
+                }
             }
             __syncwarp();
         };
         if (n_blocks > 0) issue_s(0);
         for (int g = 0; g < n_blocks; ++g) {
             const int u = g / nkb, j = g - u * nkb;
-            const bool head_ends = j == nkb - 1 && (u % nq) == nq - 1;   // K, V are single buffered: no look-ahead across heads
-            if (g + 1 < n_blocks && !head_ends) issue_s(g + 1);
+            const bool head_ends = j == nkb - 1 && (u % nq) == nq - 1;
+            if (g + 1 < n_blocks) issue_s(g + 1);
             mbar_wait(&p_full[g & 1], (g >> 1) & 1);
-            if (j == 0 && u > 0) mbar_wait(o_free, (u - 1) & 1);
+            if (j == 0) {
+                if (u > 0) mbar_wait(o_free, (u - 1) & 1);
+                if (u % nq == 0) mbar_wait(v_full, (u / nq) & 1);
+            }
             tc_fence_after();
             if (elect_one()) {
                 const int nch = (j == nkb - 1 ? last_cols : kb) / 16;
@@ -1325,11 +1343,10 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
                 }
                 if (j == nkb - 1) {
                     umma_commit(o_full);
-                    if (head_ends) umma_commit(kv_free);
+                    if (head_ends) umma_commit(v_free);
                 }
             }
             __syncwarp();
-            if (g + 1 < n_blocks && head_ends) issue_s(g + 1);
         }
     } else if (warp < ATTN3_EXP_WARPS) {
         // ------------------------------------------------------------ exponential warps
