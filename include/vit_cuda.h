@@ -91,6 +91,10 @@ int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi);
  * the previous one, up to max_batch.  Pure host arithmetic.  Returns the number of passes (<= cap)
  * or a negative status. */
 int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, int cap);
+/* staged != 0: the schedule for input that has to be gathered into pinned staging first (pageable memory,
+ * vit_cuda_forward_scattered): 64 images, then passes of 128 -- the host-side gather runs at about the rate
+ * the GPU consumes images, so equal passes keep every gather hidden under the previous pass's kernels. */
+int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* first, int* count, int cap);
 
 /* Device-resident variant for one GPU slot (0 <= gpu_slot < n_gpus): d_images and d_logits
  * are device pointers on that GPU, n <= max_batch_per_gpu.  Work is enqueued on the

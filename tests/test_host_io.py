@@ -121,6 +121,10 @@ def test_pass_schedule_covers_the_shard_with_a_small_first_pass(vit):
             else:
                 assert c <= 3 * sched[i - 1][1]
             pos += c
+    for n, mb in [(1, 1), (63, 1024), (1024, 1024), (1000, 100), (5000, 999)]:     # staged input: 64, then passes of <= 128
+        sched = vit.pass_schedule(n, mb, staged=True)
+        assert sum(c for _, c in sched) == n and all(0 < c <= min(mb, 128) for _, c in sched) and sched[0][1] <= 64
+        assert [f for f, _ in sched] == list(np.cumsum([0] + [c for _, c in sched[:-1]]))
     assert vit.pass_schedule(0, 8) == []
     assert vit.pass_schedule(1024, 1024) == [(0, 32), (32, 96), (128, 288), (416, 608)]
     with pytest.raises(vit.VitCudaError):

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -1079,11 +1080,13 @@ int vit_cuda_forward_device(int gpu_slot, const float* d_images, int n, float* d
     return vit_cuda_sync(gpu_slot);
 }
 
-int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, int cap) {
+int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* first, int* count, int cap) {
     if (n_images < 0 || max_batch <= 0 || !first || !count || cap <= 0) return set_err(VIT_E_ARG, "bad schedule arguments");
     int n = 0;
-    for (int done = 0, sz = 32; done < n_images; sz = std::min(max_batch, 3 * sz)) {
-        // more passes than `cap` (a tiny max_batch): the last entry takes max_batch-sized steps
+    // pinned input: the copy of a pass is ~3.4x faster than its kernels -> passes may triple.  Staged input (pageable or
+    // one allocation per image): the host-side gather runs at about the rate the GPU consumes images, so the passes
+    // after the first stay at 128 images -- each gather hides under the kernels of the pass before it.
+    for (int done = 0, sz = staged ? 64 : 32; done < n_images; sz = staged ? std::min(max_batch, 128) : std::min(max_batch, 3 * sz)) {
         const int nb = std::min(std::min(sz, max_batch), n_images - done);
         if (n == cap) return set_err(VIT_E_ARG, "pass schedule of %d images with max_batch %d needs more than %d passes", n_images, max_batch, cap);
         first[n] = done;
@@ -1092,6 +1095,10 @@ int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, 
         ++n;
     }
     return n;
+}
+
+int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, int cap) {
+    return vit_cuda_pass_schedule_ex(n_images, max_batch, 0, first, count, cap);
 }
 
 int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi) {
@@ -1171,8 +1178,8 @@ static int forward_host_once(const float* images_nchw, const float* const* image
     cudaGetLastError();
     const bool images_pinned = images_nchw && cudaPointerGetAttributes(&pa, images_nchw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    std::vector<int> pass_first(64), pass_count(64);
-    const int n_sched = vit_cuda_pass_schedule(per_gpu, e.max_batch, pass_first.data(), pass_count.data(), 64);
+    std::vector<int> pass_first(256), pass_count(256);
+    const int n_sched = vit_cuda_pass_schedule_ex(per_gpu, e.max_batch, (image_ptrs || !images_pinned) ? 1 : 0, pass_first.data(), pass_count.data(), 256);
     if (n_sched < 0) return n_sched;
     pass_first.resize(n_sched);
     pass_count.resize(n_sched);
@@ -1200,11 +1207,22 @@ static int forward_host_once(const float* images_nchw, const float* const* image
                 } else {
                     CU_TRY(cudaEventSynchronize(c.ev_stage[buf]));   // its previous copy has left the buffer
                 }
-                if (image_ptrs) {
-                    for (int i = 0; i < nb; ++i)
-                        memcpy(c.h_stage[buf] + static_cast<size_t>(i) * img_elems, image_ptrs[first + i], img_elems * sizeof(float));
-                } else {   // contiguous but pageable: a direct copy would be staged by the driver synchronously
-                    memcpy(c.h_stage[buf], images_nchw + static_cast<size_t>(first) * img_elems, static_cast<size_t>(nb) * img_elems * sizeof(float));
+                // One host thread copies ~10 GB/s: 1024 images (617 MB) would take longer than the GPU needs for them.
+                // Up to eight threads (half the host cores) share a pass.
+                float* dst = c.h_stage[buf];
+                auto gather = [=](int i0, int i1) {
+                    for (int i = i0; i < i1; ++i)
+                        memcpy(dst + static_cast<size_t>(i) * img_elems,
+                               image_ptrs ? image_ptrs[first + i] : images_nchw + static_cast<size_t>(first + i) * img_elems, img_elems * sizeof(float));
+                };
+                const int n_thr = std::min(std::max(1, static_cast<int>(std::thread::hardware_concurrency()) / 2), std::min(8, (nb + 15) / 16));
+                if (n_thr <= 1) {
+                    gather(0, nb);
+                } else {
+                    std::vector<std::thread> pool;
+                    for (int t = 1; t < n_thr; ++t) pool.emplace_back(gather, nb * t / n_thr, nb * (t + 1) / n_thr);
+                    gather(0, nb / n_thr);
+                    for (auto& th : pool) th.join();
                 }
                 src = c.h_stage[buf];
             } else {

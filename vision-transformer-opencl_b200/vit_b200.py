@@ -58,6 +58,7 @@ _sig("vit_cuda_forward", C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 _sig("vit_cuda_shard_range", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p)
 _sig("vit_cuda_forward_scattered", C.c_int, C.POINTER(_f32p), C.c_int, C.c_void_p, C.c_void_p)
 _sig("vit_cuda_pass_schedule", C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
+_sig("vit_cuda_pass_schedule_ex", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_forward_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_enqueue_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_sync", C.c_int, C.c_int)
@@ -262,9 +263,9 @@ def shard_range(n: int, n_gpus: int, g: int) -> tuple[int, int]:
     return lo.value, hi.value
 
 
-def pass_schedule(n_images: int, max_batch: int) -> list[tuple[int, int]]:
+def pass_schedule(n_images: int, max_batch: int, staged: bool = False) -> list[tuple[int, int]]:
     first, count = (C.c_int * 64)(), (C.c_int * 64)()
-    n = lib.vit_cuda_pass_schedule(n_images, max_batch, first, count, 64)
+    n = lib.vit_cuda_pass_schedule_ex(n_images, max_batch, 1 if staged else 0, first, count, 64)
     if n < 0:
         _check(n)
     return [(first[i], count[i]) for i in range(n)]
