@@ -105,6 +105,11 @@ def test_forward_odd_image_sizes(vit, oracle, img_size, n):
 
 
 def test_empty_and_oversized_requests(vit, weights224):
+    with vit.Engine(weights224, 224, max_batch=1) as eng:      # 70 passes of one image: any number of passes must work
+        imgs = vit.synth_images(70, 224, 7)
+        many = eng.forward(imgs)
+    with vit.Engine(weights224, 224, max_batch=64) as eng:
+        assert np.array_equal(many, eng.forward(imgs))
     with vit.Engine(weights224, 224, max_batch=2) as eng:
         out = eng.forward(np.empty((0, 3, 224, 224), dtype=np.float32))
         assert out.shape == (0, 1000)

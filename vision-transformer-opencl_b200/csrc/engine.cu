@@ -1178,8 +1178,10 @@ static int forward_host_once(const float* images_nchw, const float* const* image
     cudaGetLastError();
     const bool images_pinned = images_nchw && cudaPointerGetAttributes(&pa, images_nchw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    std::vector<int> pass_first(256), pass_count(256);
-    const int n_sched = vit_cuda_pass_schedule_ex(per_gpu, e.max_batch, (image_ptrs || !images_pinned) ? 1 : 0, pass_first.data(), pass_count.data(), 256);
+    // any number of passes (a tiny max_batch with a large n): size the schedule arrays for the worst case
+    const int worst = per_gpu / std::min(e.max_batch, 32) + 8;
+    std::vector<int> pass_first(worst), pass_count(worst);
+    const int n_sched = vit_cuda_pass_schedule_ex(per_gpu, e.max_batch, (image_ptrs || !images_pinned) ? 1 : 0, pass_first.data(), pass_count.data(), worst);
     if (n_sched < 0) return n_sched;
     pass_first.resize(n_sched);
     pass_count.resize(n_sched);
