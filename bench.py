@@ -28,7 +28,7 @@ FLOP_PER_IMAGE_224 = 35_127_656_448  # matmul-only, 2 FLOP/MAC, un-padded 197 to
 FLOP_PER_IMAGE = {224: FLOP_PER_IMAGE_224, 384: 110_968_700_928}  # 384: BASELINE.json configs[4] (577 tokens)
 # per-launch algorithmic FLOPs of one GEMM over `rows` token rows
 # DRAM bytes of one launch at B = 1024 from the ncu --set full capture committed under profiles/ (r1_ncu_layer_final.txt)
-NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_199_038_000, "out_gemm": 1_812_138_000, "fc1_gemm": 1_527_691_000, "fc2_gemm": 2_864_615_000}
+NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_197_838_000, "out_gemm": 1_812_946_000, "fc1_gemm": 1_507_901_000, "fc2_gemm": 2_845_759_000}
 GEMM_FLOP_PER_ROW = {"qkv_gemm": 2 * 768 * 2304, "out_gemm": 2 * 768 * 768, "fc1_gemm": 2 * 768 * 3072, "fc2_gemm": 2 * 3072 * 768}
 
 
