@@ -195,6 +195,44 @@ def test_class_row_pruning_of_the_last_layer_keeps_the_logits(vit, oracle, weigh
     assert np.all(np.abs(got - r) <= ATOL + RTOL * np.abs(r)), _report(got, r)
 
 
+def test_forward_with_trained_like_layernorm_parameters(vit, oracle, weights224):
+    """The LayerNorm tensors the reference ships (Network/Weight_*_ln_*.bin; the large GEMM weights are missing from the
+    mount) look nothing like random init: gains with mean 0.03 (layer 0 ln_1) ... 0.57 (layer 10 ln_2) and a
+    spread as large as the mean, some NEGATIVE, biases up to +-0.3, final gain 0.69.  Those scales go straight into the
+    folded weights W' = ln_w (.) W and the bias vector c = b + W ln_b of the LayerNorm-folded GEMMs, so the whole model is
+    checked against the oracle with LayerNorm parameters drawn from the measured per-layer statistics."""
+    rng = np.random.default_rng(2024)
+    w = [a.copy() for a in weights224]
+    ln1_mean = [0.03, 0.08, 0.13, 0.16, 0.19, 0.20, 0.23, 0.23, 0.25, 0.22, 0.23, 0.26]
+    ln1_std = [0.07, 0.09, 0.13, 0.15, 0.18, 0.17, 0.17, 0.15, 0.12, 0.10, 0.09, 0.10]
+    ln2_mean = [0.14, 0.19, 0.21, 0.30, 0.35, 0.38, 0.42, 0.48, 0.53, 0.57, 0.58, 0.55]
+    ln2_std = [0.19, 0.20, 0.21, 0.25, 0.26, 0.26, 0.23, 0.23, 0.19, 0.13, 0.10, 0.06]
+    for l in range(12):
+        b = 4 + 12 * l
+        w[b + 0] = (ln1_mean[l] + ln1_std[l] * rng.standard_normal(768)).astype(np.float32)
+        w[b + 1] = (0.035 * rng.standard_normal(768)).astype(np.float32)
+        w[b + 6] = (ln2_mean[l] + ln2_std[l] * rng.standard_normal(768)).astype(np.float32)
+        w[b + 7] = (0.09 * rng.standard_normal(768)).astype(np.float32)
+    w[148] = (0.69 + 0.125 * rng.standard_normal(768)).astype(np.float32)
+    w[149] = (0.032 * rng.standard_normal(768)).astype(np.float32)
+    w = [np.ascontiguousarray(np.round(a.astype(np.float64) * 1e6) / 1e6, dtype=np.float32) for a in w]   # the loader's rounding
+    imgs = vit.synth_images(8, 224, 11)
+    ref = oracle.forward(w, imgs, 224)
+    for prec, name in ((vit.PREC_FP16, "fp16"), (vit.PREC_BF16, "bf16")):
+        with vit.Engine(w, 224, max_batch=8, precision=prec) as eng:
+            got, top1 = eng.forward(imgs, want_top1=True)
+            eng.set_class_row_pruning(False)
+            full = eng.forward(imgs)
+        print(name, "trained-like LN", _report(got, ref), "| logit std", ref.std())
+        err = np.abs(got - ref)
+        _assert_top1(top1, ref, name + " trained-like LN")
+        if prec == vit.PREC_FP16:
+            assert np.all(err <= ATOL + RTOL * np.abs(ref)), _report(got, ref)
+            assert np.all(np.abs(full - ref) <= ATOL + RTOL * np.abs(ref))
+        else:
+            assert (err <= ATOL + RTOL * np.abs(ref)).mean() >= 0.995 and np.all(err <= 2 * ATOL + RTOL * np.abs(ref)), _report(got, ref)
+
+
 def test_batch_position_independence(vit, weights224, ref16):
     """An image's logits must not depend on its position in the batch or on the pass size
     (needed for bit-identical results across GPU counts)."""
