@@ -2,7 +2,7 @@
 """bench.py -- ViT-B/16 224x224 images/sec on B200 (BASELINE.json metric), device-resident and
 end-to-end through the C ABI, with the dominant kernel's roofline and the CPU reference beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16|fp16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision auto|fp16|bf16]
     python bench.py --impl reference ...      # the reference's own ViT_seq on the host cores
 
 A "step" is one forward pass of the hot path over one batch of B synthetic images per GPU
@@ -24,6 +24,7 @@ sys.path.insert(0, str(ROOT / "vision-transformer-opencl_b200"))
 
 import numpy as np
 
+PARITY_IMAGES = 64     # images of the timed batch checked against the oracle in the same run (bench line key "parity")
 FLOP_PER_IMAGE_224 = 35_127_656_448  # matmul-only, 2 FLOP/MAC, un-padded 197 tokens
 FLOP_PER_IMAGE = {224: FLOP_PER_IMAGE_224, 384: 110_968_700_928}  # 384: BASELINE.json configs[4] (577 tokens)
 # per-launch algorithmic FLOPs of one GEMM over `rows` token rows
@@ -99,14 +100,14 @@ def run_reference(args):
         return
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle_py as O
-    import vit_b200 as V
+    import vit_hostio as H      # host-only library: this arm never maps the product's libvit_b200.so
     cores = os.cpu_count() or 1
     if args.cpu_threads:
         cores = args.cpu_threads
-    w = V.synth_weights(224, 42)
+    w = H.synth_weights(224, 42)
     kind = "reference" if O.ref_available() else "port"
     n = cores  # images per step, one per thread
-    imgs = V.synth_images(n, 224, 7)
+    imgs = H.synth_images(n, 224, 7)
 
     def step():
         if kind == "reference":
@@ -183,6 +184,155 @@ def cpu_baseline(gpu_logits=None):
     return out
 
 
+def parity_block(gpu_logits, n_images, weights, images, dtype_name):
+    """Same-run parity of the benchmarked precision: the first n_images of the timed batch through the oracle port
+    (bit-identical to the reference's ViT_seq, tests/test_oracle_vs_reference.py) on all host cores, against the logits
+    the timed engine produced for them -- the stated tolerance 2e-2 + 1e-2 |ref| on every logit, top-1 on every image."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_py as O
+    t0 = time.perf_counter()
+    ref = O.forward(weights, np.ascontiguousarray(images[:n_images]), 224, n_threads=os.cpu_count() or 1)
+    dt = time.perf_counter() - t0
+    got = np.ascontiguousarray(gpu_logits[:n_images])
+    err = np.abs(got - ref)
+    tol = 2e-2 + 1e-2 * np.abs(ref)
+    srt = np.sort(ref, 1)
+    margin = srt[:, -1] - srt[:, -2]
+    top_ref, top_gpu = ref.argmax(1), got.argmax(1)
+    return {"images": int(n_images), "dtype": dtype_name, "tolerance": "|dlogit| <= 2e-2 + 1e-2*|ref| on every logit; top-1 identical",
+            "max_abs_dlogit": float(err.max()), "mean_abs_dlogit": float(err.mean()), "logits_outside_tolerance": int((err > tol).sum()),
+            "logits_checked": int(err.size), "top1_equal": int((top_ref == top_gpu).sum()), "top1_all_equal": bool((top_ref == top_gpu).all()),
+            "oracle_min_top2_margin": float(margin.min()), "logit_std": float(ref.std()), "passes": bool((err <= tol).all() and (top_ref == top_gpu).all()),
+            "oracle": "oracle/vit_oracle.c (C restatement of ViT_seq.c, OpenMP over images)", "oracle_seconds": dt}
+
+
+def abi_inproc(V, weights, S, B, G, steps, prec, per_process_e2e):
+    """vit_cuda_init(n_gpus = G) in ONE process: G x B pinned images through vit_cuda_forward (the ABI shards them
+    contiguously, one feeding host thread per GPU), then the same images as G x B separate allocations through
+    vit_cuda_forward_scattered (the form ViT_cuda() receives: every pass is gathered into pinned staging by host
+    threads, so this leg is bound by host memory bandwidth), wall clock, host buffers in and out."""
+    n = G * B
+    res = {"n_gpus": G, "images_per_call": n}
+    with V.Engine(weights, S, max_batch=B, n_gpus=G, device_ids=list(range(G)), precision=prec) as eng:
+        eng.set_class_row_pruning(False)
+        h_imgs, ip = V.pinned_empty((n, 3, S, S))
+        h_log, lp = V.pinned_empty((n, 1000))
+        for g in range(G):
+            V.synth_images(B, S, 7, first_index=g * B, out=h_imgs[g * B:(g + 1) * B])
+        for _ in range(2):
+            eng.forward_raw(ip, n, lp)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.forward_raw(ip, n, lp)
+        dt = time.perf_counter() - t0
+        res["pinned"] = {"value": n * steps / dt, "unit": "images/s", "ms_per_call": dt / steps * 1e3,
+                         "vs_one_process_per_gpu_e2e": n * steps / dt / per_process_e2e}
+        checksum = int(h_log.argmax(1).sum())
+        eng.set_option(V.OPT_HOST_THREADS, 0)
+        eng.forward_raw(ip, n, lp)
+        t0 = time.perf_counter()
+        for _ in range(max(steps // 3, 2)):
+            eng.forward_raw(ip, n, lp)
+        dt1 = (time.perf_counter() - t0) / max(steps // 3, 2)
+        eng.set_option(V.OPT_HOST_THREADS, 1)
+        res["pinned_single_feeding_thread"] = {"value": n / dt1, "unit": "images/s", "ms_per_call": dt1 * 1e3}
+        parts = [np.array(h_imgs[i]) for i in range(n)]       # n separate pageable allocations (Network.c:75-93)
+        eng.forward_scattered(parts)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            lg = eng.forward_scattered(parts)
+        dts = (time.perf_counter() - t0) / reps
+        res["scattered"] = {"value": n / dts, "unit": "images/s", "ms_per_call": dts * 1e3, "host_gather_gbs": n * 3 * S * S * 4 / dts / 1e9,
+                            "bound": "host memcpy into pinned staging (602 KB per image, read + write) shared by all GPUs' gather threads"}
+        res["results_equal"] = bool(int(lg.argmax(1).sum()) == checksum)
+        V.pinned_free(ip)
+        V.pinned_free(lp)
+    return res
+
+
+def variants(V, args, prec, peaks):
+    """Driver-visible sub-records: BASELINE.json configs[4] (384x384, 577 tokens, batch 512: the key-blocked attention
+    kernel), the non-default BF16 operand set at the headline configuration, and configs[1] (batch-1 latency) on the
+    weight tensors the reference ships."""
+    out = []
+
+    def measure(S, B, precision, weights, steps, label):
+        T = (S // 16) ** 2 + 1
+        with V.Engine(weights, S, max_batch=B, precision=precision) as eng:
+            eng.set_class_row_pruning(False)
+            imgs = V.synth_images(B, S, 7)
+            d_imgs, d_logits = V.dev_alloc(0, imgs.nbytes), V.dev_alloc(0, B * 1000 * 4)
+            V.dev_upload(0, d_imgs, imgs)
+            for _ in range(3):
+                eng.enqueue_device(d_imgs, B, d_logits)
+            eng.sync()
+            eng.timer_start()
+            for _ in range(steps):
+                eng.enqueue_device(d_imgs, B, d_logits)
+            ms = eng.timer_stop() / steps
+            eng.sync()
+            eng.profile_enable(True)
+            for _ in range(steps):
+                eng.enqueue_device(d_imgs, B, d_logits)
+            prof = eng.profile_read()
+            eng.profile_enable(False)
+            name = eng.info()["precision"]
+            V.dev_free(0, d_imgs)
+            V.dev_free(0, d_logits)
+        value = B / (ms * 1e-3)
+        flop = FLOP_PER_IMAGE[S]
+        return {"variant": label, "metric": f"ViT-B/16 {S}x{S} inference throughput", "value": value, "unit": "images/s", "ms_per_step": ms,
+                "steps": steps, "warmup": 3, "dtype": name, "config": {"workload": f"ViT-B/16 {S}x{S} synthetic batch {B}, {T} tokens, all rows in the last layer"},
+                "model_frac_of_peak": {"burst": flop * value / 1e12 / peaks["bf16_tflops"], "sustained": flop * value / 1e12 / peaks["bf16_tflops_sustained"]},
+                "attention_ms_per_step": prof["attention"]["ms"] / steps, "step_breakdown_ms": {k: v["ms"] / steps for k, v in prof.items()}}
+
+    steps = max(args.steps // 2, 3)
+    out.append(measure(384, 512, prec, V.synth_weights(384, 42), steps, "configs[4]: 384x384, batch 512, default precision policy"))
+    w224 = V.synth_weights(224, 42)
+    other = V.PREC_BF16 if prec != V.PREC_BF16 else V.PREC_FP16
+    out.append(measure(224, 1024, other, w224, steps, "headline configuration with the non-default operand set"))
+    # batch-1 latency on the reference's shipped tensors (116 of 152; the 36 missing GEMM weights synthetic, seed 42)
+    shipped_dir = ROOT / "baseline" / "_ref" / "Network"
+    if shipped_dir.is_dir():
+        import vit_hostio as H
+        shipped = H.load_weights_dir(str(shipped_dir))
+        n_shipped = sum(a is not None for a in shipped)
+        w = [np.ascontiguousarray(a) if a is not None and a.size == b.size else b for a, b in zip(shipped, w224)]
+        with V.Engine(w, 224, max_batch=8, precision=prec) as eng:
+            img = V.synth_images(1, 224, 7)
+            h_img, ip = V.pinned_empty((1, 3, 224, 224))
+            h_img[...] = img
+            h_log, lp = V.pinned_empty((1, 1000))
+            d_img, d_log = V.dev_alloc(0, img.nbytes), V.dev_alloc(0, 4000)
+            V.dev_upload(0, d_img, img)
+            dev_ms, host_ms = [], []
+            for i in range(50 + 1000):
+                eng.timer_start()
+                eng.enqueue_device(d_img, 1, d_log)
+                ms = eng.timer_stop()
+                if i >= 50:
+                    dev_ms.append(ms)
+            for i in range(50 + 1000):
+                t1 = time.perf_counter()
+                eng.forward_raw(ip, 1, lp)
+                if i >= 50:
+                    host_ms.append((time.perf_counter() - t1) * 1e3)
+            info = eng.info()
+            V.dev_free(0, d_img)
+            V.dev_free(0, d_log)
+            V.pinned_free(ip)
+            V.pinned_free(lp)
+        out.append({"variant": "configs[1]: batch-1 latency on the reference's shipped Network/ tensors", "shipped_tensors": n_shipped, "synthetic_tensors": 152 - n_shipped,
+                    "dtype": info["precision"], "precision_fallbacks": info["precision_fallbacks"], "runs": 1000, "warmup": 50,
+                    "device_ms_median": float(np.median(dev_ms)), "device_ms_p99": float(np.percentile(dev_ms, 99)),
+                    "host_to_host_ms_median": float(np.median(host_ms)), "host_to_host_ms_p99": float(np.percentile(host_ms, 99)),
+                    "h2d_bytes": int(img.nbytes), "d2h_bytes": 4000, "top1": int(h_log.argmax())})
+    else:
+        out.append({"variant": "configs[1]: batch-1 latency on the reference's shipped Network/ tensors", "unavailable": "baseline/_ref/Network absent (run __graft_entry__.build() where /root/reference is mounted)"})
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import vit_b200 as V
@@ -197,8 +347,9 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        wait_group = dist.new_group(backend="gloo")   # CPU-side barrier for phases in which one rank drives several GPUs
     n_gpus = world
-    prec = V.PREC_FP16 if args.precision == "fp16" else V.PREC_BF16
+    prec = {"auto": V.PREC_AUTO, "fp16": V.PREC_FP16, "bf16": V.PREC_BF16}[args.precision]
     B = args.batch
     peaks = load_peaks()
     S = args.img_size
@@ -207,6 +358,7 @@ def run_ours(args):
     weights = V.synth_weights(S, 42)
     eng = V.Engine(weights, S, max_batch=B, n_gpus=1, device_ids=[local_rank], precision=prec)
     info = eng.info()
+    dtype_name = info["precision"]      # the operand type the passes run in ("fp16" for the default policy)
 
     # synthetic batch (seed 7), distinct images per rank; pinned host copy for the end-to-end leg
     h_imgs, h_imgs_ptr = V.pinned_empty((B, 3, S, S))
@@ -275,7 +427,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_gpus * B * args.steps / e2e_s
     top1 = h_logits.argmax(1)
-    logits_first = h_logits[:64].copy()   # rank 0: images 0.. of the seeded stream, checked against the CPU reference below
+    h_logits_full = h_logits.copy()     # logits of the timed (all-rows) configuration; rank 0's first images go to the parity block
 
     # ---- the engine's default configuration: last layer pruned to the class rows (same logits)
     eng.set_class_row_pruning(True)
@@ -335,6 +487,7 @@ def run_ours(args):
         lat = {"device_ms_median": float(np.median(dev_ms)), "device_ms_p99": float(np.percentile(dev_ms, 99)),
                "host_to_host_ms_median": float(np.median(host_ms)), "host_to_host_ms_p99": float(np.percentile(host_ms, 99)), "runs": 200}
 
+    out = None
     if rank == 0:
         rows = B * T
         step_ms_by_cat = {k: v["ms"] / args.steps for k, v in prof.items()}
@@ -345,9 +498,10 @@ def run_ours(args):
         out = {
             "metric": f"ViT-B/16 {S}x{S} inference throughput", "value": value, "unit": "images/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
             "config": {"workload": f"ViT-B/16 {S}x{S} synthetic batch {B} per GPU ({n_gpus * B} total), {T} tokens, 12 layers, random-init weights (seed 42), fp32 residual stream",
-                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "last_layer": "all rows (class-row pruning off)", "l2": f"inputs ({h_imgs.nbytes // 1000000} MB/batch) and activations larger than the 126 MB L2"},
+                       "batch_per_gpu": B, "parallelism": f"dp{n_gpus}", "last_layer": "all rows (class-row pruning off)",
+                       "precision_policy": info["precision_policy"], "operands": f"{dtype_name} x {dtype_name} -> fp32 accumulate (conv_proj: tf32 from the fp32 image)", "l2": f"inputs ({h_imgs.nbytes // 1000000} MB/batch) and activations larger than the 126 MB L2"},
             "model_tflops": flop_per_image * value / 1e12,
             "model_frac_of_peak": {"burst": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops"],
                                    "sustained": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
@@ -372,14 +526,31 @@ def run_ours(args):
             out["nccl_logit_allgather_ms"] = gather_ms
         if lat:
             out["batch1_latency"] = lat
-        if n_gpus == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(logits_first if S == 224 else None)
-        sys.stdout.flush()
-        os.write(real_stdout, (json.dumps(out) + "\n").encode())
-
+    # ---- done with the per-rank engine
+    first_logits = h_logits_full[:PARITY_IMAGES].copy() if rank == 0 else None
+    first_images = h_imgs[:PARITY_IMAGES].copy() if rank == 0 else None
     V.dev_free(0, d_imgs)
     V.dev_free(0, d_logits)
     eng.close()
+    V.pinned_free(h_imgs_ptr)
+    V.pinned_free(h_logits_ptr)
+
+    # ---- N > 1: the C ABI's OWN multi-GPU path -- one process, vit_cuda_init(n_gpus = N), vit_cuda_forward feeding every
+    #      GPU from its own host thread -- driven by rank 0 while the other ranks (their engines freed) wait on the CPU
+    if world > 1:
+        dist.barrier(group=wait_group)
+        if rank == 0 and not args.no_inproc:
+            out["abi_inproc"] = abi_inproc(V, weights, S, B, world, args.steps, prec, out["e2e"]["value"])
+        dist.barrier(group=wait_group)
+
+    if rank == 0:
+        if n_gpus == 1 and S == 224 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(first_logits)
+            out["parity"] = parity_block(first_logits, PARITY_IMAGES, weights, first_images, dtype_name)
+        if n_gpus == 1 and S == 224 and B == 1024 and not args.no_variants:
+            out["variants"] = variants(V, args, prec, peaks)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -391,7 +562,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--img-size", type=int, choices=[224, 384], default=224, help="384: BASELINE.json configs[4] (use --batch 512)")
-    ap.add_argument("--precision", choices=["bf16", "fp16"], default="bf16")
+    ap.add_argument("--precision", choices=["auto", "bf16", "fp16"], default="auto", help="auto = the engine's default policy (FP16 operands, BF16 fallback on overflow)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the sub-records (384x384, non-default precision, shipped-tensor latency)")
+    ap.add_argument("--no-inproc", action="store_true", help="N > 1: skip the single-process vit_cuda_init(n_gpus = N) leg")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -40,15 +40,26 @@ enum {
     VIT_E_CUDA        = -3,  /* CUDA runtime/driver error (see last_error) */
     VIT_E_NOMEM       = -4,
     VIT_E_DEVICE_TRAP = -5,  /* a kernel watchdog fired (pipeline dead-lock guard) */
-    VIT_E_RANGE       = -6   /* vit_cuda_sync only: the single-pass softmax flagged a row (see
-                                vit_cuda_set_attention_exact); the pass must be enqueued again */
+    VIT_E_RANGE       = -6   /* vit_cuda_sync: the single-pass softmax flagged a row, or FP16 operands overflowed
+                                under VIT_PREC_AUTO -- the engine has switched to the exact softmax / to BF16 and
+                                EVERY pass enqueued on that slot since its last vit_cuda_sync must be enqueued again.
+                                vit_cuda_init_ex with VIT_PREC_FP16: a weight does not fit FP16. */
 };
 
 /* GEMM-operand storage type.  Accumulation, residual stream, LayerNorm statistics,
  * softmax and the classifier head are always fp32. */
 enum {
-    VIT_PREC_BF16 = 0,       /* default: BF16 operands, kind::f16 tcgen05, FP32 accumulate */
-    VIT_PREC_FP16 = 1        /* FP16 operands (same tensor-core rate, 3 more mantissa bits) */
+    VIT_PREC_BF16 = 0,       /* BF16 operands, kind::f16 tcgen05, FP32 accumulate.  max |dlogit| vs ViT_seq ~0.03 on
+                                random-init weights: outside the stated 2e-2 + 1e-2 |ref| on ~0.3 % of the logits. */
+    VIT_PREC_FP16 = 1,       /* FP16 operands (same tensor-core rate, 3 more mantissa bits; meets the stated tolerance
+                                with a 5x margin).  Values beyond 65504 overflow: init fails with VIT_E_RANGE if a
+                                weight does, and a forward whose activations do fails with VIT_E_RANGE. */
+    VIT_PREC_AUTO = 2        /* default (vit_cuda_init, ViT_cuda): FP16 operands, with the BF16 operand set resident
+                                beside them (+0.17 GB).  An FP16 overflow anywhere makes a logit non-finite, which the
+                                classifier kernel detects; vit_cuda_forward then transparently repeats the call with
+                                BF16 operands (after three such calls the engine stays on BF16); a weight that does
+                                not fit FP16 selects BF16 at init.  vit_cuda_info reports policy, active type and
+                                the number of fallbacks. */
 };
 
 #define VIT_NUM_TENSORS 152  /* torchvision vit_b_16 state_dict order, SURVEY.md App. A */
@@ -58,7 +69,7 @@ enum {
  * the operand precision, replicate them on n_gpus devices (devices 0..n_gpus-1) and
  * allocate per-device workspaces for up to max_batch_per_gpu images per pass.
  * The host weight arrays are not referenced after return (the reference re-uploads them
- * on every op, ViT_opencl.c:115-124). */
+ * on every op, ViT_opencl.c:115-124).  Operand precision: VIT_PREC_AUTO. */
 int vit_cuda_init(const vit_tensor* networks, int n_tensors, int img_size,
                   int max_batch_per_gpu, int n_gpus);
 
@@ -107,6 +118,16 @@ int   vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float*
 int   vit_cuda_sync(int gpu_slot);
 void* vit_cuda_stream(int gpu_slot);
 
+/* Operand-precision weight cache.  vit_cuda_save_weight_cache writes slot 0's device weight arena -- the converted
+ * GEMM operands of every resident precision, the LayerNorm-folded copies of in_proj / mlp_0 with their column sums
+ * and constant vectors, the tf32-rounded conv_proj weight and the small fp32 tensors -- as ONE checksummed file;
+ * vit_cuda_init_from_cache brings an engine up from it with one read and one host-to-device copy per GPU: no 152
+ * file reads, no fp32 upload, no conversion, no folding (the reference re-reads and re-rounds 330 MB of fp32 per
+ * start and re-uploads weights on every op, Network.c:119-194, ViT_opencl.c:115-124).  Image size and precision
+ * policy are those the cache was written with.  VIT_E_ARG on a bad / corrupt / mismatching file. */
+int vit_cuda_save_weight_cache(const char* path);
+int vit_cuda_init_from_cache(const char* path, int max_batch_per_gpu, int n_gpus, const int* device_ids);
+
 /* Release all device memory, streams and pinned staging.  Safe to call when not
  * initialised. */
 void vit_cuda_free(void);
@@ -118,8 +139,8 @@ const char* vit_cuda_last_error(void);
  * report gpu_launches. */
 long long vit_cuda_launch_count(void);
 
-/* Softmax variant of the fused attention kernel (224x224 path).  Default (0): ONE pass over the
- * scores with the exponent offset taken from 16 of the row's scores -- exact unless some logit
+/* Softmax variant of the fused attention kernel.  Default (0): ONE pass over the
+ * scores with the exponent offset taken from 8 of the row's scores -- exact unless some logit
  * exceeds those by more than ~110, which the kernel detects; vit_cuda_forward then transparently
  * repeats the call with the exact variant, vit_cuda_sync returns VIT_E_RANGE and switches the
  * engine over.  1: always the exact two-pass softmax (row maximum first, ViT_seq.c:178-191).
@@ -134,9 +155,24 @@ int vit_cuda_set_attention_exact(int on);
  * function of the input; 6.3 % of the model's multiply-adds are never executed. */
 int vit_cuda_set_class_row_pruning(int on);
 
+/* Run-time switches (all also readable).  Each has an environment variable of the same meaning that is read ONCE,
+ * at vit_cuda_init*: VIT_ATTN_EXACT, VIT_PRUNE_LAST, VIT_LN_FUSED, VIT_PDL, VIT_GRAPHS, VIT_HOST_THREADS. */
+enum {
+    VIT_OPT_ATTENTION_EXACT   = 0,  /* 1: always the exact two-pass softmax (default 0, see vit_cuda_set_attention_exact) */
+    VIT_OPT_CLASS_ROW_PRUNING = 1,  /* default 1, see vit_cuda_set_class_row_pruning */
+    VIT_OPT_LN_FUSED          = 2,  /* default 1: LayerNorm folded into the GEMMs; 0: separate warp-per-row LayerNorm kernels */
+    VIT_OPT_PDL               = 3,  /* default 1: programmatic dependent launch between the kernels of a pass */
+    VIT_OPT_GRAPHS            = 4,  /* default 1: passes of <= 8 images replay a captured CUDA graph */
+    VIT_OPT_HOST_THREADS      = 5   /* default 1: vit_cuda_forward feeds every GPU from its own host thread (n_gpus > 1);
+                                       0: one thread issues for all GPUs in turn */
+};
+int vit_cuda_set_option(int option, int value);
+int vit_cuda_get_option(int option, int* value);
+
 /* Facts about the engine/device, for logs: fills up to n entries of
- * {sm_count, cc_major, cc_minor, max_batch, tokens, precision, n_gpus, ws_bytes>>20,
- *  attention_exact, attention_fallbacks, class_row_pruning}. */
+ * {sm_count, cc_major, cc_minor, max_batch, tokens, active operand precision (VIT_PREC_BF16 / FP16), n_gpus,
+ *  ws_bytes>>20, attention_exact, attention_fallbacks, class_row_pruning, precision policy (VIT_PREC_*),
+ *  precision_fallbacks, weight_bytes>>20}. */
 int vit_cuda_info(long long* out, int n);
 
 /* CUDA-event stopwatch on a slot's stream: start records an event, stop records a second one,
@@ -148,8 +184,8 @@ int vit_cuda_timer_stop(int gpu_slot, float* ms);
  * by an event pair on the slot's stream; vit_cuda_profile_read synchronises, returns the summed
  * milliseconds and launch count per category (VIT_PROF_*) since the last read, and resets. */
 enum {
-    VIT_PROF_PATCHIFY = 0,   /* patch extraction + class rows */
-    VIT_PROF_EMBED_GEMM,     /* conv_proj GEMM */
+    VIT_PROF_PATCHIFY = 0,   /* class-token rows (there is no patch extraction: conv_proj reads the image) */
+    VIT_PROF_EMBED_GEMM,     /* conv_proj GEMM (tf32, straight from the fp32 image) */
     VIT_PROF_LAYERNORM,      /* ln_1 + ln_2 */
     VIT_PROF_QKV_GEMM,       /* in_proj */
     VIT_PROF_ATTENTION,      /* fused softmax(QK^T)V */
@@ -229,9 +265,13 @@ int vit_cuda_debug_attention_trace(const float* qkv, int batch, int tokens, int 
 
 /* Patch embedding for `batch` images [batch][3][S][S]: conv_proj + class token + position
  * embedding -> out [batch*tokens][768] fp32.  Replaces Conv2d/flatten_transpose/
- * class_token/pos_emb, ViT_seq.c:25-101 / Conv2d_Kernel, kernel.cl:120-175. */
+ * class_token/pos_emb, ViT_seq.c:25-101 / Conv2d_Kernel, kernel.cl:120-175.  The GEMM reads the fp32
+ * image directly (5-D TMA view, no im2col buffer) as kind::tf32: pixels are used with their 13 low
+ * mantissa bits ignored, conv_w rounded to tf32; `precision` only selects the type of the
+ * operand-precision copy of the rows that the kernel emits beside the fp32 result.
+ * out_cast (nullable): that copy widened to fp32. */
 int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w,
-                      const float* conv_b, const float* pos, float* out,
+                      const float* conv_b, const float* pos, float* out, float* out_cast,
                       int batch, int img_size, int precision);
 
 /* Final LayerNorm of the class rows + classifier: x [batch*tokens][768] fp32 ->

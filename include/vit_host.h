@@ -38,6 +38,15 @@ typedef vit_tensor Network;
 ImageData* load_image_data(const char* filename);
 void       free_image_data(ImageData* images);
 
+/* Streaming form of load_image_data for files that should not be held in memory as a whole (the reference reads the
+ * complete file into n separately malloc'd images, Network.c:66-93): open validates the header against the file size,
+ * read copies up to max_images further images, contiguous NCHW, into a caller-provided buffer (pinned memory makes
+ * the engine's host-to-device copy direct) and returns how many it delivered (0 at the end, -1 on error). */
+typedef struct vit_image_stream vit_image_stream;
+vit_image_stream* vit_image_stream_open(const char* filename, int* n, int* c, int* h, int* w);
+int  vit_image_stream_read(vit_image_stream* s, float* dst, int max_images);
+void vit_image_stream_close(vit_image_stream* s);
+
 /* Scans `directory` for Weight_<idx>_*.bin, idx in [0,count); reads each as raw fp32 and
  * rounds every value to 6 decimals exactly as Network.c:185-187 does.  Unlike the
  * reference it does not exit(): returns the number of tensors loaded, or -1 if the
@@ -66,11 +75,11 @@ int load_weights_blob(const char* path, Network network[], int count, int* img_s
 /* ---- engine lifecycle with the reference's shape --------------------------------------- */
 
 /* Configuration picked up by initialize_cuda()/ViT_cuda(); also settable through the
- * environment: VIT_GPUS, VIT_MAX_BATCH, VIT_PRECISION=bf16|fp16. */
+ * environment: VIT_GPUS, VIT_MAX_BATCH, VIT_PRECISION=auto|fp16|bf16. */
 typedef struct {
     int n_gpus;             /* default 1 */
     int max_batch_per_gpu;  /* default 256 */
-    int precision;          /* VIT_PREC_* */
+    int precision;          /* VIT_PREC_*, default VIT_PREC_AUTO */
 } vit_host_config;
 void vit_host_set_config(const vit_host_config* cfg);
 
@@ -83,6 +92,11 @@ int  initialize_cuda(void);
 void ViT_cuda(ImageData* image, Network* networks, float** prb);
 /* Status of the last ViT_cuda() call (0 ok). */
 int  ViT_cuda_status(void);
+/* ViT_cuda() uploads the weights when it first sees them and again whenever the Network array's address, any tensor's
+ * data pointer or size, or a sample of 64 elements per tensor has changed since (the reference's usage is ONE static
+ * Network[152] array, so reloading other weights into it keeps the address).  A caller that edits weights in place
+ * in a way the sample may miss calls this to force the next ViT_cuda() to upload again. */
+void vit_host_invalidate_weights(void);
 /* Replaces Release_opencl(). */
 void Release_cuda(void);
 

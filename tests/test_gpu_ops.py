@@ -5,7 +5,7 @@ kernel (fp32 accumulation order + one output rounding)."""
 import numpy as np
 import pytest
 
-from conftest import round_operand
+from conftest import round_operand, round_tf32, trunc_tf32
 
 pytestmark = pytest.mark.gpu
 
@@ -165,19 +165,36 @@ def test_attention_dominant_late_key(vit, oracle, prec, tokens, late_key):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("img_size,batch", [(224, 3), (384, 2), (32, 5)])
+@pytest.mark.parametrize("img_size,batch", [(224, 3), (384, 2), (32, 5), (64, 2), (240, 1)])
 def test_embed(vit, oracle, prec, weights224, img_size, batch):
     """conv_proj + class_token + pos_embedding (Conv2d / flatten_transpose / class_token / pos_emb,
-    ViT_seq.c:25-101).  196 patches fit one 256-row tile per image, 576 (384x384) take three, 4 (32x32)
-    leave most of a tile empty: the per-image tiling must clip and zero-fill correctly in all of them."""
+    ViT_seq.c:25-101), im2col-free: the kernel reads the fp32 image through a 5-D TMA view and multiplies in
+    kind::tf32.  A CTA tile is floor(128 / G) whole patch rows of one image: 126 of 128 tile rows at 224 (one CTA
+    pair per image, the second clipped at patch 196), 120 at 384 (three pairs, the last CTA entirely out of
+    bounds), 4 patches at 32x32, 16 at 64, 225 at 240: the per-image tiling must clip and zero-fill correctly in
+    all of them.  Inputs are pre-rounded to what the tensor core keeps (tf32: pixels truncated, weights rounded
+    as the engine rounds them), so only the accumulation order differs from the oracle.  The operand-precision
+    copy of the rows (what the first LayerNorm-folded GEMM reads) must be the rounding of the fp32 rows."""
     w = weights224
     tokens = (img_size // 16) ** 2 + 1
     pos = w[3] if img_size == 224 else _rand((tokens * 768,), 90 + img_size, 0.05)
-    imgs = round_operand(vit.synth_images(batch, img_size, 21), prec)
-    conv_w = round_operand(w[1], prec)
-    got = vit.op_embed(imgs, w[0], conv_w, w[2], pos, precision=prec)
+    imgs = trunc_tf32(vit.synth_images(batch, img_size, 21))
+    conv_w = round_tf32(w[1])
+    got, cast = vit.op_embed(imgs, w[0], conv_w, w[2], pos, precision=prec, want_cast=True)
     ref = np.concatenate([oracle.embed(imgs[i], w[0], conv_w, w[2], pos) for i in range(batch)])
     _close(got, ref, 1e-5, 2e-5, f"patch embedding {img_size}")
+    assert np.array_equal(cast, round_operand(got, prec)), "operand-precision copy is not the rounding of the fp32 rows"
+
+
+def test_embed_on_unrounded_pixels(vit, oracle, weights224):
+    """The same kernel on raw fp32 pixels and weights, as the forward pass feeds it: tf32 keeps a 10-bit mantissa
+    (weights rounded, pixels truncated: relative error <= 2^-10 per product), so the rows stay within 2e-3 of the fp32
+    oracle on values of order 1."""
+    w = weights224
+    imgs = vit.synth_images(2, 224, 22)
+    got = vit.op_embed(imgs, w[0], w[1], w[2], w[3], precision=PRECS[0])
+    ref = np.concatenate([oracle.embed(imgs[i], w[0], w[1], w[2], w[3]) for i in range(2)])
+    assert np.abs(got - ref).max() <= 2e-3 * max(1.0, float(np.abs(ref).max())), np.abs(got - ref).max()
 
 
 def test_head(vit, oracle, weights224):

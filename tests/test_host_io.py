@@ -158,3 +158,52 @@ def test_weight_cache_blob_round_trip_and_damage_detection(vit, tmp_path):
     short = [a for a in w]
     short[6] = short[6][:-1].copy()
     assert vit.lib.save_weights_blob(str(bad).encode(), vit.as_network(short), 152, 224) != 0
+
+
+def test_streaming_image_reader_delivers_the_file_in_chunks(vit, tmp_path):
+    """vit_image_stream_* (bounded-memory form of load_image_data, Network.c:24-97): same pixels as the whole-file
+    loader in any chunking, n-limit respected, truncated files and bad headers refused."""
+    lib = vit.lib
+    lib.vit_image_stream_open.restype = C.c_void_p
+    lib.vit_image_stream_open.argtypes = [C.c_char_p] + [C.POINTER(C.c_int)] * 4
+    lib.vit_image_stream_read.restype = C.c_int
+    lib.vit_image_stream_read.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+    lib.vit_image_stream_close.restype = None
+    lib.vit_image_stream_close.argtypes = [C.c_void_p]
+    n, S = 7, 32
+    imgs = vit.synth_images(n, S, 5)
+    path = tmp_path / "input-7.bin"
+    assert lib.save_image_data(str(path).encode(), vit.fptr(imgs), n, 3, S, S) == 0
+    for chunk in (1, 3, 7, 50):
+        dims = [C.c_int() for _ in range(4)]
+        s = lib.vit_image_stream_open(str(path).encode(), *[C.byref(d) for d in dims])
+        assert s and [d.value for d in dims] == [n, 3, S, S]
+        got, buf = [], np.empty((chunk, 3, S, S), dtype=np.float32)
+        while True:
+            k = lib.vit_image_stream_read(s, vit.fptr(buf), chunk)
+            assert k >= 0
+            if k == 0:
+                break
+            got.append(buf[:k].copy())
+        assert lib.vit_image_stream_read(s, vit.fptr(buf), chunk) == 0       # stays at the end
+        lib.vit_image_stream_close(s)
+        assert np.array_equal(np.concatenate(got), imgs)
+    short = tmp_path / "short.bin"
+    short.write_bytes(path.read_bytes()[:-100])
+    assert not lib.vit_image_stream_open(str(short).encode(), None, None, None, None)
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(np.array([0, 3, S, S], dtype=np.int32).tobytes())
+    assert not lib.vit_image_stream_open(str(bad).encode(), None, None, None, None)
+    assert not lib.vit_image_stream_open(str(tmp_path / "none.bin").encode(), None, None, None, None)
+
+
+def test_host_only_library_has_the_same_assets_and_no_cuda(vit):
+    """lib/libvit_hostio.so (what bench.py --impl reference loads instead of the product library): same synthetic assets
+    bit for bit, and no dependency on the CUDA runtime."""
+    import subprocess
+    import vit_hostio as H
+    a, b = H.synth_weights(224, 42), vit.synth_weights(224, 42)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(H.synth_images(3, 224, 7, first_index=5), vit.synth_images(3, 224, 7, first_index=5))
+    ldd = subprocess.run(["ldd", str(H.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "cuda" not in ldd.lower() and "vit_b200" not in ldd

@@ -18,7 +18,6 @@ struct AttnParams {
     int kpad;          // tokens rounded up to 16
     void* out;         // [batch*tokens][768], operand precision
     float scale_log2;  // (1/sqrt(64)) * log2(e)
-    int no_pingpong;   // debug / tuning: 1 = the two query tiles do not take turns on the exponentials
     unsigned long long* trace;  // optional (debug): SM-clock timestamps of CTA 0's pipeline events, see ATTN_TRACE
 };
 
@@ -38,451 +37,36 @@ constexpr int ATTN_Q_TILE_BYTES = 128 * 128;  // 128 rows x 64 x 2 B
 
 __host__ __device__ inline int attn_kv_bytes(int kpad) { return kpad * 128; }
 
-// =============================================================================================
-// Persistent, software-pipelined kernel.
-//
-// One CTA per SM loops over (image, head) items.  Per item the two 128-row query tiles own one
-// TMEM region each:   S_t fp32 [0,kpad)  ->  P_t (bf16, packed two per column, written back in
-// place by the softmax threads)  ->  O_t fp32.  P never touches shared memory: the second MMA
-// takes its A operand from TMEM.  Shared memory holds the double-buffered Q/K/V tiles of the
-// current and the next item (TMA loads of item i+1 run under the softmax of item i) and one
-// output staging tile per query tile.
-//
-// TWO threads per query row.  One softmax warp per SM sub-partition and tile issues a dependent
-// instruction only every ~4 cycles (fixed-latency stalls; the MUFU pipe sat at 40 % with one thread
-// per row, profiles/r1_attention_trace.md), so every row is split by key range between two threads
-// of two different warps -- both may address the row's TMEM lane, as lane access is by (warp % 4):
-//     half A: keys [0,128)     S cols [0,128)     -> P cols [0,64)
-//     half B: keys [128,kpad)  S cols [128,kpad)  -> P cols [128, 128 + (kpad-128)/2)
-// Each half overwrites only S columns it has itself already read, and S cols [64,128) are dead
-// once half A is through, which is where O_t goes.  The halves agree on the row maximum through
-// shared memory (one 64-thread named barrier per item) and add their row sums in the epilogue.
-//
-//   warps 0-7 / 8-15  softmax + output for query tile 0 / 1: warp = tile*8 + half*4 + lane quarter
-//   warp 16  TMA producer     warps 17, 18  MMA issuers for query tile 0 / 1 (warp 17 owns TMEM)
-constexpr int ATTN2_THREADS = 19 * 32;
-constexpr int ATTN2_W_PRODUCER = 16, ATTN2_W_ISSUER = 17;
-// TMEM column plan (512 columns).  With kpad <= 224 (ViT-B/16 at 224^2: kpad = 208):
-//   S_0 [0,kpad)   S_1 [kpad,2 kpad)   O_1 at S_1 + 64   O_0 [2 kpad, 2 kpad+64)
-// so S_0 of the next item can be issued without waiting for O_0 to be drained.  Otherwise
-//   S_0 [0,256)  S_1 [256,512)  O_t at S_t + 64.
-struct AttnTmemPlan {
-    uint32_t s1, o0, o1;  // column of S_1, O_0, O_1 (S_0 is at column 0)
-    bool spare;
-    __device__ __forceinline__ uint32_t s_col(int t) const { return t ? s1 : 0u; }
-    __device__ __forceinline__ uint32_t o_col(int t) const { return t ? o1 : o0; }
-};
-__device__ __forceinline__ AttnTmemPlan attn2_tmem_plan(int kpad) {
-    AttnTmemPlan pl;
-    pl.spare = 2 * kpad + 64 <= 512;
-    pl.s1 = pl.spare ? kpad : 256;
-    pl.o1 = pl.s1 + 64;
-    pl.o0 = pl.spare ? 2 * kpad : 64;
-    return pl;
-}
-// Shared memory: two stages of {Q, K, V} x kpad rows x 128 B (Q only needs `tokens` rows; the second
-// query tile's descriptor runs on into the K rows behind it, whose S rows nobody reads), one
-// 128 x 128 B output staging tile per query tile, the row max / row sum exchange between the two
-// halves of a row, and the barriers.
+// Shared memory of the single-block kernels: two stages of {Q, K, V} x kpad rows x 128 B (Q only needs `tokens`
+// rows; the second query tile's descriptor runs on into the K rows behind it, whose S rows nobody reads).
 __host__ __device__ inline int attn2_stage_bytes(int kpad) { return 3 * attn_kv_bytes(kpad); }
-constexpr int ATTN2_OSTAGE_BYTES = 128 * 128;
-constexpr int ATTN2_XCH_BYTES = (2 * 2 * 128 + 2 * 2 * 2 * 128) * 4;  // max [tile][half][row], sum [parity][tile][half][row]
-__host__ inline int attn2_smem_bytes(int kpad) {
-    return 2 * attn2_stage_bytes(kpad) + 2 * ATTN2_OSTAGE_BYTES + ATTN2_XCH_BYTES + 256 + 1024;
-}
+constexpr int ATTN2_OSTAGE_BYTES = 128 * 128;   // one 128-row output staging tile (key-blocked two-pass kernel)
 
 template <int NTHREADS>
 __device__ __forceinline__ void attn_bar_sync(int id) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
 }
 
-template <int NTHREADS>
-__device__ __forceinline__ void attn_bar_arrive(int id) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTHREADS) : "memory");
-}
-
-// Set (sticky) by the single-pass softmax when a row's exponent range left its safe window (see the
-// kernel): the host then repeats the work with the exact two-pass variant.
-__device__ unsigned int g_attn_range_flag = 0;
+// The single-pass softmax raises VIT_FLAG_ATTN_RANGE in g_status_flags (ptx.cuh) when a row's exponent range left
+// its safe window (see the kernels): the host then repeats the work with the exact two-pass variant.
 constexpr float ATTN_FAST_SHIFT = 64.f;      // exponent head-room of the single-pass softmax (log2 units)
 constexpr float ATTN_FAST_SUM_MAX = 1.0e30f; // ~2^100: a larger row sum means the window was left
 
 // EXACT = true : two passes over S (exact row maximum first), P <= 1 as in the reference.
 // EXACT = false: ONE pass.  Softmax is shift invariant, so the exponent offset need not be the row
-//   maximum: it is m_ref = max of 16 of the row's scores (a chunk read by both halves of the row, so they
-//   agree without an exchange), lowered by 2^-64:  P_j = 2^((s_j - m_ref) c - 64).  The true maximum is
-//   >= m_ref, so the largest P is >= 2^-64 (nothing relevant underflows: bf16 and fp32 share the 8-bit
-//   exponent), and nothing overflows unless some score exceeds m_ref by more than ~160 / c (a logit
-//   gap of > 110 between a key and the best of those 16 keys).  That case is DETECTED (row sum
-//   beyond 2^100 or not finite -> g_attn_range_flag) and the host reruns with EXACT = true.
-//   TMEM reads (~64 B/clk/SM) bound this kernel, and this halves the reads of S.
-template <typename T, bool EXACT>
-__global__ void __launch_bounds__(ATTN2_THREADS, 1)
-attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
-                                  const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int kv_bytes = attn_kv_bytes(p.kpad);
-    const int stage_bytes = attn2_stage_bytes(p.kpad);
-    uint8_t* sO = smem + 2 * stage_bytes;  // [2 tiles] output staging, 128B-swizzled rows of 64 x 16-bit
-    float* xmax = reinterpret_cast<float*>(sO + 2 * ATTN2_OSTAGE_BYTES);  // [tile][half][128]
-    float* xsum = xmax + 2 * 2 * 128;                                     // [item parity][tile][half][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + ATTN2_XCH_BYTES);
-    uint64_t* kv_full = bars;        // [2 stages] Q,K,V of an item landed (tx)
-    uint64_t* stage_free = bars + 2; // [2 stages] every MMA reading the stage has completed
-    uint64_t* s_full = bars + 4;     // [2 tiles]  S_t in TMEM
-    uint64_t* p_full = bars + 6;     // [2 tiles]  P_t written back (256 arrivals)
-    uint64_t* o_full = bars + 8;     // [2 tiles]  O_t in TMEM
-    uint64_t* o_free = bars + 10;    // [2 tiles]  O_t drained, region reusable (256 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n_items = p.batch * 12;
-    const int nqt = p.tokens > 128 ? 2 : 1;
-    const AttnTmemPlan plan = attn2_tmem_plan(p.kpad);
-
-    if (warp == ATTN2_W_PRODUCER && lane == 0) {
-        tma_prefetch_desc(&tmap_qkv);
-        tma_prefetch_desc(&tmap_out);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&stage_free[i], nqt);
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 256);
-            mbar_init(&o_full[i], 1);
-            mbar_init(&o_free[i], 256);
-        }
-        fence_barrier_init();
-    }
-    if (warp == ATTN2_W_ISSUER) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == ATTN2_W_PRODUCER) {
-        // ------------------------------------------------------------ TMA producer
-        // One TMA operation keeps only a few dozen 128-byte row requests in flight, and every row of
-        // a head's Q/K/V slice lies in a different DRAM page (row pitch 4608 B): a whole item issued
-        // as three boxes took ~10 k cycles to land and set the kernel's period (profiles/r1_attention_
-        // trace.md).  So each of Q, K, V is fetched as two half-height boxes (six operations in flight),
-        // and the item after next is pulled into L2 ahead of time, where the real load then hits.
-        if (lane == 0) {
-            const int half_rows = p.kpad >> 1, half_bytes = half_rows * 128;
-            int it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int s = it & 1;
-                const int img = item / 12, head = item - img * 12;
-                const int row0 = img * p.tokens;
-                uint8_t* sQ = smem + s * stage_bytes;
-                uint8_t* sK = sQ + kv_bytes;
-                uint8_t* sV = sK + kv_bytes;
-                mbar_wait(&stage_free[s], ((it >> 1) & 1) ^ 1);
-                ATTN_TRACE(warp, it, 0);
-                mbar_arrive_expect_tx(&kv_full[s], stage_bytes);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    tma_load_2d(sQ + h * half_bytes, &tmap_qkv, &kv_full[s], head * ATTN_DH, row0 + h * half_rows);
-                    tma_load_2d(sK + h * half_bytes, &tmap_qkv, &kv_full[s], ATTN_DIM + head * ATTN_DH, row0 + h * half_rows);
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    tma_load_2d(sV + h * half_bytes, &tmap_qkv, &kv_full[s], 2 * ATTN_DIM + head * ATTN_DH, row0 + h * half_rows);
-                const int ahead = item + 2 * static_cast<int>(gridDim.x);
-                if (ahead < n_items) {
-                    const int img2 = ahead / 12, head2 = ahead - img2 * 12;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        tma_prefetch_l2_2d(&tmap_qkv, head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
-                        tma_prefetch_l2_2d(&tmap_qkv, ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
-                        tma_prefetch_l2_2d(&tmap_qkv, 2 * ATTN_DIM + head2 * ATTN_DH, img2 * p.tokens + h * half_rows);
-                    }
-                }
-            }
-        }
-    } else if (warp >= ATTN2_W_ISSUER) {
-        // ------------------------------------------------------------ MMA issuers: one warp per query tile
-        // Each a plain blocking loop  P_t(i) -> PV_t(i) -> K(i+1) -> S_t(i+1).  (A single warp polling both
-        // tiles' barriers sat on the critical path of both: each of its four issue actions per item cost
-        // 0.6-1.1 k cycles, profiles/r1_attention_trace.md.)  The two tiles share no TMEM columns, and the
-        // tensor pipe executes each issuer's instructions in order, which protects P_t(i) from S_t(i+1).
-        // The whole warp walks the loop so that descriptors and barrier addresses live in uniform
-        // registers; one elected lane issues.
-        const int t = warp - ATTN2_W_ISSUER;
-        const uint32_t idesc_s = make_idesc<T>(128, static_cast<uint32_t>(p.kpad), 0, 0);
-        const uint32_t idesc_o = make_idesc<__nv_bfloat16>(128, ATTN_DH, 0, 1);  // P, V are always bf16
-        const int ksteps = p.kpad / 16;
-        auto issue_s = [&](int stage, int it) {  // S_t = Q_t K^T of the item staged in `stage`
-            ATTN_TRACE(warp, it, 0);
-            if (elect_one()) {
-                const uint32_t q_addr = smem_u32(smem + stage * stage_bytes);
-                const uint32_t k_addr = q_addr + kv_bytes;
-#pragma unroll
-                for (int k = 0; k < ATTN_DH / 16; ++k)
-                    umma_f16(tmem_base + plan.s_col(t), desc_kmajor_sw128(q_addr + t * ATTN_Q_TILE_BYTES, k),
-                             desc_kmajor_sw128(k_addr, k), idesc_s, k != 0);
-                umma_commit(&s_full[t]);
-            }
-            __syncwarp();
-        };
-        auto issue_pv = [&](int stage, int it) {  // O_t = P_t V, P_t read from TMEM; then hand the stage back
-            ATTN_TRACE(warp, it, 1);
-            if (elect_one()) {
-                const uint32_t v_addr = smem_u32(smem + stage * stage_bytes) + 2 * kv_bytes;
-                for (int ks = 0; ks < ksteps; ++ks)  // keys [16 ks, 16 ks + 16): P cols of half A, then of half B
-                    umma_f16_ts(tmem_base + plan.o_col(t), tmem_base + plan.s_col(t) + ks * 8 + (ks >= 8 ? 64 : 0),
-                                desc_mnmajor_sw128(v_addr, ks), idesc_o, ks != 0);
-                umma_commit(&o_full[t]);
-                umma_commit(&stage_free[stage]);  // one arrival per query tile
-            }
-            __syncwarp();
-        };
-        const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-        const bool own_o = t == 0 && plan.spare;  // O_t has columns of its own (not inside the S_t region)
-        if (t < nqt && my_items > 0) {
-            mbar_wait(&kv_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            for (int it = 0; it < my_items; ++it) {
-                mbar_wait(&p_full[t], it & 1);
-                if (own_o) mbar_wait(&o_free[t], (it & 1) ^ 1);  // O_t(it-1) drained
-                tc_fence_after();
-                issue_pv(it & 1, it);
-                if (it + 1 < my_items) {
-                    mbar_wait(&kv_full[(it + 1) & 1], ((it + 1) >> 1) & 1);
-                    if (!own_o) mbar_wait(&o_free[t], it & 1);   // O_t(it) lives inside the S_t region
-                    tc_fence_after();
-                    issue_s((it + 1) & 1, it + 1);
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------ softmax / output warps
-        const int t = warp >> 3;            // query tile
-        const int half = (warp >> 2) & 1;   // key range: A = [0,128), B = [128,kpad)
-        const int quarter = warp & 3;       // TMEM lane quarter (must be warp % 4)
-        const int row = quarter * 32 + lane;  // row inside the tile
-        const bool warp_active = t < nqt && (t * 128 + quarter * 32) < p.tokens;
-        const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t taddr = tmem_base + lane_bits + plan.s_col(t & 1);
-        const uint32_t oaddr = tmem_base + lane_bits + plan.o_col(t & 1) + half * 32;  // this half's 32 O columns
-        const int nch = p.kpad / 16;
-        const int ch0 = half ? 8 : 0;                        // first 16-key chunk of this half
-        const int ch1 = half ? nch : (nch < 8 ? nch : 8);    // one past its last chunk
-        const uint32_t pbias = half ? 64u : 0u;              // P chunk c goes to column 8 c + pbias
-        const bool split = nch > 8;                          // half B has keys at all
-        const bool storer = (warp & 7) == 0 && lane == 0;    // issues this tile's output stores
-        const int pair_bar = 1 + t * 4 + quarter;            // named barrier of the two warps sharing these rows
-        const int nsteps = ch1 - ch0;                        // 16-key chunks of this half (<= 0: none)
-        const int my_items = blockIdx.x < n_items ? (n_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-        const bool pingpong = nqt == 2 && !p.no_pingpong;
-        if (pingpong && t == 1 && my_items > 0) attn_bar_arrive<512>(11);  // tile 0 exponentiates first
-        float* my_max = xmax + (t * 2 + half) * 128 + row;
-        const float* other_max = xmax + (t * 2 + (half ^ 1)) * 128 + row;
-        int it = 0;
-        // A warp whose rows are all padding still walks the barriers in lockstep (an mbarrier cannot
-        // take arrivals for a future phase); the warps of an unused tile (tokens <= 128) do nothing.
-        for (int item = blockIdx.x; t < nqt && item < n_items; item += gridDim.x, ++it) {
-            const int img = item / 12, head = item - img * 12;
-            float* my_sum = xsum + (((it & 1) * 2 + t) * 2 + half) * 128 + row;
-            const float* other_sum = xsum + (((it & 1) * 2 + t) * 2 + (half ^ 1)) * 128 + row;
-            ATTN_TRACE(warp, it, 0);
-            mbar_wait(&s_full[t], it & 1);
-            tc_fence_after();
-            ATTN_TRACE(warp, it, 1);
-            uint32_t ra[16], rb[16];
-            float mx = 0.f;
-            if (warp_active) {
-              if constexpr (EXACT) {
-                // Two passes over this half's S columns: pass 1 finds the exact row maximum (tcgen05.ld + max
-                // only), pass 2 is a straight stream  tcgen05.ld -> FFMA -> ex2 -> add / pack -> tcgen05.st  with
-                // no vote, branch or rescale.  With the true maximum every P is <= 1, exactly as in the
-                // reference's softmax (ViT_seq.c:178-191).  Cost: S is read twice, and TMEM reads (~64 B/clk/SM)
-                // are this kernel's ceiling (profiles/r1_attention_trace.md).
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                {
-                    int c = ch0;
-                    for (; c + 2 <= ch1; c += 2) {
-                        uint32_t v[32];
-                        tmem_ld_x32(taddr + c * 16, v);
-                        tmem_ld_wait();
-                        if (c * 16 + 32 <= p.tokens) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (c * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
-                        }
-                    }
-                    for (; c < ch1; ++c) {
-                        uint32_t v[16];
-                        tmem_ld_x16p(taddr + c * 16, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
-                    }
-                }
-                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                ATTN_TRACE(warp, it, 6);
-                if (nsteps > 0) tmem_ld_x16p(taddr + ch0 * 16, ra);  // pass 2's first load flies during the exchange
-                if (split) {
-                    *my_max = mx;
-                    attn_bar_sync<64>(pair_bar);
-                    mx = fmaxf(mx, *other_max);
-                }
-              } else {
-                // m_ref = max of the 16 scores of half A's LAST chunk, read by both halves of the row.  That
-                // chunk's columns never receive P (chunk c's P lands on columns [8c, 8c+8) < 8 * chunks of A)
-                // and become part of O only after every thread has arrived at p_full, so both halves see the
-                // same 16 scores whatever their relative progress.  The first chunk of the stream is fetched
-                // by the same round trip.
-                const int cm = (nch < 8 ? nch : 8) - 1;
-                tmem_ld_x16p(taddr + cm * 16, rb);
-                if (nsteps > 0) tmem_ld_x16p(taddr + ch0 * 16, ra);
-                tmem_ld_wait();
-                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                if (cm * 16 + 16 <= p.tokens) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        m4[j & 3] = fmaxf(m4[j & 3], fmaxf(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (cm * 16 + j < p.tokens) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(rb[j]));
-                }
-                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                ATTN_TRACE(warp, it, 6);
-              }
-            }
-            // Ping-pong: the exponentials of the two query tiles take turns on the MUFU pipe, so that one
-            // tile's MMA round trips, maximum pass and output epilogue run under the other tile's
-            // exponentials instead of both tiles computing and then both waiting.
-            if (pingpong) attn_bar_sync<512>(11 + t);
-            if (warp_active) {
-                const float moff = EXACT ? -mx * p.scale_log2 : fmaf(-mx, p.scale_log2, -ATTN_FAST_SHIFT);
-                ATTN_TRACE(warp, it, 7);
-                float sum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
-                auto exp_step = [&](const uint32_t* v, int c) {
-                    const int base = c * 16;
-                    uint32_t packed[8];
-                    if (base + 16 <= p.tokens) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
-                            const float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-                            sum4[j & 3] += e0 + e1;
-                            packed[j] = pack2<__nv_bfloat16>(e0, e1);
-                        }
-                    } else {  // ragged last chunk (at 197 tokens: 5 valid keys)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int c0 = base + 2 * j;
-                            float e0 = 0.f, e1 = 0.f;
-                            if (c0 < p.tokens) e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, moff));
-                            if (c0 + 1 < p.tokens) e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, moff));
-                            sum4[j & 3] += e0 + e1;
-                            packed[j] = pack2<__nv_bfloat16>(e0, e1);
-                        }
-                    }
-                    // in place: P chunk c lands on S columns this thread has already read
-                    tmem_st_x8p(taddr + c * 8 + pbias, packed);
-                };
-                // fully unrolled over the (at most 8) chunks of a half: TMEM addresses become base + immediate
-                // (no per-step R2UR / loop branch), the next chunk's load is in flight while this one is processed
-                const uint32_t sbase = taddr + ch0 * 16;
-#pragma unroll
-                for (int i = 0; i < 8; i += 2) {
-                    if (i < nsteps) {
-                        tmem_ld_wait();
-                        if (i + 1 < nsteps) tmem_ld_x16p(sbase + (i + 1) * 16, rb);
-                        exp_step(ra, ch0 + i);
-                    }
-                    if (i + 1 < nsteps) {
-                        tmem_ld_wait();
-                        if (i + 2 < nsteps) tmem_ld_x16p(sbase + (i + 2) * 16, ra);
-                        exp_step(rb, ch0 + i + 1);
-                    }
-                }
-                *my_sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-            }
-            if (pingpong && (t == 0 || it + 1 < my_items)) attn_bar_arrive<512>(11 + (t ^ 1));  // the other tile's turn
-            if (warp_active) {
-                tmem_st_wait();
-                tc_fence_before();
-            }
-            ATTN_TRACE(warp, it, 2);
-            // The previous item's output store must have finished reading the staging tile before anyone
-            // rewrites it: its issuer checks here, and nobody passes o_full (the PV MMA needs all 256
-            // p_full arrivals, this one included) before that.
-            if (storer) tma_store_wait_read<0>();
-            mbar_arrive(&p_full[t]);
-            mbar_wait(&o_full[t], it & 1);
-            tc_fence_after();
-            ATTN_TRACE(warp, it, 3);
-            if (warp_active) {
-                // both halves' row sums were written before their p_full arrivals (release), which the PV
-                // MMA behind o_full waited for; the buffer alternates per item, so a fast partner cannot
-                // overwrite it before this read
-                const float row_sum = *my_sum + *other_sum;  // a half without keys wrote 0
-                if constexpr (!EXACT) {
-                    if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN
-                }
-                const float inv_sum = fast_rcp(row_sum);
-                uint32_t r0[32];
-                tmem_ld_x32(oaddr, r0);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&o_free[t]);
-                ATTN_TRACE(warp, it, 4);
-                // this half's 32 O columns -> staging tile (128B-swizzled rows, conflict-free 16-byte
-                // pieces).  Rows past the image's last token are written too; the 3-D store clips them.
-                uint8_t* srow = sO + t * ATTN2_OSTAGE_BYTES + row * 128;
-                const uint32_t sw = lane & 7;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        w[q] = pack2<T>(__uint_as_float(r0[8 * j + 2 * q]) * inv_sum, __uint_as_float(r0[8 * j + 2 * q + 1]) * inv_sum);
-                    *reinterpret_cast<uint4*>(srow + (((half * 4 + j) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                fence_proxy_async_smem();
-            } else {
-                mbar_arrive(&o_free[t]);
-            }
-            // one full-width TMA store per query tile instead of 32 scattered 128-byte rows per warp
-            // instruction (the direct stores cost ~1.7 k LSU cycles per item, profiles/r1_attention_trace.md)
-            attn_bar_sync<256>(9 + t);
-            if (storer) {
-                tma_store_3d(&tmap_out, sO + t * ATTN2_OSTAGE_BYTES, head * ATTN_DH, t * 128, img);
-                tma_store_commit();
-            }
-            ATTN_TRACE(warp, it, 5);
-        }
-        if (storer) tma_store_wait_all<0>();
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == ATTN2_W_ISSUER) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
-    }
-}
-
+//   maximum: it is m_ref = max of a few of the row's scores, lowered by 2^-64:  P_j = 2^((s_j - m_ref) c - 64).
+//   The true maximum is >= m_ref, so the largest P is >= 2^-64 (nothing relevant underflows: bf16 and fp32
+//   share the 8-bit exponent), and nothing overflows unless some score exceeds m_ref by more than ~160 / c
+//   (a logit gap of > 110 between a key and the best of the reference keys).  That case is DETECTED (row sum
+//   beyond 2^100 or not finite -> VIT_FLAG_ATTN_RANGE) and the host reruns with EXACT = true.
+//   TMEM reads (~64 B/clk/SM) bound these kernels, and this halves the reads of S.
 
 // =============================================================================================
 // Streaming kernel (the one the engine uses for tokens <= 224).
 //
-// The persistent kernel above keeps the two query tiles of an item in two TMEM slots, and each slot is
-// a strictly serial chain  S MMA -> softmax -> PV MMA -> output epilogue -> next S MMA  (the next item's S
-// cannot be computed while P of this one still sits in the slot).  Its timeline (profiles/r1_attention_
-// trace.md, round-1 addendum) shows the softmax threads waiting or doing epilogue work for more than half
-// of every period, and the MUFU pipe -- one ex2 per score, the true floor of this kernel -- busy ~50 %.
+// (Round 1's first kernel kept the two query tiles of an item in two TMEM slots, each a strictly serial chain
+// S MMA -> softmax -> PV MMA -> output epilogue -> next S MMA; its timeline, profiles/r1_attention_trace.md,
+// showed the softmax threads waiting or doing epilogue work for more than half of every period.  It is gone.)
 //
 // Here the unit of work is ONE 128-row query tile (an item is two consecutive units), the S accumulator
 // is DOUBLE BUFFERED across units, and the roles are split so that nobody who exponentiates ever waits:
@@ -500,7 +84,7 @@ attention_sm100_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv, 
 // P(u-1), whose PV(u-1) was issued before it (the pipe executes in order); PV(u) waits for P(u) and for the
 // output warps to have drained O(u-1).
 //
-// Softmax: EXACT as in the persistent kernel (two passes, row maximum exchanged between the three parts),
+// Softmax: EXACT (two passes, row maximum exchanged between the three parts through shared memory),
 // otherwise single pass with the exponent offset m_ref = max of the LAST EIGHT scores of part 0's range --
 // columns that never receive P (a part's P fills only the first half of its range), so all three parts read
 // the same eight scores whatever their relative progress.
@@ -569,7 +153,7 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
     griddep_launch();
 
     if (warp == ATTN3_W_PRODUCER) {
-        // ------------------------------------------------------------ TMA producer (as in the persistent kernel)
+        // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             const int half_rows = p.kpad >> 1, half_bytes = half_rows * 128;
             int it = 0;
@@ -811,7 +395,7 @@ attention_sm100_stream_kernel(const __grid_constant__ CUtensorMap tmap_qkv, cons
                 const float* ps = xsum + (u % 3) * 3 * 128 + row;
                 const float row_sum = (ps[0] + ps[128]) + ps[256];
                 if constexpr (!EXACT) {
-                    if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN
+                    if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_status_flags, VIT_FLAG_ATTN_RANGE);  // also inf / NaN
                 }
                 const float inv_sum = fast_rcp(row_sum);
                 uint32_t r0[32], r1[32];
@@ -1170,7 +754,7 @@ namespace vit {
 //   head's last S has completed (its reload for the next head runs under the head's last exponentials and PVs),
 //   V once its last PV has (its reload runs under the next head's first block of exponentials).
 //
-// Rows whose scores leave the exponent window raise g_attn_range_flag exactly as in the single-block kernel;
+// Rows whose scores leave the exponent window raise VIT_FLAG_ATTN_RANGE exactly as in the single-block kernel;
 // the host then repeats the call with attention_sm100_blocked_kernel (exact).
 constexpr int ATTN4_THREADS = 18 * 32;
 // keys per S block: the row is cut into the fewest blocks of at most 224 keys (2 S buffers + O fit the 512 TMEM
@@ -1456,7 +1040,7 @@ attention_sm100_stream_blocked_kernel(const __grid_constant__ CUtensorMap tmap_q
                 }
                 const float* ps = xsum + (u & 1) * 3 * 128 + row;
                 const float row_sum = (ps[0] + ps[128]) + ps[256];
-                if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_attn_range_flag, 1u);  // also inf / NaN
+                if (t * 128 + row < p.tokens && !(row_sum < ATTN_FAST_SUM_MAX)) atomicOr(&g_status_flags, VIT_FLAG_ATTN_RANGE);  // also inf / NaN
                 const float inv_sum = fast_rcp(row_sum);
                 uint32_t r0[32], r1[32];
                 tmem_ld_x32(oaddr, r0);

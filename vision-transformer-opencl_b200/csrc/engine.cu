@@ -1,6 +1,7 @@
-// engine.cu -- the C ABI of include/vit_cuda.h: weight upload, workspaces, TMA descriptors,
-// the ViT-B/16 forward schedule (ViT_seq.c:337-439 / ViT_opencl.c:785-883 re-expressed as a
-// batch of token-flattened kernels) and the single-operator test entry points.
+// engine.cu -- the C ABI of include/vit_cuda.h: weight arena (conversion, LayerNorm folding, cache file),
+// workspaces, TMA descriptors, the ViT-B/16 forward schedule (ViT_seq.c:337-439 / ViT_opencl.c:785-883
+// re-expressed as a batch of token-flattened kernels), the host pipeline (one feeding thread per GPU) and the
+// single-operator test entry points (op_entry.inc).
 //
 // There is deliberately no CPU fallback: every entry point fails with VIT_E_NODEVICE unless a
 // compute-capability-10.x device is present.
@@ -54,79 +55,97 @@ int set_err(int code, const char* fmt, ...) {
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled g_encode = nullptr;
+std::atomic<PFN_encodeTiled> g_encode{nullptr};
 
 int load_driver() {
-    if (g_encode) return 0;
+    if (g_encode.load()) return 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled not available");
-    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    g_encode.store(reinterpret_cast<PFN_encodeTiled>(fn));
     return 0;
 }
 
-// 2-D row-major [rows][cols] tensor, box {box_cols, box_rows}, 128B swizzle (box_cols * elem = 128 B).
+CUtensorMapDataType operand_dtype(int prec) {
+    return prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
+// Dense tensor of `rank` dimensions (dims / box innermost first), 128B swizzle: the innermost box extent times the
+// element size is <= 128 bytes.  strides_bytes[i] = stride of dimension i + 1.
+int encode_tmap(CUtensorMap* m, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    VIT_TRY(load_driver());
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = g_encode.load()(m, dt, rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d, dims %llu x %llu ..., box %u x %u ...", (int)r, rank,
+                       (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return 0;
+}
+
+// 2-D row-major [rows][cols] tensor, box {box_cols, box_rows} (box_cols * elem = 128 B).
 int make_tmap_raw(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t cols, uint64_t rows,
                   uint32_t box_cols, uint32_t box_rows) {
-    VIT_TRY(load_driver());
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * elem_bytes};
     const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = g_encode(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu box=%ux%u", (int)r,
-                       (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
-    return 0;
+    return encode_tmap(m, dt, 2, base, dims, strides, box);
 }
 // operand-precision (16-bit) tensor
-int make_tmap(CUtensorMap* m, int prec, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
-              uint32_t box_rows) {
-    return make_tmap_raw(m, prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base,
-                         cols, rows, box_cols, box_rows);
+int make_tmap(CUtensorMap* m, int prec, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows) {
+    return make_tmap_raw(m, operand_dtype(prec), 2, base, cols, rows, box_cols, box_rows);
 }
-// fp32 tensor (residual stream): 32 columns = 128 bytes per box row
+// fp32 tensor (residual stream, tf32 conv_proj weight): 32 columns = 128 bytes per box row
 int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
     return make_tmap_raw(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, cols, rows, 32, box_rows);
 }
-
-// 3-D [d2][d1][d0] tensor of 16-bit elements, dense, box {64, box_d1, 1}, 128B swizzle: per-image views
-// whose rows past d1 are clipped on store / zero-filled on load.
+// 3-D [d2][d1][d0] tensor of 16-bit elements, dense, box {64, box_d1, 1}: per-image views whose rows
+// past d1 are clipped on store / zero-filled on load.
 int make_tmap_3d(CUtensorMap* m, int prec, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box_d1) {
-    VIT_TRY(load_driver());
     const cuuint64_t dims[3] = {d0, d1, d2};
     const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
     const cuuint32_t box[3] = {64, box_d1, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = g_encode(m, prec == VIT_PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                                const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) dims=%llu,%llu,%llu", (int)r,
-                                          (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
-    return 0;
+    return encode_tmap(m, operand_dtype(prec), 3, base, dims, strides, box);
 }
-
-// 3-D [d2][d1][d0] fp32 tensor, box {32, box_d1, 1} (128 bytes per box row), 128B swizzle
+// 3-D [d2][d1][d0] fp32 tensor, box {32, box_d1, 1} (128 bytes per box row)
 int make_tmap_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box_d1) {
-    VIT_TRY(load_driver());
     const cuuint64_t dims[3] = {d0, d1, d2};
     const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
     const cuuint32_t box[3] = {32, box_d1, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_err(VIT_E_CUDA, "cuTensorMapEncodeTiled(3d f32) failed (%d) dims=%llu,%llu,%llu", (int)r,
-                                          (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
-    return 0;
+    return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box);
+}
+// The fp32 images [nb][3][S][S] as the A operand of conv_proj (no im2col buffer): dimensions, innermost first,
+// kx (16, contiguous), ky (16, stride S), gx (G, stride 16), gy (G, stride 16 S), plane = image * 3 + channel
+// (stride S * S).  A box {16, 2, G, 128 / G, 1} is (128 / G) * G patch rows of 2 x 16 pixels = 128 bytes each.
+int make_tmap_image5d(CUtensorMap* m, const float* images, int S, int nb) {
+    const uint64_t G = S / kPatch, gyc = 128 / G;
+    const cuuint64_t dims[5] = {16, 16, G, G, static_cast<cuuint64_t>(3) * nb};
+    const cuuint64_t strides[4] = {static_cast<cuuint64_t>(S) * 4, 16 * 4, static_cast<cuuint64_t>(16) * S * 4, static_cast<cuuint64_t>(S) * S * 4};
+    const cuuint32_t box[5] = {16, 2, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(gyc), 1};
+    return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, images, dims, strides, box);
+}
+// rows of a conv_proj CTA tile = box rows of its 3-D store maps (gemm_sm100_staged_kernel, EMBED)
+int embed_rows_per_cta(int S) { return (128 / (S / kPatch)) * (S / kPatch); }
+int embed_tiles_per_image(int S) {
+    const int G = S / kPatch, gyc = 128 / G;
+    return (G + 2 * gyc - 1) / (2 * gyc);
+}
+
+// ------------------------------------------------------------------------------------ run-time switches
+struct Options {
+    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1};
+};
+Options g_opt;
+
+int env_flag(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? (atoi(s) != 0) : dflt;
 }
 
 // ------------------------------------------------------------------------------------ launches
-constexpr int kGemmBN = 256, kGemmStages = 4, kGemmEpiWG = 2;
-constexpr int kGemmThreads = (GEMM_NON_EPI_WARPS + 4 * kGemmEpiWG) * 32;
+constexpr int kGemmBN = 256;
 
 int check_launch(const char* what) {
     const cudaError_t e = cudaGetLastError();
@@ -136,15 +155,7 @@ int check_launch(const char* what) {
 }
 
 // Launch with programmatic stream serialization (the kernel must call griddep_wait() before it touches anything
-// its predecessor wrote).  VIT_PDL=0: ordinary launches.
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("VIT_PDL");
-        v = (s && atoi(s) == 0) ? 0 : 1;
-    }
-    return v == 1;
-}
+// its predecessor wrote).  VIT_OPT_PDL = 0: ordinary launches.
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -154,52 +165,26 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = g_opt.pdl.load(std::memory_order_relaxed) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-int attn_no_pingpong() {  // VIT_ATTN_NO_PINGPONG=1: tuning switch of the attention kernel (A/B testing)
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("VIT_ATTN_NO_PINGPONG");
-        v = (s && atoi(s) != 0) ? 1 : 0;
-    }
-    return v;
-}
-
-constexpr int kPairStages = 6;
-int gemm_impl() {  // VIT_GEMM_IMPL=1 selects the single-CTA 128x256 kernel (A/B testing)
-    static int impl = -1;
-    if (impl < 0) {
-        const char* s = getenv("VIT_GEMM_IMPL");
-        impl = (s && atoi(s) == 1) ? 1 : 2;
-    }
-    return impl;
-}
-
-template <typename T, int EPI>
-int launch_gemm_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count, cudaStream_t st) {
-    using L = GemmPairSmem<kPairStages>;
-    auto kern = gemm_sm100_pair_kernel<T, kPairStages, kGemmEpiWG, EPI>;
-    static int configured_dev_mask = 0;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): set once per pair, from whichever host
+// thread gets there first (one feeding thread per GPU, so the mask is atomic).
+template <typename K>
+int configure_smem(K kern, std::atomic<unsigned>& done_mask, int bytes) {
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured_dev_mask & (1 << dev))) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        configured_dev_mask |= 1 << dev;
+    CU_TRY(cudaGetDevice(&dev));
+    if (!(done_mask.load(std::memory_order_acquire) & (1u << dev))) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done_mask.fetch_or(1u << dev, std::memory_order_release);
     }
-    const int tiles = ((p.M + 255) / 256) * (p.N / 256);
-    const int grid = 2 * std::min(tiles, sm_count / 2);
-    kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, p);
-    return check_launch("gemm_pair");
+    return 0;
 }
 
 constexpr int kStagedStages = 5, kStagedSlots = 4;
-// LN = true: LayerNorm folded into the GEMM (consumer for EPI_BIAS / EPI_BIAS_GELU, producer for
-// EPI_BIAS_RESIDUAL, see gemm_sm100.cuh).  The producer gives one operand stage up for the two
-// staging tiles of the operand-precision copy.
 template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false, int kEpiWarps = 8>
 int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
                            const GemmParams& p, int sm_count, cudaStream_t st, const CUtensorMap* tres = nullptr) {
@@ -207,29 +192,18 @@ int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const C
     using L = GemmStagedSmem<STAGES, SLOTS, CAST, kPreFloats * 4>;
     static_assert(L::DYN_BYTES <= 232448, "shared memory budget");
     auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED, EMBED>;
-    static int configured_dev_mask = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured_dev_mask & (1 << dev))) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        configured_dev_mask |= 1 << dev;
-    }
+    static std::atomic<unsigned> configured{0};
+    VIT_TRY(configure_smem(kern, configured, L::DYN_BYTES));
     if (p.N % kGemmBN || p.K % GEMM_BK || p.M <= 0)
         return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64)", p.M, p.N, p.K);
     if (LN && (EPI == EPI_BIAS_RESIDUAL ? (p.N != kDim || !p.stats_out) : (p.K != kDim || !p.stats_in || !p.colsum || p.stats_parts <= 0)))
         return set_err(VIT_E_ARG, "LayerNorm-folded gemm: bad statistics arguments (N=%d K=%d)", p.N, p.K);
+    if (EMBED && (p.grid_w <= 0 || p.grid_w > 64 || p.patches != p.grid_w * p.grid_w))
+        return set_err(VIT_E_ARG, "conv_proj: patch grid %d x %d not supported (1..64)", p.grid_w, p.grid_w);
     const int tiles = ((p.M + 255) / 256) * (p.N / 256);
     const int grid = 2 * std::min(tiles, sm_count / 2);
     CU_TRY(launch_pdl(kern, dim3(grid), dim3((GEMM_NON_EPI_WARPS + kEpiWarps) * 32), L::DYN_BYTES, st, ta, tb, tout, tcast, tres ? *tres : tout, p));
     return check_launch("gemm_staged");
-}
-int res_cfg() {  // VIT_RES_CFG: A/B switch of the residual GEMM's shared-memory split (tuning)
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("VIT_RES_CFG");
-        v = s ? atoi(s) : 0;
-    }
-    return v;
 }
 // LN = true: LayerNorm folded into the GEMM (consumer for EPI_BIAS / EPI_BIAS_GELU, producer for
 // EPI_BIAS_RESIDUAL, see gemm_sm100.cuh).  The producer pays for the staging tiles of the
@@ -241,25 +215,21 @@ int launch_gemm_staged_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
         // Measured (B = 1024): mlp_3 (K = 3072, tensor bound) needs the fifth operand stage (4 stages: +9 %) and
         // is indifferent to the slot count; out_proj (K = 768, HBM bound) needs the four residual slots to keep
         // enough chunk loads in flight (3 slots: +23 %) and is indifferent to the stage count.
-        if ((p.K >= 2048) != (res_cfg() == 1)) return launch_gemm_staged_cfg<T, EPI, LN, 5, 3, 1>(ta, tb, tout, tcast, p, sm_count, st);
+        if (p.K >= 2048) return launch_gemm_staged_cfg<T, EPI, LN, 5, 3, 1>(ta, tb, tout, tcast, p, sm_count, st);
         return launch_gemm_staged_cfg<T, EPI, LN, 4, 4, 2>(ta, tb, tout, tcast, p, sm_count, st);
     } else if constexpr (EPI == EPI_BIAS_RESIDUAL) {
         return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0>(ta, tb, tout, tcast, p, sm_count, st);
     } else if constexpr (LN) {
-        // 6 KB of staged parameters cost one output slot; loading them in the epilogue threads instead (4 slots)
-        // measured 7 % slower on mlp_0
-        if (res_cfg() == 4) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, false>(ta, tb, tout, tcast, p, sm_count, st);
-        if constexpr (EPI == EPI_BIAS_GELU) {
-            if (res_cfg() == 6) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, 3, 0, true, false, 16>(ta, tb, tout, tcast, p, sm_count, st);
-        }
+        // 6 KB of staged parameters cost one output slot (loading them in the epilogue threads instead, with 4 slots,
+        // measured 7 % slower on mlp_0; 16 instead of 8 epilogue warps for the GELU epilogue: no change)
         return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, 3, 0, true>(ta, tb, tout, tcast, p, sm_count, st);
     } else {
-        if (res_cfg() == 5) return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, false>(ta, tb, tout, tcast, p, sm_count, st);
         return launch_gemm_staged_cfg<T, EPI, LN, kStagedStages, kStagedSlots, 0, true>(ta, tb, tout, tcast, p, sm_count, st);
     }
 }
-// conv_proj as the EMBED variant of the residual kernel (one CTA pair per image): ta 3-D patch map, tout 3-D fp32
-// token map, tcast 3-D operand-precision token map (ln only), tpos 2-D pos_embedding map.  p.M = images * row tiles per image * 256.
+// conv_proj as the EMBED variant of the residual kernel (tf32 MMA straight from the fp32 image): ta 5-D image map
+// (make_tmap_image5d), tb fp32 weight map, tout 3-D fp32 token map, tcast 3-D operand-precision token map (ln only) --
+// both with embed_rows_per_cta() rows per box --, tpos 2-D pos_embedding map.  p.M = images * tiles per image * 256.
 template <typename T>
 int launch_gemm_embed_t(bool ln, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
                         const CUtensorMap& tpos, const GemmParams& p, int sm_count, cudaStream_t st) {
@@ -289,75 +259,29 @@ int launch_gemm_staged_ln(int prec, const CUtensorMap& ta, const CUtensorMap& tb
                                  : launch_gemm_staged_t<__nv_bfloat16, EPI, true>(ta, tb, tout, taux, p, sm_count, st);
 }
 
-template <typename T, int EPI>
-int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count, cudaStream_t st) {
-    if (p.N % kGemmBN || p.K % GEMM_BK || p.N > GEMM_MAX_N || p.M <= 0)
-        return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64, N<=3072)", p.M, p.N, p.K);
-    if (gemm_impl() == 2) return launch_gemm_pair_t<T, EPI>(ta, tb, p, sm_count, st);
-    using L = GemmSmem<kGemmBN, kGemmStages>;
-    auto kern = gemm_sm100_kernel<T, kGemmBN, kGemmStages, kGemmEpiWG, EPI>;
-    static bool configured = false;  // per instantiation; attribute is per device but identical on all
-    static int configured_dev_mask = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured || !(configured_dev_mask & (1 << dev))) {
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        configured = true;
-        configured_dev_mask |= 1 << dev;
-    }
-    if (p.N % kGemmBN || p.K % GEMM_BK || p.N > GEMM_MAX_N || p.M <= 0)
-        return set_err(VIT_E_ARG, "gemm shape M=%d N=%d K=%d unsupported (N%%256, K%%64, N<=3072)", p.M, p.N, p.K);
-    const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / kGemmBN);
-    const int grid = std::min(tiles, sm_count);
-    kern<<<grid, kGemmThreads, L::DYN_BYTES, st>>>(ta, tb, p);
-    return check_launch("gemm");
-}
-
-template <int EPI>
-int launch_gemm(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int sm_count,
-                cudaStream_t st) {
-    return prec == VIT_PREC_FP16 ? launch_gemm_t<__half, EPI>(ta, tb, p, sm_count, st)
-                                 : launch_gemm_t<__nv_bfloat16, EPI>(ta, tb, p, sm_count, st);
-}
-
-template <typename T, bool EXACT>
-int launch_attention_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count, cudaStream_t st) {
-    auto kern = attention_sm100_persistent_kernel<T, EXACT>;
-    const int smem = attn2_smem_bytes(p.kpad);
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<std::min(p.batch * kHeads, sm_count), ATTN2_THREADS, smem, st>>>(tqkv, tout, p);
-    return check_launch("attention");
-}
 template <typename T, bool EXACT>
 int launch_attention_stream_t(const CUtensorMap& tqkv, const CUtensorMap& tout32, const AttnParams& p, int sm_count, cudaStream_t st) {
     auto kern = attention_sm100_stream_kernel<T, EXACT>;
-    const int smem = attn3_smem_bytes(p.kpad);
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN3_THREADS), smem, st, tqkv, tout32, p));
+    const int smem = attn3_smem_bytes(224);   // the largest single-block case: one attribute value serves every token count
+    static std::atomic<unsigned> configured{0};
+    VIT_TRY(configure_smem(kern, configured, smem));
+    CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN3_THREADS), attn3_smem_bytes(p.kpad), st, tqkv, tout32, p));
     return check_launch("attention_stream");
 }
 template <typename T>
 int launch_attention_stream_blocked_t(const CUtensorMap& tqkv, const CUtensorMap& tout32, const AttnParams& p, int sm_count, cudaStream_t st) {
     auto kern = attention_sm100_stream_blocked_kernel<T>;
-    const int smem = attn4_smem_bytes(p.tokens);
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN4_THREADS), smem, st, tqkv, tout32, p));
+    static std::atomic<unsigned> configured{0};
+    VIT_TRY(configure_smem(kern, configured, attn4_smem_bytes(ATTNL_MAX_TOKENS)));
+    CU_TRY(launch_pdl(kern, dim3(std::min(p.batch * kHeads, sm_count)), dim3(ATTN4_THREADS), attn4_smem_bytes(p.tokens), st, tqkv, tout32, p));
     return check_launch("attention_stream_blocked");
-}
-int attn_impl() {  // VIT_ATTN_IMPL=2: the two-slot persistent kernel instead of the streaming one (A/B testing)
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("VIT_ATTN_IMPL");
-        v = (s && atoi(s) == 2) ? 2 : 3;
-    }
-    return v;
 }
 template <typename T>
 int launch_attention_blocked_t(const CUtensorMap& tqkv, const CUtensorMap& tout, const AttnParams& p, int sm_count, cudaStream_t st) {
     auto kern = attention_sm100_blocked_kernel<T>;
-    const int smem = attnl_smem_bytes(p.tokens);
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<std::min(p.batch * kHeads, sm_count), ATTNL_THREADS, smem, st>>>(tqkv, tout, p);
+    static std::atomic<unsigned> configured{0};
+    VIT_TRY(configure_smem(kern, configured, attnl_smem_bytes(ATTNL_MAX_TOKENS)));
+    kern<<<std::min(p.batch * kHeads, sm_count), ATTNL_THREADS, attnl_smem_bytes(p.tokens), st>>>(tqkv, tout, p);
     return check_launch("attention_blocked");
 }
 constexpr int kAttnSingleBlockMaxTokens = 224;  // up to here the whole key range of an image is one S block in TMEM
@@ -365,40 +289,36 @@ constexpr int kAttnSingleBlockMaxTokens = 224;  // up to here the whole key rang
 int attention_load_box_rows(int tokens) {
     return tokens <= kAttnSingleBlockMaxTokens ? ((tokens + 15) / 16 * 16) / 2 : ATTNL_KB;
 }
-// tqkv: load map of the packed QKV activation with attention_load_box_rows(tokens) rows per box,
-// tout: 3-D store map of the output (make_tmap_3d, 128 rows per box)
+// tqkv: load map of the packed QKV activation with attention_load_box_rows(tokens) rows per box.
 // exact: two-pass softmax (exact row maximum); otherwise the single-pass variant, which raises
-// g_attn_range_flag when a row left its exponent window (the caller then repeats with exact = true).
-// tout: 3-D store map of the output with 128-row boxes (persistent and key-blocked kernels), tout32: the same
-// with 32-row boxes (streaming kernel, one store per output warp).
+// VIT_FLAG_ATTN_RANGE when a row left its exponent window (the caller then repeats with exact = true).
+// tout: 3-D store map of the output with 128-row boxes (two-pass key-blocked kernel), tout32: the same
+// with 32-row boxes (streaming kernels, one store per output warp).
 int launch_attention(int prec, const CUtensorMap& tqkv, const CUtensorMap& tout, const CUtensorMap& tout32, const AttnParams& p,
                      int sm_count, cudaStream_t st, bool exact) {
     if (p.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", p.tokens, ATTNL_MAX_TOKENS);
     const bool h = prec == VIT_PREC_FP16;
     if (p.tokens > kAttnSingleBlockMaxTokens) {
         // key-blocked: single-pass streaming kernel unless the exact softmax is asked for (or after a range flag)
-        if (!exact && attn_impl() == 3)
+        if (!exact)
             return h ? launch_attention_stream_blocked_t<__half>(tqkv, tout32, p, sm_count, st)
                      : launch_attention_stream_blocked_t<__nv_bfloat16>(tqkv, tout32, p, sm_count, st);
         return h ? launch_attention_blocked_t<__half>(tqkv, tout, p, sm_count, st) : launch_attention_blocked_t<__nv_bfloat16>(tqkv, tout, p, sm_count, st);
     }
-    if (attn_impl() == 3) {
-        if (exact) return h ? launch_attention_stream_t<__half, true>(tqkv, tout32, p, sm_count, st)
-                            : launch_attention_stream_t<__nv_bfloat16, true>(tqkv, tout32, p, sm_count, st);
-        return h ? launch_attention_stream_t<__half, false>(tqkv, tout32, p, sm_count, st)
-                 : launch_attention_stream_t<__nv_bfloat16, false>(tqkv, tout32, p, sm_count, st);
-    }
-    if (exact) return h ? launch_attention_t<__half, true>(tqkv, tout, p, sm_count, st) : launch_attention_t<__nv_bfloat16, true>(tqkv, tout, p, sm_count, st);
-    return h ? launch_attention_t<__half, false>(tqkv, tout, p, sm_count, st) : launch_attention_t<__nv_bfloat16, false>(tqkv, tout, p, sm_count, st);
+    if (exact) return h ? launch_attention_stream_t<__half, true>(tqkv, tout32, p, sm_count, st)
+                        : launch_attention_stream_t<__nv_bfloat16, true>(tqkv, tout32, p, sm_count, st);
+    return h ? launch_attention_stream_t<__half, false>(tqkv, tout32, p, sm_count, st)
+             : launch_attention_stream_t<__nv_bfloat16, false>(tqkv, tout32, p, sm_count, st);
 }
-// Reads and clears the current device's range flag (after the stream has been synchronised).
-int take_attn_range_flag(bool* was_set) {
+
+// Reads and clears the current device's status word (synchronous; operator tests and init).
+int take_status_flags(unsigned int* flags) {
     unsigned int v = 0;
-    CU_TRY(cudaMemcpyFromSymbol(&v, g_attn_range_flag, sizeof(v)));
-    *was_set = v != 0;
+    CU_TRY(cudaMemcpyFromSymbol(&v, g_status_flags, sizeof(v)));
+    *flags = v;
     if (v) {
         v = 0;
-        CU_TRY(cudaMemcpyToSymbol(g_attn_range_flag, &v, sizeof(v)));
+        CU_TRY(cudaMemcpyToSymbol(g_status_flags, &v, sizeof(v)));
     }
     return 0;
 }
@@ -427,18 +347,14 @@ int launch_fold_ln(int prec, const float* W, const float* ln_w, const float* ln_
     return check_launch("fold_ln_weights");
 }
 
-template <typename T>
-void launch_patchify_t(const float* img, T* patches, int batch, int S, cudaStream_t st) {
-    const dim3 grid((S * (S / 4) + 511) / 512, 3 * batch);
-    if (S == 224) patchify_kernel<T, 224><<<grid, 256, 0, st>>>(img, patches, batch, S);
-    else if (S == 384) patchify_kernel<T, 384><<<grid, 256, 0, st>>>(img, patches, batch, S);
-    else patchify_kernel<T, 0><<<grid, 256, 0, st>>>(img, patches, batch, S);
-}
-int launch_patchify(int prec, const float* img, void* patches, int batch, int S, int sm_count, cudaStream_t st) {
-    (void)sm_count;
-    if (prec == VIT_PREC_FP16) launch_patchify_t(img, static_cast<__half*>(patches), batch, S, st);
-    else launch_patchify_t(img, static_cast<__nv_bfloat16*>(patches), batch, S, st);
-    return check_launch("patchify");
+int launch_cls_rows(int prec, bool ln, float* x, void* xn, float2* pstats, int stats_rows, const float* cls, const float* pos, int nb,
+                    int tokens, cudaStream_t st) {
+    if (!ln) cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(x, cls, pos, nb, tokens);
+    else if (prec == VIT_PREC_FP16)
+        cls_rows_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(x, static_cast<__half*>(xn), pstats, stats_rows, cls, pos, nb, tokens);
+    else
+        cls_rows_ln_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(xn), pstats, stats_rows, cls, pos, nb, tokens);
+    return check_launch("cls_rows");
 }
 
 int launch_convert_from_f32(int prec, const float* src, void* dst, size_t n, cudaStream_t st) {
@@ -452,6 +368,10 @@ int launch_convert_to_f32(int prec, const void* src, float* dst, size_t n, cudaS
     if (prec == VIT_PREC_FP16) convert_to_f32_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
     else convert_to_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst, n);
     return check_launch("convert");
+}
+int launch_round_tf32(const float* src, float* dst, size_t n, cudaStream_t st) {
+    round_tf32_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16)), 256, 0, st>>>(src, dst, n);
+    return check_launch("round_tf32");
 }
 
 // ------------------------------------------------------------------------------------ device check
@@ -483,14 +403,29 @@ struct timerEvents_t {
     cudaEvent_t start = nullptr, stop = nullptr;
 };
 
-struct LayerW {
-    float *ln1_w, *ln1_b, *qkv_b, *out_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;  // fp32
-    void *qkv_w, *out_w, *fc1_w, *fc2_w;                                    // operand precision
-    CUtensorMap tm_qkv_w, tm_out_w, tm_fc1_w, tm_fc2_w;
-    // LayerNorm folded into in_proj / mlp_0: W' = ln_w (.) W, column sums of W', c = bias + W ln_b
+// One operand precision's GEMM weights of an encoder layer
+struct OperandW {
+    void *qkv_w = nullptr, *out_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;
+    // LayerNorm folded into in_proj / mlp_0: W' = ln_w (.) W (rounded), column sums of the rounded W'
     void *qkv_wf = nullptr, *fc1_wf = nullptr;
-    float *qkv_s = nullptr, *qkv_c = nullptr, *fc1_s = nullptr, *fc1_c = nullptr;
-    CUtensorMap tm_qkv_wf, tm_fc1_wf;
+    float *qkv_s = nullptr, *fc1_s = nullptr;
+    CUtensorMap tm_qkv_w, tm_out_w, tm_fc1_w, tm_fc2_w, tm_qkv_wf, tm_fc1_wf;
+};
+struct LayerW {
+    float *ln1_w, *ln1_b, *qkv_b, *out_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;  // fp32, verbatim
+    float *qkv_c, *fc1_c;                                                   // c = bias + W ln_b (fp32, from the unrounded W)
+    OperandW op[2];                                                         // [VIT_PREC_BF16], [VIT_PREC_FP16]
+};
+
+// Bump allocator over the weight arena.  A dry run (base == nullptr) only adds up the size.
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t off = 0;
+    template <typename P>
+    void take(P** p, size_t bytes) {
+        *p = reinterpret_cast<P*>(base + off);
+        off += (bytes + 255) & ~static_cast<size_t>(255);
+    }
 };
 
 struct DeviceCtx {
@@ -499,15 +434,17 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::vector<void*> allocs;
-    // weights
+    // ---- weights: ONE device allocation (the arena), laid out by layout_weights(); this is what the cache file holds
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
     float *cls = nullptr, *conv_b = nullptr, *pos = nullptr, *lnf_w = nullptr, *lnf_b = nullptr, *head_w = nullptr,
           *head_b = nullptr;
-    void* conv_w = nullptr;
-    CUtensorMap tm_conv_w;
+    float* conv_w = nullptr;   // fp32 rounded to tf32 (conv_proj runs as kind::tf32 on the raw image)
+    CUtensorMap tm_conv_w, tm_pos;
     LayerW layer[kDepth];
-    // workspace (capacity = max_batch images)
+    // ---- workspace (capacity = max_batch images)
     float* images[2] = {nullptr, nullptr};
-    void *patches = nullptr, *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr;
+    void *xn = nullptr, *qkv = nullptr, *ao = nullptr, *hid = nullptr;
     float *x = nullptr, *cls_ln = nullptr, *logits = nullptr;
     float* h_stage[2] = {nullptr, nullptr};  // pinned staging for scattered host images (vit_cuda_forward_scattered), lazily allocated
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};   // the H2D copy out of h_stage[i] has completed
@@ -519,23 +456,36 @@ struct DeviceCtx {
     float* x_c = nullptr;
     float2* pstats_c = nullptr;
     size_t stats_rows_c = 0;
-    CUtensorMap tm_ao_c, tm_x_c, tm_xn_c, tm_hid_c, tm_hid_c32;
     float2* pstats = nullptr;  // [6][max rows] partial (sum, sum of squares) of the residual rows (LN folding)
     size_t stats_rows = 0;
-    // activation tensor maps, rebuilt when the pass size changes: row extent = rows actually in
-    // use, so TMA zero-fills loads and clips stores past the last image
-    int maps_nb = -1;
-    CUtensorMap tm_patches3, tm_x3, tm_xn3 /* per-image 3-D views for conv_proj */, tm_pos, tm_patches, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_hid32, tm_qkv_st32 /* 32-row store boxes */, tm_x, tm_q /* attention loads */, tm_kv /* attention store */, tm_kv32 /* attention store, 32-row boxes */;
+    // activation tensor maps, rebuilt when the pass size or the operand precision changes: row extent = rows
+    // actually in use, so TMA zero-fills loads and clips stores past the last image
+    int maps_nb = -1, maps_prec = -1;
+    CUtensorMap tm_ao_c, tm_x_c, tm_xn_c, tm_hid_c, tm_hid_c32;
+    CUtensorMap tm_x3, tm_xn3 /* per-image 3-D views for conv_proj */, tm_xn, tm_ao, tm_hid, tm_qkv_st, tm_hid32, tm_qkv_st32 /* 32-row store boxes */, tm_x, tm_q /* attention loads */, tm_kv /* attention store */, tm_kv32 /* attention store, 32-row boxes */;
+    // 5-D views of the image buffers conv_proj has been asked to read (small cache: the two engine buffers, a caller's own)
+    struct ImgMap {
+        const float* ptr = nullptr;
+        int nb = 0;
+        CUtensorMap map;
+    };
+    ImgMap img_maps[4];
+    int img_map_next = 0;
     size_t ws_bytes = 0;
+    // device status word (g_status_flags of this device) and its pinned host mirror, read back after a pass
+    unsigned int* d_flags = nullptr;
+    unsigned int* h_flags = nullptr;
+    bool pending_fast_softmax = false, pending_fp16 = false;   // work enqueued since the flags were last read
+    char err[512] = "";   // failure text of this slot's feeding thread
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
     size_t prof_used[VIT_PROF_NCAT] = {};
     timerEvents_t timer;
     struct Graph {   // captured launch sequence of one small pass
-        int nb = 0;
+        int nb = 0, prec = 0;
         const float* images = nullptr;
         float* logits = nullptr;
-        bool attn_exact = false, ln_fused = true, prune_last = true;
+        bool attn_exact = false, ln_fused = true, prune_last = true, pdl = true;
         long long launches = 0;
         cudaGraphExec_t exec = nullptr;
     };
@@ -545,11 +495,12 @@ struct DeviceCtx {
 struct Engine {
     bool up = false;
     bool profiling = false;
-    bool prune_last = true;       // last layer: everything behind the attention for the class rows only (VIT_PRUNE_LAST=0: all rows)
-    bool ln_fused = true;         // LayerNorm folded into the GEMMs (VIT_LN_FUSED=0: separate LayerNorm kernels)
-    bool attn_exact = false;      // two-pass softmax (VIT_ATTN_EXACT=1, vit_cuda_set_attention_exact, or after a range flag)
-    long long attn_fallbacks = 0; // forwards repeated with the exact softmax
-    int img = 0, grid = 0, patches = 0, tokens = 0, max_batch = 0, prec = 0;
+    long long attn_fallbacks = 0;   // forwards repeated with the exact softmax
+    long long prec_fallbacks = 0;   // forwards repeated with BF16 operands (VIT_PREC_AUTO)
+    int img = 0, grid = 0, patches = 0, tokens = 0, max_batch = 0;
+    int policy = VIT_PREC_AUTO;     // what the caller asked for
+    int prec = VIT_PREC_FP16;       // operand precision of the next pass (VIT_PREC_BF16 / VIT_PREC_FP16)
+    bool resident[2] = {false, false};   // which operand sets the arena holds
     std::vector<DeviceCtx> ctx;
 };
 Engine g_eng;
@@ -562,43 +513,99 @@ int dev_alloc(DeviceCtx& c, void** p, size_t bytes, bool zero) {
     return 0;
 }
 
-int upload_f32(DeviceCtx& c, float** dst, const vit_tensor& t) {
-    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(dst), t.size * sizeof(float), false));
-    CU_TRY(cudaMemcpyAsync(*dst, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+size_t tensor_numel(int idx, int img) {
+    const size_t g = img / kPatch, tokens = g * g + 1;
+    switch (idx) {
+        case 0: case 2: case 148: case 149: return kDim;
+        case 1: return static_cast<size_t>(kDim) * 3 * kPatch * kPatch;
+        case 3: return tokens * kDim;
+        case 150: return static_cast<size_t>(kClasses) * kDim;
+        case 151: return kClasses;
+    }
+    switch ((idx - 4) % 12) {
+        case 2: return static_cast<size_t>(3) * kDim * kDim;
+        case 3: return 3 * kDim;
+        case 4: return static_cast<size_t>(kDim) * kDim;
+        case 8: case 10: return static_cast<size_t>(kHidden) * kDim;
+        case 9: return kHidden;
+        default: return kDim;
+    }
+}
+
+// Assigns every weight pointer of the context inside the arena, in a fixed order that depends only on
+// (image size, resident precisions) -- the cache file is the arena's bytes.
+void layout_weights(DeviceCtx& c, Arena& a, const Engine& e) {
+    const size_t f = sizeof(float);
+    a.take(&c.cls, kDim * f);
+    a.take(&c.conv_w, static_cast<size_t>(kDim) * kDim * f);
+    a.take(&c.conv_b, kDim * f);
+    a.take(&c.pos, static_cast<size_t>(e.tokens) * kDim * f);
+    for (int l = 0; l < kDepth; ++l) {
+        LayerW& L = c.layer[l];
+        a.take(&L.ln1_w, kDim * f);
+        a.take(&L.ln1_b, kDim * f);
+        a.take(&L.qkv_b, 3 * kDim * f);
+        a.take(&L.out_b, kDim * f);
+        a.take(&L.ln2_w, kDim * f);
+        a.take(&L.ln2_b, kDim * f);
+        a.take(&L.fc1_b, kHidden * f);
+        a.take(&L.fc2_b, kDim * f);
+        a.take(&L.qkv_c, 3 * kDim * f);
+        a.take(&L.fc1_c, kHidden * f);
+        for (int pr = 0; pr < 2; ++pr) {
+            if (!e.resident[pr]) continue;
+            OperandW& o = L.op[pr];
+            a.take(&o.qkv_w, static_cast<size_t>(3) * kDim * kDim * 2);
+            a.take(&o.out_w, static_cast<size_t>(kDim) * kDim * 2);
+            a.take(&o.fc1_w, static_cast<size_t>(kHidden) * kDim * 2);
+            a.take(&o.fc2_w, static_cast<size_t>(kHidden) * kDim * 2);
+            a.take(&o.qkv_wf, static_cast<size_t>(3) * kDim * kDim * 2);
+            a.take(&o.fc1_wf, static_cast<size_t>(kHidden) * kDim * 2);
+            a.take(&o.qkv_s, 3 * kDim * f);
+            a.take(&o.fc1_s, kHidden * f);
+        }
+    }
+    a.take(&c.lnf_w, kDim * f);
+    a.take(&c.lnf_b, kDim * f);
+    a.take(&c.head_w, static_cast<size_t>(kClasses) * kDim * f);
+    a.take(&c.head_b, kClasses * f);
+}
+
+int make_weight_maps(DeviceCtx& c, const Engine& e) {
+    for (int l = 0; l < kDepth; ++l)
+        for (int pr = 0; pr < 2; ++pr) {
+            if (!e.resident[pr]) continue;
+            OperandW& o = c.layer[l].op[pr];
+            VIT_TRY(make_tmap(&o.tm_qkv_w, pr, o.qkv_w, kDim, 3 * kDim, GEMM_BK, 128));
+            VIT_TRY(make_tmap(&o.tm_out_w, pr, o.out_w, kDim, kDim, GEMM_BK, 128));
+            VIT_TRY(make_tmap(&o.tm_fc1_w, pr, o.fc1_w, kDim, kHidden, GEMM_BK, 128));
+            VIT_TRY(make_tmap(&o.tm_fc2_w, pr, o.fc2_w, kHidden, kDim, GEMM_BK, 128));
+            VIT_TRY(make_tmap(&o.tm_qkv_wf, pr, o.qkv_wf, kDim, 3 * kDim, GEMM_BK, 128));
+            VIT_TRY(make_tmap(&o.tm_fc1_wf, pr, o.fc1_wf, kDim, kHidden, GEMM_BK, 128));
+        }
+    VIT_TRY(make_tmap_f32(&c.tm_conv_w, c.conv_w, kDim, kDim, 128));
+    VIT_TRY(make_tmap_f32(&c.tm_pos, c.pos, kDim, e.tokens, GEMM_BM));
     return 0;
-}
-
-int upload_operand(DeviceCtx& c, void** dst, const vit_tensor& t, float* scratch, int prec) {
-    VIT_TRY(dev_alloc(c, dst, t.size * 2, false));
-    CU_TRY(cudaMemcpyAsync(scratch, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-    return launch_convert_from_f32(prec, scratch, *dst, t.size, c.stream);
-}
-
-// Folded copy of a [N][768] weight whose fp32 values are still in `scratch` (just uploaded by
-// upload_operand): W' = ln_w (.) W in the operand precision, its column sums and c = bias + W ln_b.
-int upload_folded(DeviceCtx& c, void** wf, float** colsum, float** cvec, const float* scratch, const float* ln_w,
-                  const float* ln_b, const float* bias, int N, int prec) {
-    VIT_TRY(dev_alloc(c, wf, static_cast<size_t>(N) * kDim * 2, false));
-    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(colsum), static_cast<size_t>(N) * 4, false));
-    VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(cvec), static_cast<size_t>(N) * 4, false));
-    return launch_fold_ln(prec, scratch, ln_w, ln_b, bias, *wf, *colsum, *cvec, N, c.stream);
 }
 
 void destroy_ctx(DeviceCtx& c) {
     if (c.device < 0) return;
     cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
+    if (c.copy_stream) cudaStreamSynchronize(c.copy_stream);
     for (int i = 0; i < 2; ++i) {
         if (c.h_stage[i]) cudaFreeHost(c.h_stage[i]);
         if (c.ev_stage[i]) cudaEventDestroy(c.ev_stage[i]);
         if (c.h_logits[i]) cudaFreeHost(c.h_logits[i]);
         if (c.ev_logits[i]) cudaEventDestroy(c.ev_logits[i]);
     }
+    if (c.h_flags) cudaFreeHost(c.h_flags);
     for (auto& g : c.graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     c.graphs.clear();
     for (void* p : c.allocs) cudaFree(p);
     c.allocs.clear();
+    if (c.arena) cudaFree(c.arena);
     for (int i = 0; i < 2; ++i) {
         if (c.ev_h2d[i]) cudaEventDestroy(c.ev_h2d[i]);
         if (c.ev_done[i]) cudaEventDestroy(c.ev_done[i]);
@@ -615,7 +622,8 @@ void destroy_ctx(DeviceCtx& c) {
     c = DeviceCtx();
 }
 
-int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
+// Streams, events, status word and the (empty) weight arena of one slot.
+int open_ctx(DeviceCtx& c, int device, const Engine& e) {
     c.device = device;
     VIT_TRY(check_device(device, &c.sm_count));
     CU_TRY(cudaSetDevice(device));
@@ -625,58 +633,85 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
         CU_TRY(cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
     }
-    const int prec = e.prec;
-    // ---- weights: fp32 small tensors verbatim, GEMM operands converted once
+    CU_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&c.d_flags), g_status_flags));
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_flags), sizeof(unsigned int), cudaHostAllocPortable));
+    *c.h_flags = 0;
+    CU_TRY(cudaMemsetAsync(c.d_flags, 0, sizeof(unsigned int), c.stream));
+    Arena dry;
+    layout_weights(c, dry, e);
+    c.arena_bytes = dry.off;
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c.arena), c.arena_bytes));
+    Arena a;
+    a.base = c.arena;
+    layout_weights(c, a, e);
+    return 0;
+}
+
+// Fills the arena from the 152 fp32 host tensors: small tensors verbatim, GEMM operands converted once per resident
+// precision, in_proj / mlp_0 additionally folded with their LayerNorm, conv_proj.weight rounded to tf32.
+int fill_arena_from_tensors(DeviceCtx& c, const vit_tensor* w, const Engine& e) {
+    cudaStream_t st = c.stream;
     float* scratch = nullptr;
     CU_TRY(cudaMalloc(&scratch, static_cast<size_t>(kHidden) * kDim * sizeof(float)));
+    auto put_f32 = [&](float* dst, const vit_tensor& t) -> int {
+        CU_TRY(cudaMemcpyAsync(dst, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    // fp32 tensor -> scratch, then one conversion per resident precision; `fold`: also W' = ln_w (.) W etc.
+    auto put_operand = [&](const vit_tensor& t, void* OperandW::*plain, LayerW& L, void* OperandW::*folded, float* OperandW::*colsum,
+                           const float* ln_w, const float* ln_b, const float* bias, float* cvec, int N) -> int {
+        CU_TRY(cudaMemcpyAsync(scratch, t.data, t.size * sizeof(float), cudaMemcpyHostToDevice, st));
+        for (int pr = 0; pr < 2; ++pr) {
+            if (!e.resident[pr]) continue;
+            OperandW& o = L.op[pr];
+            VIT_TRY(launch_convert_from_f32(pr, scratch, o.*plain, t.size, st));
+            if (folded) VIT_TRY(launch_fold_ln(pr, scratch, ln_w, ln_b, bias, o.*folded, o.*colsum, cvec, N, st));
+        }
+        return 0;
+    };
     int rc = 0;
     do {
-        if ((rc = upload_f32(c, &c.cls, w[0]))) break;
-        if ((rc = upload_operand(c, &c.conv_w, w[1], scratch, prec))) break;
-        if ((rc = upload_f32(c, &c.conv_b, w[2]))) break;
-        if ((rc = upload_f32(c, &c.pos, w[3]))) break;
+        if ((rc = put_f32(c.cls, w[0]))) break;
+        CU_TRY(cudaMemcpyAsync(scratch, w[1].data, w[1].size * sizeof(float), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_round_tf32(scratch, c.conv_w, w[1].size, st))) break;
+        if ((rc = put_f32(c.conv_b, w[2]))) break;
+        if ((rc = put_f32(c.pos, w[3]))) break;
         for (int l = 0; l < kDepth && !rc; ++l) {
             const vit_tensor* lw = w + 4 + 12 * l;
             LayerW& L = c.layer[l];
-            if ((rc = upload_f32(c, &L.ln1_w, lw[0]))) break;
-            if ((rc = upload_f32(c, &L.ln1_b, lw[1]))) break;
-            if ((rc = upload_operand(c, &L.qkv_w, lw[2], scratch, prec))) break;
-            if ((rc = upload_f32(c, &L.qkv_b, lw[3]))) break;
-            if ((rc = upload_folded(c, &L.qkv_wf, &L.qkv_s, &L.qkv_c, scratch, L.ln1_w, L.ln1_b, L.qkv_b, 3 * kDim, prec))) break;
-            if ((rc = upload_operand(c, &L.out_w, lw[4], scratch, prec))) break;
-            if ((rc = upload_f32(c, &L.out_b, lw[5]))) break;
-            if ((rc = upload_f32(c, &L.ln2_w, lw[6]))) break;
-            if ((rc = upload_f32(c, &L.ln2_b, lw[7]))) break;
-            if ((rc = upload_operand(c, &L.fc1_w, lw[8], scratch, prec))) break;
-            if ((rc = upload_f32(c, &L.fc1_b, lw[9]))) break;
-            if ((rc = upload_folded(c, &L.fc1_wf, &L.fc1_s, &L.fc1_c, scratch, L.ln2_w, L.ln2_b, L.fc1_b, kHidden, prec))) break;
-            if ((rc = upload_operand(c, &L.fc2_w, lw[10], scratch, prec))) break;
-            if ((rc = upload_f32(c, &L.fc2_b, lw[11]))) break;
-            if ((rc = make_tmap(&L.tm_qkv_w, prec, L.qkv_w, kDim, 3 * kDim, GEMM_BK, 128))) break;
-            if ((rc = make_tmap(&L.tm_out_w, prec, L.out_w, kDim, kDim, GEMM_BK, 128))) break;
-            if ((rc = make_tmap(&L.tm_fc1_w, prec, L.fc1_w, kDim, kHidden, GEMM_BK, 128))) break;
-            if ((rc = make_tmap(&L.tm_fc2_w, prec, L.fc2_w, kHidden, kDim, GEMM_BK, 128))) break;
-            if ((rc = make_tmap(&L.tm_qkv_wf, prec, L.qkv_wf, kDim, 3 * kDim, GEMM_BK, 128))) break;
-            if ((rc = make_tmap(&L.tm_fc1_wf, prec, L.fc1_wf, kDim, kHidden, GEMM_BK, 128))) break;
+            if ((rc = put_f32(L.ln1_w, lw[0]))) break;
+            if ((rc = put_f32(L.ln1_b, lw[1]))) break;
+            if ((rc = put_f32(L.qkv_b, lw[3]))) break;
+            if ((rc = put_f32(L.out_b, lw[5]))) break;
+            if ((rc = put_f32(L.ln2_w, lw[6]))) break;
+            if ((rc = put_f32(L.ln2_b, lw[7]))) break;
+            if ((rc = put_f32(L.fc1_b, lw[9]))) break;
+            if ((rc = put_f32(L.fc2_b, lw[11]))) break;
+            if ((rc = put_operand(lw[2], &OperandW::qkv_w, L, &OperandW::qkv_wf, &OperandW::qkv_s, L.ln1_w, L.ln1_b, L.qkv_b, L.qkv_c, 3 * kDim))) break;
+            if ((rc = put_operand(lw[4], &OperandW::out_w, L, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0))) break;
+            if ((rc = put_operand(lw[8], &OperandW::fc1_w, L, &OperandW::fc1_wf, &OperandW::fc1_s, L.ln2_w, L.ln2_b, L.fc1_b, L.fc1_c, kHidden))) break;
+            if ((rc = put_operand(lw[10], &OperandW::fc2_w, L, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0))) break;
         }
         if (rc) break;
-        if ((rc = upload_f32(c, &c.lnf_w, w[148]))) break;
-        if ((rc = upload_f32(c, &c.lnf_b, w[149]))) break;
-        if ((rc = upload_f32(c, &c.head_w, w[150]))) break;
-        if ((rc = upload_f32(c, &c.head_b, w[151]))) break;
-        if ((rc = make_tmap(&c.tm_conv_w, prec, c.conv_w, kDim, kDim, GEMM_BK, 128))) break;
+        if ((rc = put_f32(c.lnf_w, w[148]))) break;
+        if ((rc = put_f32(c.lnf_b, w[149]))) break;
+        if ((rc = put_f32(c.head_w, w[150]))) break;
+        if ((rc = put_f32(c.head_b, w[151]))) break;
     } while (0);
-    cudaError_t se = cudaStreamSynchronize(c.stream);
+    const cudaError_t se = cudaStreamSynchronize(st);
     cudaFree(scratch);
     if (rc) return rc;
     if (se != cudaSuccess) return watchdog_or_cuda_error(se, "weight upload");
+    return 0;
+}
 
-    // ---- workspaces.  Zero-filled once: attention may read (and multiply by P == 0) rows
-    // past the last image of a pass, which must therefore always hold finite values.
-    const size_t B = e.max_batch, rows = B * e.tokens, prow = B * e.patches;
+// Workspaces.  Zero-filled once: attention may read (and multiply by P == 0) rows past the last image of a
+// pass, which must therefore always hold finite values.
+int alloc_workspace(DeviceCtx& c, const Engine& e) {
+    CU_TRY(cudaSetDevice(c.device));
+    const size_t B = e.max_batch, rows = B * e.tokens;
     const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
     for (int i = 0; i < 2; ++i) VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.images[i]), B * img_elems * 4, false));
-    VIT_TRY(dev_alloc(c, &c.patches, prow * kDim * 2, true));
     VIT_TRY(dev_alloc(c, reinterpret_cast<void**>(&c.x), rows * kDim * 4, true));
     VIT_TRY(dev_alloc(c, &c.xn, rows * kDim * 2, true));
     VIT_TRY(dev_alloc(c, &c.qkv, rows * 3 * kDim * 2, true));
@@ -696,19 +731,16 @@ int init_ctx(DeviceCtx& c, int device, const vit_tensor* w, const Engine& e) {
     return 0;
 }
 
-int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
-    if (c.maps_nb == nb) return 0;
-    const int prec = e.prec;
-    const uint64_t rows = static_cast<uint64_t>(nb) * e.tokens, prow = static_cast<uint64_t>(nb) * e.patches;
-    VIT_TRY(make_tmap(&c.tm_patches, prec, c.patches, kDim, prow, GEMM_BK, GEMM_BM));
+int ensure_maps(DeviceCtx& c, const Engine& e, int nb, int prec) {
+    if (c.maps_nb == nb && c.maps_prec == prec) return 0;
+    const uint64_t rows = static_cast<uint64_t>(nb) * e.tokens;
+    const uint32_t erows = embed_rows_per_cta(e.img);
     VIT_TRY(make_tmap(&c.tm_xn, prec, c.xn, kDim, rows, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&c.tm_ao, prec, c.ao, kDim, rows, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap(&c.tm_hid, prec, c.hid, kHidden, rows, GEMM_BK, GEMM_BM));     // mlp_0 store + mlp_3 A load
     VIT_TRY(make_tmap(&c.tm_qkv_st, prec, c.qkv, 3 * kDim, rows, GEMM_BK, GEMM_BM)); // in_proj store
-    VIT_TRY(make_tmap_3d(&c.tm_patches3, prec, c.patches, kDim, e.patches, nb, GEMM_BM));
-    VIT_TRY(make_tmap_3d_f32(&c.tm_x3, c.x, kDim, e.tokens, nb, GEMM_BM));
-    VIT_TRY(make_tmap_3d(&c.tm_xn3, prec, c.xn, kDim, e.tokens, nb, GEMM_BM));
-    VIT_TRY(make_tmap_f32(&c.tm_pos, c.pos, kDim, e.tokens, GEMM_BM));
+    VIT_TRY(make_tmap_3d_f32(&c.tm_x3, c.x, kDim, e.tokens, nb, erows));
+    VIT_TRY(make_tmap_3d(&c.tm_xn3, prec, c.xn, kDim, e.tokens, nb, erows));
     VIT_TRY(make_tmap(&c.tm_ao_c, prec, c.ao_c, kDim, nb, GEMM_BK, GEMM_BM));
     VIT_TRY(make_tmap_f32(&c.tm_x_c, c.x_c, kDim, nb, GEMM_BM));
     VIT_TRY(make_tmap(&c.tm_xn_c, prec, c.xn_c, kDim, nb, GEMM_BK, GEMM_BM));
@@ -721,6 +753,23 @@ int ensure_maps(DeviceCtx& c, const Engine& e, int nb) {
     VIT_TRY(make_tmap_3d(&c.tm_kv, prec, c.ao, kDim, e.tokens, nb, 128));                                   // per-image output tiles
     VIT_TRY(make_tmap_3d(&c.tm_kv32, prec, c.ao, kDim, e.tokens, nb, 32));
     c.maps_nb = nb;
+    c.maps_prec = prec;
+    return 0;
+}
+
+int image_map(DeviceCtx& c, const Engine& e, const float* d_images, int nb, const CUtensorMap** out) {
+    for (auto& m : c.img_maps)
+        if (m.ptr == d_images && m.nb == nb) {
+            *out = &m.map;
+            return 0;
+        }
+    if (reinterpret_cast<uintptr_t>(d_images) & 15) return set_err(VIT_E_ARG, "device images must be 16-byte aligned");
+    DeviceCtx::ImgMap& m = c.img_maps[c.img_map_next];
+    c.img_map_next = (c.img_map_next + 1) % 4;
+    VIT_TRY(make_tmap_image5d(&m.map, d_images, e.img, nb));
+    m.ptr = d_images;
+    m.nb = nb;
+    *out = &m.map;
     return 0;
 }
 
@@ -747,69 +796,64 @@ struct ProfScope {
     }
 };
 
+// The switches a pass is enqueued with (snapshotted once per host call, so that a pass is self-consistent)
+struct PassMode {
+    int prec;
+    bool attn_exact, ln_fused, prune_last, pdl;
+};
+PassMode current_mode(const Engine& e) {
+    return PassMode{e.prec, g_opt.attn_exact.load() != 0, g_opt.ln_fused.load() != 0, g_opt.prune_last.load() != 0, g_opt.pdl.load() != 0};
+}
+
 // Enqueue the whole forward for nb images already resident in d_images (fp32 NCHW) on c.stream.
-int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
+int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, const float* d_images, int nb, float* d_logits) {
     cudaStream_t st = c.stream;
-    const int prec = e.prec;
+    const int prec = m.prec;
     const int rows = nb * e.tokens;
-    VIT_TRY(ensure_maps(c, e, nb));
-    const bool staged = gemm_impl() == 2;
-    // conv_proj: patch rows -> GEMM with (+bias, +pos_embedding, row remap) epilogue; class rows aside
+    VIT_TRY(ensure_maps(c, e, nb, prec));
+    const CUtensorMap* tm_img = nullptr;
+    VIT_TRY(image_map(c, e, d_images, nb, &tm_img));
     const bool pf = e.profiling;
     // LayerNorm folded into the GEMMs (default): in_proj / mlp_0 read the operand-precision copy of the raw
     // residual rows (c.xn) with the per-row statistics (c.pstats) that the previous residual GEMM -- for
     // layer 0 conv_proj and the class-row kernel -- left behind.  Otherwise: a LayerNorm kernel before each.
-    const bool fused = staged && e.ln_fused;
+    const bool fused = m.ln_fused;
     const int stats_rows = static_cast<int>(c.stats_rows);
-    {
+    {   // class-token rows (class_token + pos_emb, ViT_seq.c:72-101)
         ProfScope ps(c, pf, VIT_PROF_PATCHIFY);
-        VIT_TRY(launch_patchify(prec, d_images, c.patches, nb, e.img, c.sm_count, st));
-        if (fused) {
-            if (prec == VIT_PREC_FP16)
-                cls_rows_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(c.x, static_cast<__half*>(c.xn), c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens);
-            else
-                cls_rows_ln_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, st>>>(c.x, static_cast<__nv_bfloat16*>(c.xn), c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens);
-        } else {
-            cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(c.x, c.cls, c.pos, nb, e.tokens);
-        }
-        VIT_TRY(check_launch("cls_rows"));
+        VIT_TRY(launch_cls_rows(prec, fused, c.x, c.xn, c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens, st));
     }
-    {
+    {   // conv_proj: tf32 GEMM straight from the fp32 image; class_token offset / pos_emb / token layout are TMA addressing
         ProfScope ps(c, pf, VIT_PROF_EMBED_GEMM);
-        if (staged) {   // one CTA pair per image; class_token / pos_emb / token layout are pure TMA addressing
-            GemmParams p{nb * ((e.patches + 255) / 256) * 256, kDim, kDim, c.conv_b, c.x, nullptr, e.patches, e.tokens};
-            if (fused) {
-                p.stats_out = c.pstats;
-                p.stats_rows = stats_rows;
-            }
-            VIT_TRY(launch_gemm_embed(prec, fused, c.tm_patches3, c.tm_conv_w, c.tm_x3, c.tm_xn3, c.tm_pos, p, c.sm_count, st));
-        } else {
-            GemmParams p{nb * e.patches, kDim, kDim, c.conv_b, c.x, c.pos, e.patches, e.tokens};
-            VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(prec, c.tm_patches, c.tm_conv_w, p, c.sm_count, st));
+        GemmParams p{nb * embed_tiles_per_image(e.img) * 256, kDim, kDim, c.conv_b, c.x, nullptr, e.patches, e.tokens, e.grid};
+        if (fused) {
+            p.stats_out = c.pstats;
+            p.stats_rows = stats_rows;
         }
+        VIT_TRY(launch_gemm_embed(prec, fused, *tm_img, c.tm_conv_w, c.tm_x3, c.tm_xn3, c.tm_pos, p, c.sm_count, st));
     }
-    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
+    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, nullptr};
     bool pruned_tail = false;
     for (int l = 0; l < kDepth; ++l) {
         const LayerW& L = c.layer[l];
+        const OperandW& W = L.op[prec];
         if (!fused) {
             ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
             VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
-            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 2 * kDim};  // V block stored as bf16
+            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 0, 2 * kDim};  // V block stored as bf16
             if (fused) {
                 p.bias = L.qkv_c;
-                p.colsum = L.qkv_s;
+                p.colsum = W.qkv_s;
                 p.stats_in = c.pstats;
                 p.stats_parts = 6;
                 p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
-            else VIT_TRY(launch_gemm<EPI_BIAS>(prec, c.tm_xn, L.tm_qkv_w, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, W.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
+            } else VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, W.tm_qkv_w, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
         }
-        if (l == kDepth - 1 && fused && e.prune_last) {
+        if (l == kDepth - 1 && fused && m.prune_last) {
             // Last layer: only the class token reaches the head, and no token reads another one after the attention.
             // Attention for the class query alone (all keys and values), then out_proj / LayerNorm / MLP on the compact
             // [nb][768] class rows: 1/197 of the rows of the other layers.
@@ -824,41 +868,40 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
             const int srows_c = static_cast<int>(c.stats_rows_c);
             {
                 ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
-                GemmParams p{nb, kDim, kDim, L.out_b, c.x_c, c.x_c, 0, 0};
+                GemmParams p{nb, kDim, kDim, L.out_b, c.x_c, c.x_c};
                 p.stats_out = c.pstats_c;
                 p.stats_rows = srows_c;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao_c, L.tm_out_w, c.tm_x_c, c.tm_xn_c, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao_c, W.tm_out_w, c.tm_x_c, c.tm_xn_c, p, c.sm_count, st));
             }
             {
                 ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
-                GemmParams p{nb, kHidden, kDim, L.fc1_c, c.hid_c, nullptr, 0, 0};
-                p.colsum = L.fc1_s;
+                GemmParams p{nb, kHidden, kDim, L.fc1_c, c.hid_c, nullptr};
+                p.colsum = W.fc1_s;
                 p.stats_in = c.pstats_c;
                 p.stats_parts = 6;
                 p.stats_rows = srows_c;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn_c, L.tm_fc1_wf, c.tm_hid_c, c.tm_hid_c32, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn_c, W.tm_fc1_wf, c.tm_hid_c, c.tm_hid_c32, p, c.sm_count, st));
             }
             {
                 ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
-                GemmParams p{nb, kDim, kHidden, L.fc2_b, c.x_c, c.x_c, 0, 0};
-                VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid_c, L.tm_fc2_w, c.tm_x_c, c.tm_x_c, p, c.sm_count, st));
+                GemmParams p{nb, kDim, kHidden, L.fc2_b, c.x_c, c.x_c};
+                VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid_c, W.tm_fc2_w, c.tm_x_c, c.tm_x_c, p, c.sm_count, st));
             }
             pruned_tail = true;
             break;
         }
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
-            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, c.tm_kv32, ap, c.sm_count, st, e.attn_exact));
+            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, c.tm_kv32, ap, c.sm_count, st, m.attn_exact));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
-            GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x, 0, 0};
+            GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x};
             if (fused) {
                 p.stats_out = c.pstats;
                 p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, c.tm_x, c.tm_x, p, c.sm_count, st));
-            else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, L.tm_out_w, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
+            } else VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_x, p, c.sm_count, st));
         }
         if (!fused) {
             ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
@@ -866,26 +909,24 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
         }
         {
             ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
-            GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr, 0, 0};
+            GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr};
             if (fused) {
                 p.bias = L.fc1_c;
-                p.colsum = L.fc1_s;
+                p.colsum = W.fc1_s;
                 p.stats_in = c.pstats;
                 p.stats_parts = 6;
                 p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_wf, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
-            else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(prec, c.tm_xn, L.tm_fc1_w, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, W.tm_fc1_wf, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
+            } else VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, W.tm_fc1_w, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
         }
         {
             ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
-            GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x, 0, 0};
+            GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x};
             if (fused && l + 1 < kDepth) {   // the last layer's output only feeds the class-row LayerNorm of the head
                 p.stats_out = c.pstats;
                 p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
-            } else if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, c.tm_x, c.tm_x, p, c.sm_count, st));
-            else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, L.tm_fc2_w, p, c.sm_count, st));
+                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
+            } else VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_x, p, c.sm_count, st));
         }
     }
     ProfScope ps(c, pf, VIT_PROF_HEAD);
@@ -898,33 +939,28 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const float* d_images
 }
 
 // Small passes (batch-1 latency, BASELINE.json configs[1]) are launch bound: ~65 kernels of 5-20 us each.  Their
-// launch sequence is captured once per (pass size, buffers, softmax mode) into a CUDA graph and replayed with a
-// single launch.  VIT_GRAPHS=0 disables this.
+// launch sequence is captured once per (pass size, buffers, mode) into a CUDA graph and replayed with a
+// single launch.  VIT_OPT_GRAPHS = 0 disables this.
 constexpr int kGraphMaxBatch = 8;
-bool graphs_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* s = getenv("VIT_GRAPHS");
-        v = (s && atoi(s) == 0) ? 0 : 1;
-    }
-    return v == 1;
-}
-int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb, float* d_logits) {
-    if (nb > kGraphMaxBatch || e.profiling || !graphs_enabled() || gemm_impl() != 2)
-        return enqueue_forward_kernels(c, e, d_images, nb, d_logits);
+int enqueue_forward(DeviceCtx& c, const Engine& e, const PassMode& m, const float* d_images, int nb, float* d_logits) {
+    if (!m.attn_exact) c.pending_fast_softmax = true;
+    if (m.prec == VIT_PREC_FP16) c.pending_fp16 = true;
+    if (nb > kGraphMaxBatch || e.profiling || !g_opt.graphs.load())
+        return enqueue_forward_kernels(c, e, m, d_images, nb, d_logits);
     for (auto& g : c.graphs)
-        if (g.nb == nb && g.images == d_images && g.logits == d_logits && g.attn_exact == e.attn_exact && g.ln_fused == e.ln_fused && g.prune_last == e.prune_last) {
+        if (g.nb == nb && g.prec == m.prec && g.images == d_images && g.logits == d_logits && g.attn_exact == m.attn_exact &&
+            g.ln_fused == m.ln_fused && g.prune_last == m.prune_last && g.pdl == m.pdl) {
             CU_TRY(cudaGraphLaunch(g.exec, c.stream));
             g_launches.fetch_add(g.launches, std::memory_order_relaxed);
             return 0;
         }
     // first time: run it once the ordinary way (sets the kernels' attributes, builds the tensor maps), then capture
-    VIT_TRY(enqueue_forward_kernels(c, e, d_images, nb, d_logits));
+    VIT_TRY(enqueue_forward_kernels(c, e, m, d_images, nb, d_logits));
     if (c.graphs.size() >= 16) return 0;   // a caller cycling through many buffers: stay with plain launches
     cudaGraph_t graph = nullptr;
     const long long before = g_launches.load();
     CU_TRY(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_forward_kernels(c, e, d_images, nb, d_logits);
+    const int rc = enqueue_forward_kernels(c, e, m, d_images, nb, d_logits);
     const cudaError_t ce = cudaStreamEndCapture(c.stream, &graph);
     const long long captured = g_launches.load() - before;
     g_launches.fetch_sub(captured, std::memory_order_relaxed);   // captured, not launched
@@ -935,11 +971,13 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     if (ce != cudaSuccess) return set_err(VIT_E_CUDA, "graph capture: %s", cudaGetErrorString(ce));
     DeviceCtx::Graph g;
     g.nb = nb;
+    g.prec = m.prec;
     g.images = d_images;
     g.logits = d_logits;
-    g.attn_exact = e.attn_exact;
-    g.ln_fused = e.ln_fused;
-    g.prune_last = e.prune_last;
+    g.attn_exact = m.attn_exact;
+    g.ln_fused = m.ln_fused;
+    g.prune_last = m.prune_last;
+    g.pdl = m.pdl;
     g.launches = captured;
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -948,23 +986,78 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const float* d_images, int nb
     return 0;
 }
 
-size_t tensor_numel(int idx, int img) {
-    const size_t g = img / kPatch, tokens = g * g + 1;
-    switch (idx) {
-        case 0: case 2: case 148: case 149: return kDim;
-        case 1: return static_cast<size_t>(kDim) * 3 * kPatch * kPatch;
-        case 3: return tokens * kDim;
-        case 150: return static_cast<size_t>(kClasses) * kDim;
-        case 151: return kClasses;
+// After the slot's stream has been synchronised behind a read_flags_async(): what the kernels reported.  Clears the
+// device word when set, and the slot's pending marks.  Returns the flags that apply to the work that was pending.
+int read_flags_async(DeviceCtx& c) {
+    CU_TRY(cudaMemcpyAsync(c.h_flags, c.d_flags, sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+    return 0;
+}
+int collect_flags(DeviceCtx& c, unsigned int* flags) {
+    unsigned int v = *c.h_flags;
+    if (v) CU_TRY(cudaMemsetAsync(c.d_flags, 0, sizeof(unsigned int), c.stream));
+    *c.h_flags = 0;
+    if (!c.pending_fast_softmax) v &= ~VIT_FLAG_ATTN_RANGE;
+    if (!c.pending_fp16) v &= ~VIT_FLAG_NONFINITE;
+    c.pending_fast_softmax = c.pending_fp16 = false;
+    *flags = v & (VIT_FLAG_ATTN_RANGE | VIT_FLAG_NONFINITE);
+    return 0;
+}
+
+void read_env_options() {
+    g_opt.attn_exact = env_flag("VIT_ATTN_EXACT", 0);
+    g_opt.prune_last = env_flag("VIT_PRUNE_LAST", 1);
+    g_opt.ln_fused = env_flag("VIT_LN_FUSED", 1);
+    g_opt.pdl = env_flag("VIT_PDL", 1);
+    g_opt.graphs = env_flag("VIT_GRAPHS", 1);
+    g_opt.host_threads = env_flag("VIT_HOST_THREADS", 1);
+}
+
+int configure_engine(Engine& e, int img_size, int max_batch_per_gpu, int n_gpus, const int* device_ids, int precision) {
+    if (img_size <= 0 || img_size % kPatch || img_size > 1024) return set_err(VIT_E_ARG, "img_size %d must be a positive multiple of 16 (<= 1024)", img_size);
+    if (max_batch_per_gpu <= 0 || n_gpus <= 0 || n_gpus > 32) return set_err(VIT_E_ARG, "max_batch_per_gpu and n_gpus must be positive (n_gpus <= 32)");
+    if (precision != VIT_PREC_BF16 && precision != VIT_PREC_FP16 && precision != VIT_PREC_AUTO) return set_err(VIT_E_ARG, "unknown precision %d", precision);
+    for (int g = 0; g < n_gpus; ++g)
+        for (int h = 0; h < g; ++h)
+            if ((device_ids ? device_ids[g] : g) == (device_ids ? device_ids[h] : h)) return set_err(VIT_E_ARG, "device %d listed twice", device_ids[g]);
+    e.img = img_size;
+    e.grid = img_size / kPatch;
+    e.patches = e.grid * e.grid;
+    e.tokens = e.patches + 1;
+    e.max_batch = max_batch_per_gpu;
+    e.policy = precision;
+    e.prec = precision == VIT_PREC_BF16 ? VIT_PREC_BF16 : VIT_PREC_FP16;
+    e.resident[VIT_PREC_BF16] = precision != VIT_PREC_FP16;
+    e.resident[VIT_PREC_FP16] = precision != VIT_PREC_BF16;
+    e.attn_fallbacks = e.prec_fallbacks = 0;
+    e.profiling = false;
+    read_env_options();
+    return 0;
+}
+
+void fail_init(int) {
+    char keep[sizeof(t_err)];
+    memcpy(keep, t_err, sizeof(keep));
+    vit_cuda_free();
+    memcpy(t_err, keep, sizeof(keep));
+}
+
+// ---- weight cache file: header + the arena's bytes
+struct CacheHeader {
+    char magic[8];            // "VITB200W"
+    uint32_t version, img_size, policy, resident_mask;
+    uint64_t arena_bytes, checksum;   // FNV-1a 64 over the arena, 8 bytes at a time
+};
+constexpr uint32_t kCacheVersion = 2;
+uint64_t fnv1a64_words(const uint8_t* p, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x100000001b3ull;
     }
-    switch ((idx - 4) % 12) {
-        case 2: return static_cast<size_t>(3) * kDim * kDim;
-        case 3: return 3 * kDim;
-        case 4: return static_cast<size_t>(kDim) * kDim;
-        case 8: case 10: return static_cast<size_t>(kHidden) * kDim;
-        case 9: return kHidden;
-        default: return kDim;
-    }
+    for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
 }
 
 }  // namespace
@@ -985,37 +1078,28 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size, in
                      const int* device_ids, int precision) {
     if (g_eng.up) vit_cuda_free();
     if (!networks || n_tensors != VIT_NUM_TENSORS) return set_err(VIT_E_ARG, "expected %d weight tensors, got %d", VIT_NUM_TENSORS, n_tensors);
-    if (img_size <= 0 || img_size % kPatch || img_size > 1024) return set_err(VIT_E_ARG, "img_size %d must be a positive multiple of 16", img_size);
-    if (max_batch_per_gpu <= 0 || n_gpus <= 0) return set_err(VIT_E_ARG, "max_batch_per_gpu and n_gpus must be positive");
-    if (precision != VIT_PREC_BF16 && precision != VIT_PREC_FP16) return set_err(VIT_E_ARG, "unknown precision %d", precision);
+    Engine& e = g_eng;
+    VIT_TRY(configure_engine(e, img_size, max_batch_per_gpu, n_gpus, device_ids, precision));
     for (int i = 0; i < n_tensors; ++i)
         if (!networks[i].data || networks[i].size != tensor_numel(i, img_size))
             return set_err(VIT_E_ARG, "weight tensor %d: have %zu floats%s, need %zu for img_size %d", i, networks[i].size,
                            networks[i].data ? "" : " (missing)", tensor_numel(i, img_size), img_size);
-    Engine& e = g_eng;
-    e.img = img_size;
-    e.grid = img_size / kPatch;
-    e.patches = e.grid * e.grid;
-    e.tokens = e.patches + 1;
-    e.max_batch = max_batch_per_gpu;
-    e.prec = precision;
-    {
-        const char* ex = getenv("VIT_ATTN_EXACT");
-        e.attn_exact = ex && atoi(ex) != 0;
-        e.attn_fallbacks = 0;
-        const char* lf = getenv("VIT_LN_FUSED");
-        e.ln_fused = !(lf && atoi(lf) == 0);
-        const char* pl = getenv("VIT_PRUNE_LAST");
-        e.prune_last = !(pl && atoi(pl) == 0);
-    }
     e.ctx.assign(n_gpus, DeviceCtx());
     for (int g = 0; g < n_gpus; ++g) {
-        const int rc = init_ctx(e.ctx[g], device_ids ? device_ids[g] : g, networks, e);
+        DeviceCtx& c = e.ctx[g];
+        int rc = open_ctx(c, device_ids ? device_ids[g] : g, e);
+        if (!rc) rc = fill_arena_from_tensors(c, networks, e);
+        unsigned int flags = 0;
+        if (!rc) rc = take_status_flags(&flags);
+        if (!rc && (flags & VIT_FLAG_WEIGHT_RANGE)) {
+            // a finite fp32 weight (or ln_w (.) W) does not fit FP16
+            if (e.policy == VIT_PREC_FP16) rc = set_err(VIT_E_RANGE, "a weight exceeds the FP16 range (65504): use VIT_PREC_AUTO or VIT_PREC_BF16");
+            else e.prec = VIT_PREC_BF16;   // AUTO: run on the BF16 set from the start
+        }
+        if (!rc) rc = make_weight_maps(c, e);
+        if (!rc) rc = alloc_workspace(c, e);
         if (rc) {
-            char keep[sizeof(t_err)];
-            memcpy(keep, t_err, sizeof(keep));
-            vit_cuda_free();
-            memcpy(t_err, keep, sizeof(keep));
+            fail_init(rc);
             return rc;
         }
     }
@@ -1024,7 +1108,114 @@ int vit_cuda_init_ex(const vit_tensor* networks, int n_tensors, int img_size, in
 }
 
 int vit_cuda_init(const vit_tensor* networks, int n_tensors, int img_size, int max_batch_per_gpu, int n_gpus) {
-    return vit_cuda_init_ex(networks, n_tensors, img_size, max_batch_per_gpu, n_gpus, nullptr, VIT_PREC_BF16);
+    return vit_cuda_init_ex(networks, n_tensors, img_size, max_batch_per_gpu, n_gpus, nullptr, VIT_PREC_AUTO);
+}
+
+int vit_cuda_save_weight_cache(const char* path) {
+    Engine& e = g_eng;
+    if (!e.up || !path) return set_err(VIT_E_ARG, "engine not initialised");
+    DeviceCtx& c = e.ctx[0];
+    CU_TRY(cudaSetDevice(c.device));
+    std::vector<uint8_t> host(c.arena_bytes);
+    CU_TRY(cudaMemcpy(host.data(), c.arena, c.arena_bytes, cudaMemcpyDeviceToHost));
+    CacheHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "VITB200W", 8);
+    h.version = kCacheVersion;
+    h.img_size = static_cast<uint32_t>(e.img);
+    h.policy = static_cast<uint32_t>(e.policy);
+    h.resident_mask = (e.resident[0] ? 1u : 0u) | (e.resident[1] ? 2u : 0u);
+    h.arena_bytes = c.arena_bytes;
+    h.checksum = fnv1a64_words(host.data(), host.size());
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_err(VIT_E_ARG, "cannot open %s for writing", path);
+    const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(host.data(), 1, host.size(), f) == host.size();
+    if (fclose(f) != 0 || !ok) return set_err(VIT_E_ARG, "short write to %s", path);
+    return 0;
+}
+
+int vit_cuda_init_from_cache(const char* path, int max_batch_per_gpu, int n_gpus, const int* device_ids) {
+    if (g_eng.up) vit_cuda_free();
+    if (!path) return set_err(VIT_E_ARG, "no cache path");
+    VIT_TRY(check_device(device_ids ? device_ids[0] : 0, nullptr));
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_err(VIT_E_ARG, "cannot open weight cache %s", path);
+    CacheHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "VITB200W", 8) != 0 || h.version != kCacheVersion) {
+        fclose(f);
+        return set_err(VIT_E_ARG, "%s is not a weight cache of this engine (version %u)", path, kCacheVersion);
+    }
+    Engine& e = g_eng;
+    int rc = configure_engine(e, static_cast<int>(h.img_size), max_batch_per_gpu, n_gpus, device_ids, static_cast<int>(h.policy));
+    if (rc) {
+        fclose(f);
+        return rc;
+    }
+    uint8_t* host = nullptr;   // pinned: the host-to-device copies run at full PCIe rate
+    if (cudaHostAlloc(reinterpret_cast<void**>(&host), h.arena_bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        fclose(f);
+        return set_err(VIT_E_NOMEM, "cannot allocate %llu bytes of pinned memory for the weight cache", (unsigned long long)h.arena_bytes);
+    }
+    const bool read_ok = fread(host, 1, h.arena_bytes, f) == h.arena_bytes;
+    fclose(f);
+    if (!read_ok || fnv1a64_words(host, h.arena_bytes) != h.checksum) {
+        cudaFreeHost(host);
+        return set_err(VIT_E_ARG, "weight cache %s is truncated or corrupt (checksum)", path);
+    }
+    e.ctx.assign(n_gpus, DeviceCtx());
+    for (int g = 0; g < n_gpus && !rc; ++g) {
+        DeviceCtx& c = e.ctx[g];
+        rc = open_ctx(c, device_ids ? device_ids[g] : g, e);
+        if (!rc && (c.arena_bytes != h.arena_bytes || h.resident_mask != ((e.resident[0] ? 1u : 0u) | (e.resident[1] ? 2u : 0u))))
+            rc = set_err(VIT_E_ARG, "weight cache %s: arena of %llu bytes, this build lays out %zu", path, (unsigned long long)h.arena_bytes, c.arena_bytes);
+        if (!rc && cudaMemcpyAsync(c.arena, host, c.arena_bytes, cudaMemcpyHostToDevice, c.stream) != cudaSuccess)
+            rc = set_err(VIT_E_CUDA, "weight cache upload: %s", cudaGetErrorString(cudaGetLastError()));
+        if (!rc) rc = make_weight_maps(c, e);
+        if (!rc) rc = alloc_workspace(c, e);   // ends with a stream synchronise: the upload is through
+    }
+    cudaFreeHost(host);
+    if (rc) {
+        fail_init(rc);
+        return rc;
+    }
+    e.up = true;
+    return 0;
+}
+
+int vit_cuda_set_option(int option, int value) {
+    const int v = value != 0;
+    switch (option) {
+        case VIT_OPT_ATTENTION_EXACT: g_opt.attn_exact = v; break;
+        case VIT_OPT_CLASS_ROW_PRUNING: g_opt.prune_last = v; break;
+        case VIT_OPT_LN_FUSED: g_opt.ln_fused = v; break;
+        case VIT_OPT_PDL: g_opt.pdl = v; break;
+        case VIT_OPT_GRAPHS: g_opt.graphs = v; break;
+        case VIT_OPT_HOST_THREADS: g_opt.host_threads = v; break;
+        default: return set_err(VIT_E_ARG, "unknown option %d", option);
+    }
+    return 0;
+}
+int vit_cuda_get_option(int option, int* value) {
+    if (!value) return set_err(VIT_E_ARG, "bad arguments");
+    switch (option) {
+        case VIT_OPT_ATTENTION_EXACT: *value = g_opt.attn_exact; break;
+        case VIT_OPT_CLASS_ROW_PRUNING: *value = g_opt.prune_last; break;
+        case VIT_OPT_LN_FUSED: *value = g_opt.ln_fused; break;
+        case VIT_OPT_PDL: *value = g_opt.pdl; break;
+        case VIT_OPT_GRAPHS: *value = g_opt.graphs; break;
+        case VIT_OPT_HOST_THREADS: *value = g_opt.host_threads; break;
+        default: return set_err(VIT_E_ARG, "unknown option %d", option);
+    }
+    return 0;
+}
+int vit_cuda_set_class_row_pruning(int on) {
+    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
+    return vit_cuda_set_option(VIT_OPT_CLASS_ROW_PRUNING, on);
+}
+int vit_cuda_set_attention_exact(int on) {
+    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
+    return vit_cuda_set_option(VIT_OPT_ATTENTION_EXACT, on);
 }
 
 int vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d_logits) {
@@ -1033,40 +1224,39 @@ int vit_cuda_enqueue_device(int gpu_slot, const float* d_images, int n, float* d
     if (gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
     if (n <= 0 || n > e.max_batch) return set_err(VIT_E_ARG, "n=%d outside (0, max_batch=%d]", n, e.max_batch);
     if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
-    if (gemm_impl() != 2 && e.prec != VIT_PREC_BF16) return set_err(VIT_E_ARG, "VIT_GEMM_IMPL=1 (A/B test kernels) supports bf16 only");
     DeviceCtx& c = e.ctx[gpu_slot];
     CU_TRY(cudaSetDevice(c.device));
-    return enqueue_forward(c, e, d_images, n, d_logits);
+    return enqueue_forward(c, e, current_mode(e), d_images, n, d_logits);
 }
 
 int vit_cuda_sync(int gpu_slot) {
     Engine& e = g_eng;
     if (!e.up || gpu_slot < 0 || gpu_slot >= (int)e.ctx.size()) return set_err(VIT_E_ARG, "bad gpu slot %d", gpu_slot);
-    CU_TRY(cudaSetDevice(e.ctx[gpu_slot].device));
-    const cudaError_t se = cudaStreamSynchronize(e.ctx[gpu_slot].stream);
+    DeviceCtx& c = e.ctx[gpu_slot];
+    CU_TRY(cudaSetDevice(c.device));
+    const bool check = c.pending_fast_softmax || c.pending_fp16;
+    if (check) VIT_TRY(read_flags_async(c));
+    const cudaError_t se = cudaStreamSynchronize(c.stream);
     if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
-    if (!e.attn_exact) {
-        bool flagged = false;
-        VIT_TRY(take_attn_range_flag(&flagged));
-        if (flagged) {
-            e.attn_exact = true;  // device-resident callers re-enqueue; the engine stays on the exact softmax
-            ++e.attn_fallbacks;
-            return set_err(VIT_E_RANGE, "attention: a row's scores left the single-pass softmax's exponent window; the results of "
-                                        "this pass are invalid.  The engine has switched to the exact two-pass softmax: enqueue again");
-        }
+    if (!check) return 0;
+    unsigned int flags = 0;
+    VIT_TRY(collect_flags(c, &flags));
+    if (flags & VIT_FLAG_ATTN_RANGE) {
+        g_opt.attn_exact = 1;  // device-resident callers re-enqueue; the engine stays on the exact softmax
+        ++e.attn_fallbacks;
+        return set_err(VIT_E_RANGE, "attention: a row's scores left the single-pass softmax's exponent window; every pass enqueued on slot %d "
+                                    "since its last sync is invalid.  The engine has switched to the exact two-pass softmax: enqueue them again", gpu_slot);
     }
-    return 0;
-}
-
-int vit_cuda_set_class_row_pruning(int on) {
-    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
-    g_eng.prune_last = on != 0;
-    return 0;
-}
-
-int vit_cuda_set_attention_exact(int on) {
-    if (!g_eng.up) return set_err(VIT_E_ARG, "engine not initialised");
-    g_eng.attn_exact = on != 0;
+    if (flags & VIT_FLAG_NONFINITE) {
+        if (e.policy == VIT_PREC_AUTO && e.prec == VIT_PREC_FP16) {
+            e.prec = VIT_PREC_BF16;
+            ++e.prec_fallbacks;
+            return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow): every pass enqueued on slot %d since its last sync is "
+                                        "invalid.  The engine has switched to BF16 operands: enqueue them again", gpu_slot);
+        }
+        if (e.policy == VIT_PREC_FP16)
+            return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow) on slot %d: use VIT_PREC_AUTO or VIT_PREC_BF16", gpu_slot);
+    }
     return 0;
 }
 
@@ -1109,17 +1299,228 @@ int vit_cuda_shard_range(int n, int n_gpus, int g, int* lo, int* hi) {
     return 0;
 }
 
-static int forward_host_once(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, bool* range_flag);
+}  // extern "C"
 
-static int forward_host(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, int* top1_out);
+namespace {
+
 // hand the logits parked in pinned staging buffer `buf` (if any) over to the caller's (pageable) array
-static int drain_logits(DeviceCtx& c, int buf, float* logits_out) {
+int drain_logits(DeviceCtx& c, int buf, float* logits_out) {
     if (c.pend_count[buf] == 0) return 0;
     CU_TRY(cudaEventSynchronize(c.ev_logits[buf]));
     memcpy(logits_out + static_cast<size_t>(c.pend_first[buf]) * kClasses, c.h_logits[buf], static_cast<size_t>(c.pend_count[buf]) * kClasses * sizeof(float));
     c.pend_count[buf] = 0;
     return 0;
 }
+
+// What one host call hands to every slot's feeding thread
+struct HostJob {
+    const float* images_nchw;          // contiguous images, or
+    const float* const* image_ptrs;    // one pointer per image (the reference loader's form)
+    int n;
+    float* logits_out;
+    bool images_pinned, logits_pinned;
+    PassMode mode;
+    int gather_threads;                // host threads a slot may use to gather a staged pass
+    const std::vector<int>*pass_first, *pass_count;
+};
+
+// One slot's shard of a host call: its passes, H2D copies on the copy stream into alternating image buffers under the
+// kernels of the previous pass, logits back per pass; ends with the slot's stream synchronised and its status flags read.
+// Runs on the slot's own host thread when the engine has several GPUs: a gather of pass i + 1 for one GPU
+// must not hold up the enqueueing for another.
+int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
+    DeviceCtx& c = e.ctx[g];
+    const int G = static_cast<int>(e.ctx.size());
+    const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
+    *flags_out = 0;
+    CU_TRY(cudaSetDevice(c.device));
+    c.pend_count[0] = c.pend_count[1] = 0;   // nothing parked from an earlier call that failed half-way
+    int lo, hi;
+    vit_cuda_shard_range(job.n, G, g, &lo, &hi);
+    const bool staged = job.image_ptrs || !job.images_pinned;
+    const int n_pass = static_cast<int>(job.pass_first->size());
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int first = lo + (*job.pass_first)[pass];
+        if (first >= hi) break;
+        const int nb = std::min((*job.pass_count)[pass], hi - first);
+        const int buf = pass & 1;
+        // H2D of this pass overlaps the previous pass's compute (other image buffer)
+        if (pass >= 2) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_done[buf], 0));
+        const float* src = nullptr;
+        if (staged) {
+            // separately allocated images (the reference's loader, Network.c:75-93) or pageable memory: gather this
+            // pass into the slot's pinned staging buffer while the GPU works on the previous pass
+            if (!c.h_stage[buf]) {
+                CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_stage[buf]), static_cast<size_t>(e.max_batch) * img_elems * sizeof(float), cudaHostAllocPortable));
+                CU_TRY(cudaEventCreateWithFlags(&c.ev_stage[buf], cudaEventDisableTiming));
+            } else {
+                CU_TRY(cudaEventSynchronize(c.ev_stage[buf]));   // its previous copy has left the buffer
+            }
+            // One host thread copies ~10 GB/s: 1024 images (617 MB) would take longer than the GPU needs for them.
+            float* dst = c.h_stage[buf];
+            const float* const* ptrs = job.image_ptrs;
+            const float* flat = job.images_nchw;
+            auto gather = [=](int i0, int i1) {
+                for (int i = i0; i < i1; ++i)
+                    memcpy(dst + static_cast<size_t>(i) * img_elems, ptrs ? ptrs[first + i] : flat + static_cast<size_t>(first + i) * img_elems, img_elems * sizeof(float));
+            };
+            const int n_thr = std::min(job.gather_threads, (nb + 15) / 16);
+            if (n_thr <= 1) {
+                gather(0, nb);
+            } else {
+                std::vector<std::thread> pool;
+                for (int t = 1; t < n_thr; ++t) pool.emplace_back(gather, nb * t / n_thr, nb * (t + 1) / n_thr);
+                gather(0, nb / n_thr);
+                for (auto& th : pool) th.join();
+            }
+            src = dst;
+        } else {
+            src = job.images_nchw + static_cast<size_t>(first) * img_elems;
+        }
+        CU_TRY(cudaMemcpyAsync(c.images[buf], src, static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+        if (staged) CU_TRY(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
+        CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
+        CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
+        VIT_TRY(enqueue_forward(c, e, job.mode, c.images[buf], nb, c.logits));
+        CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
+        if (job.logits_pinned) {
+            CU_TRY(cudaMemcpyAsync(job.logits_out + static_cast<size_t>(first) * kClasses, c.logits,
+                                   static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+        } else {
+            // a device-to-pageable copy would block the host until this pass is through, and with it the
+            // enqueueing (and gathering) of the next one: go through pinned staging, hand over later
+            if (!c.h_logits[buf]) {
+                CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_logits[buf]), static_cast<size_t>(e.max_batch) * kClasses * sizeof(float), cudaHostAllocPortable));
+                CU_TRY(cudaEventCreateWithFlags(&c.ev_logits[buf], cudaEventDisableTiming));
+            }
+            VIT_TRY(drain_logits(c, buf, job.logits_out));
+            CU_TRY(cudaMemcpyAsync(c.h_logits[buf], c.logits, static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+            CU_TRY(cudaEventRecord(c.ev_logits[buf], c.stream));
+            c.pend_first[buf] = first;
+            c.pend_count[buf] = nb;
+        }
+    }
+    VIT_TRY(read_flags_async(c));
+    const cudaError_t se = cudaStreamSynchronize(c.stream);
+    if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
+    for (int buf = 0; buf < 2; ++buf) VIT_TRY(drain_logits(c, buf, job.logits_out));
+    return collect_flags(c, flags_out);
+}
+
+// After a failed shard: let everything this call put on the slot's streams finish, so that the next call starts clean.
+void quiesce(DeviceCtx& c) {
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.copy_stream);
+    cudaStreamSynchronize(c.stream);
+    c.pend_count[0] = c.pend_count[1] = 0;
+    cudaGetLastError();
+}
+
+int forward_host_once(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, unsigned int* flags) {
+    Engine& e = g_eng;
+    *flags = 0;
+    if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
+    const int G = static_cast<int>(e.ctx.size());
+    const int per_gpu = (n + G - 1) / G;  // contiguous shards (SURVEY.md 8e)
+    // Pass schedule of a shard: the H2D copy of pass i+1 (copy stream, second image buffer) hides under the
+    // kernels of pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB), and
+    // every later pass may be three times the previous one (PCIe Gen5 moves images ~3.4x faster than
+    // the kernels consume them) up to the workspace size.  1024 images: 32 + 96 + 288 + 608.
+    HostJob job;
+    job.images_nchw = images_nchw;
+    job.image_ptrs = image_ptrs;
+    job.n = n;
+    job.logits_out = logits_out;
+    cudaPointerAttributes pa;
+    job.logits_pinned = cudaPointerGetAttributes(&pa, logits_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    job.images_pinned = images_nchw && cudaPointerGetAttributes(&pa, images_nchw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    job.mode = current_mode(e);
+    // any number of passes (a tiny max_batch with a large n): size the schedule arrays for the worst case
+    const int worst = per_gpu / std::min(e.max_batch, 32) + 8;
+    std::vector<int> pass_first(worst), pass_count(worst);
+    const int n_sched = vit_cuda_pass_schedule_ex(per_gpu, e.max_batch, (image_ptrs || !job.images_pinned) ? 1 : 0, pass_first.data(), pass_count.data(), worst);
+    if (n_sched < 0) return n_sched;
+    pass_first.resize(n_sched);
+    pass_count.resize(n_sched);
+    job.pass_first = &pass_first;
+    job.pass_count = &pass_count;
+    // gathering threads: up to eight per slot, all slots together at most half the host's cores
+    const int hw = std::max(2, static_cast<int>(std::thread::hardware_concurrency()));
+    job.gather_threads = std::max(1, std::min(8, hw / (2 * G)));
+
+    std::vector<int> rc(G, 0);
+    std::vector<unsigned int> fl(G, 0);
+    auto work = [&](int g) {
+        rc[g] = run_shard(e, g, job, &fl[g]);
+        if (rc[g]) {
+            memcpy(e.ctx[g].err, t_err, sizeof(t_err));
+            quiesce(e.ctx[g]);
+        }
+    };
+    if (G == 1 || !g_opt.host_threads.load()) {
+        // single GPU, or VIT_OPT_HOST_THREADS = 0: this thread serves the slots one after the other
+        for (int g = 0; g < G; ++g) work(g);
+    } else {
+        std::vector<std::thread> feeders;
+        for (int g = 1; g < G; ++g) feeders.emplace_back(work, g);
+        work(0);
+        for (auto& th : feeders) th.join();
+    }
+    for (int g = 0; g < G; ++g) {
+        if (rc[g]) {
+            memcpy(t_err, e.ctx[g].err, sizeof(t_err));
+            return rc[g];
+        }
+        *flags |= fl[g];
+    }
+    return 0;
+}
+
+int forward_host(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, int* top1_out) {
+    Engine& e = g_eng;
+    if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
+    if (!logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
+    if (n == 0) return 0;
+    // A flagged call is repeated: with the exact two-pass softmax (a row left the single-pass softmax's exponent window)
+    // and / or, under VIT_PREC_AUTO, with the BF16 operand set (an FP16 operand overflowed -- 8-bit exponent instead of 5).
+    // Either switch becomes permanent once it has been needed in three calls: the data evidently does it regularly.
+    bool temp_exact = false, temp_bf16 = false;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        unsigned int flags = 0;
+        VIT_TRY(forward_host_once(images_nchw, image_ptrs, n, logits_out, &flags));
+        bool again = false;
+        if ((flags & VIT_FLAG_ATTN_RANGE) && !g_opt.attn_exact.load()) {
+            ++e.attn_fallbacks;
+            g_opt.attn_exact = 1;
+            temp_exact = again = true;
+        }
+        if ((flags & VIT_FLAG_NONFINITE) && e.prec == VIT_PREC_FP16) {
+            if (e.policy == VIT_PREC_FP16)
+                return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow): use VIT_PREC_AUTO or VIT_PREC_BF16");
+            ++e.prec_fallbacks;
+            e.prec = VIT_PREC_BF16;
+            temp_bf16 = again = true;
+        }
+        if (!again) break;
+    }
+    if (temp_exact && e.attn_fallbacks < 3) g_opt.attn_exact = 0;
+    if (temp_bf16 && e.prec_fallbacks < 3) e.prec = VIT_PREC_FP16;
+    if (top1_out)
+        for (int i = 0; i < n; ++i) {
+            const float* row = logits_out + static_cast<size_t>(i) * kClasses;
+            int best = 0;
+            for (int j = 1; j < kClasses; ++j)
+                if (row[j] > row[best]) best = j;
+            top1_out[i] = best;
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
 
 int vit_cuda_forward(const float* images_nchw, int n, float* logits_out, int* top1_out) {
     if (n == 0 && g_eng.up) return 0;   // nothing to do, whatever the pointers are
@@ -1135,149 +1536,16 @@ int vit_cuda_forward_scattered(const float* const* images, int n, float* logits_
     return forward_host(nullptr, images, n, logits_out, top1_out);
 }
 
-static int forward_host(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, int* top1_out) {
-    Engine& e = g_eng;
-    if (!e.up) return set_err(VIT_E_ARG, "engine not initialised");
-    if (!logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
-    if (n == 0) return 0;
-    bool flagged = false;
-    VIT_TRY(forward_host_once(images_nchw, image_ptrs, n, logits_out, &flagged));
-    if (flagged) {
-        // some row left the single-pass softmax's exponent window: repeat with the exact two-pass softmax
-        // (and stay there once this has happened three times -- the data evidently does it regularly)
-        ++e.attn_fallbacks;
-        e.attn_exact = true;
-        const int rc = forward_host_once(images_nchw, image_ptrs, n, logits_out, &flagged);
-        if (e.attn_fallbacks < 3) e.attn_exact = false;
-        VIT_TRY(rc);
-    }
-    if (top1_out)
-        for (int i = 0; i < n; ++i) {
-            const float* row = logits_out + static_cast<size_t>(i) * kClasses;
-            int best = 0;
-            for (int j = 1; j < kClasses; ++j)
-                if (row[j] > row[best]) best = j;
-            top1_out[i] = best;
-        }
-    return 0;
-}
-
-static int forward_host_once(const float* images_nchw, const float* const* image_ptrs, int n, float* logits_out, bool* range_flag) {
-    Engine& e = g_eng;
-    *range_flag = false;
-    if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
-    const int G = static_cast<int>(e.ctx.size());
-    const size_t img_elems = static_cast<size_t>(3) * e.img * e.img;
-    const int per_gpu = (n + G - 1) / G;  // contiguous shards (SURVEY.md 8e)
-    // Pass schedule of a shard: the H2D copy of pass i+1 (copy stream, second image buffer) hides under the
-    // kernels of pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB), and
-    // every later pass may be three times the previous one (PCIe Gen5 moves images ~3.4x faster than
-    // the kernels consume them) up to the workspace size.  1024 images: 32 + 96 + 288 + 608.
-    cudaPointerAttributes pa;
-    const bool logits_pinned = cudaPointerGetAttributes(&pa, logits_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    const bool images_pinned = images_nchw && cudaPointerGetAttributes(&pa, images_nchw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    // any number of passes (a tiny max_batch with a large n): size the schedule arrays for the worst case
-    const int worst = per_gpu / std::min(e.max_batch, 32) + 8;
-    std::vector<int> pass_first(worst), pass_count(worst);
-    const int n_sched = vit_cuda_pass_schedule_ex(per_gpu, e.max_batch, (image_ptrs || !images_pinned) ? 1 : 0, pass_first.data(), pass_count.data(), worst);
-    if (n_sched < 0) return n_sched;
-    pass_first.resize(n_sched);
-    pass_count.resize(n_sched);
-    const int max_passes = static_cast<int>(pass_first.size());
-    // pass-major issue order so that all GPUs are fed before any host-side wait
-    for (int pass = 0; pass < max_passes; ++pass) {
-        for (int g = 0; g < G; ++g) {
-            DeviceCtx& c = e.ctx[g];
-            int lo, hi;
-            vit_cuda_shard_range(n, G, g, &lo, &hi);
-            const int first = lo + pass_first[pass];
-            if (first >= hi) continue;
-            const int nb = std::min(pass_count[pass], hi - first);
-            const int buf = pass & 1;
-            CU_TRY(cudaSetDevice(c.device));
-            // H2D of this pass overlaps the previous pass's compute (other image buffer)
-            if (pass >= 2) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_done[buf], 0));
-            const float* src = nullptr;
-            if (image_ptrs || !images_pinned) {
-                // separately allocated images (the reference's loader, Network.c:75-93) or pageable memory: gather this
-                // pass into the slot's pinned staging buffer while the GPU works on the previous pass
-                if (!c.h_stage[buf]) {
-                    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_stage[buf]), static_cast<size_t>(e.max_batch) * img_elems * sizeof(float), cudaHostAllocPortable));
-                    CU_TRY(cudaEventCreateWithFlags(&c.ev_stage[buf], cudaEventDisableTiming));
-                } else {
-                    CU_TRY(cudaEventSynchronize(c.ev_stage[buf]));   // its previous copy has left the buffer
-                }
-                // One host thread copies ~10 GB/s: 1024 images (617 MB) would take longer than the GPU needs for them.
-                // Up to eight threads (half the host cores) share a pass.
-                float* dst = c.h_stage[buf];
-                auto gather = [=](int i0, int i1) {
-                    for (int i = i0; i < i1; ++i)
-                        memcpy(dst + static_cast<size_t>(i) * img_elems,
-                               image_ptrs ? image_ptrs[first + i] : images_nchw + static_cast<size_t>(first + i) * img_elems, img_elems * sizeof(float));
-                };
-                const int n_thr = std::min(std::max(1, static_cast<int>(std::thread::hardware_concurrency()) / 2), std::min(8, (nb + 15) / 16));
-                if (n_thr <= 1) {
-                    gather(0, nb);
-                } else {
-                    std::vector<std::thread> pool;
-                    for (int t = 1; t < n_thr; ++t) pool.emplace_back(gather, nb * t / n_thr, nb * (t + 1) / n_thr);
-                    gather(0, nb / n_thr);
-                    for (auto& th : pool) th.join();
-                }
-                src = c.h_stage[buf];
-            } else {
-                src = images_nchw + static_cast<size_t>(first) * img_elems;
-            }
-            CU_TRY(cudaMemcpyAsync(c.images[buf], src, static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
-            if (src == c.h_stage[buf]) CU_TRY(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
-            CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
-            CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
-            VIT_TRY(enqueue_forward(c, e, c.images[buf], nb, c.logits));
-            CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
-            if (logits_pinned) {
-                CU_TRY(cudaMemcpyAsync(logits_out + static_cast<size_t>(first) * kClasses, c.logits,
-                                       static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-            } else {
-                // a device-to-pageable copy would block the host until this pass is through, and with it the
-                // enqueueing (and gathering) of the next one: go through pinned staging, hand over later
-                if (!c.h_logits[buf]) {
-                    CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.h_logits[buf]), static_cast<size_t>(e.max_batch) * kClasses * sizeof(float), cudaHostAllocPortable));
-                    CU_TRY(cudaEventCreateWithFlags(&c.ev_logits[buf], cudaEventDisableTiming));
-                }
-                VIT_TRY(drain_logits(c, buf, logits_out));
-                CU_TRY(cudaMemcpyAsync(c.h_logits[buf], c.logits, static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaEventRecord(c.ev_logits[buf], c.stream));
-                c.pend_first[buf] = first;
-                c.pend_count[buf] = nb;
-            }
-        }
-    }
-    for (int g = 0; g < G; ++g) {
-        DeviceCtx& c = e.ctx[g];
-        CU_TRY(cudaSetDevice(c.device));
-        const cudaError_t se = cudaStreamSynchronize(c.stream);
-        if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
-        for (int buf = 0; buf < 2; ++buf) VIT_TRY(drain_logits(c, buf, logits_out));
-        if (!e.attn_exact) {
-            bool f = false;
-            VIT_TRY(take_attn_range_flag(&f));
-            *range_flag |= f;
-        }
-    }
-    return 0;
-}
-
 int vit_cuda_info(long long* out, int n) {
     if (!g_eng.up || !out) return set_err(VIT_E_ARG, "engine not initialised");
     const DeviceCtx& c = g_eng.ctx[0];
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, c.device));
-    const long long v[11] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
-                             (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20), g_eng.attn_exact ? 1 : 0,
-                             g_eng.attn_fallbacks, g_eng.prune_last ? 1 : 0};
-    for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+    const long long v[14] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
+                             (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20), g_opt.attn_exact.load() ? 1 : 0,
+                             g_eng.attn_fallbacks, g_opt.prune_last.load() ? 1 : 0, g_eng.policy, g_eng.prec_fallbacks,
+                             (long long)(c.arena_bytes >> 20)};
+    for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
     return 0;
 }
 
@@ -1380,329 +1648,6 @@ int vit_cuda_host_free_pinned(void* h_ptr) {
     return 0;
 }
 
-// ------------------------------------------------------------------------------------ single-op entry points
-namespace {
-struct Scratch {  // RAII device buffers for the op tests
-    std::vector<void*> ptrs;
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
-    int alloc(void** p, size_t bytes, bool zero = false) {
-        CU_TRY(cudaMalloc(p, bytes));
-        ptrs.push_back(*p);
-        if (zero) CU_TRY(cudaMemset(*p, 0, bytes));
-        return 0;
-    }
-    int upload_f32(float** p, const float* h, size_t n) {
-        VIT_TRY(alloc(reinterpret_cast<void**>(p), n * 4));
-        CU_TRY(cudaMemcpy(*p, h, n * 4, cudaMemcpyHostToDevice));
-        return 0;
-    }
-    // fp32 host -> operand precision device (rows padded with zeros up to pad_elems)
-    int upload_operand(void** p, const float* h, size_t n, int prec, size_t pad_elems = 0) {
-        float* tmp = nullptr;
-        VIT_TRY(upload_f32(&tmp, h, n));
-        VIT_TRY(alloc(p, std::max(n, pad_elems) * 2, true));
-        VIT_TRY(launch_convert_from_f32(prec, tmp, *p, n, nullptr));
-        CU_TRY(cudaDeviceSynchronize());
-        return 0;
-    }
-    int download_operand(float* h, const void* d, size_t n, int prec) {
-        float* tmp = nullptr;
-        VIT_TRY(alloc(reinterpret_cast<void**>(&tmp), n * 4));
-        VIT_TRY(launch_convert_to_f32(prec, d, tmp, n, nullptr));
-        CU_TRY(cudaMemcpy(h, tmp, n * 4, cudaMemcpyDeviceToHost));
-        return 0;
-    }
-};
-int op_begin(int* sm_count) {
-    VIT_TRY(check_device(0, sm_count));
-    CU_TRY(cudaSetDevice(0));
-    return 0;
-}
-int op_end(const char* what) {
-    const cudaError_t se = cudaDeviceSynchronize();
-    if (se != cudaSuccess) return watchdog_or_cuda_error(se, what);
-    return 0;
-}
-}  // namespace
-
-int vit_cuda_op_linear(const float* x, const float* W, const float* b, const float* residual, float* y, int m, int n,
-                       int k, int epilogue, int precision) {
-    int sms = 0;
-    VIT_TRY(op_begin(&sms));
-    if (!x || !W || !b || !y || m <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    if (epilogue == VIT_EPI_BIAS_RESIDUAL && !residual) return set_err(VIT_E_ARG, "residual epilogue needs a residual");
-    Scratch s;
-    void *dx, *dw;
-    float* db;
-    VIT_TRY(s.upload_operand(&dx, x, (size_t)m * k, precision));
-    VIT_TRY(s.upload_operand(&dw, W, (size_t)n * k, precision));
-    VIT_TRY(s.upload_f32(&db, b, n));
-    CUtensorMap ta, tb;
-    VIT_TRY(make_tmap(&ta, precision, dx, k, m, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&tb, precision, dw, k, n, GEMM_BK, 128));
-    const bool staged = gemm_impl() == 2;
-    CUtensorMap tout;
-    if (epilogue == VIT_EPI_BIAS_RESIDUAL) {
-        float* dy;
-        VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * n));
-        GemmParams p{m, n, k, db, dy, dy, 0, 0};
-        VIT_TRY(make_tmap_f32(&tout, dy, n, m, GEMM_BM));
-        if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(precision, ta, tb, tout, tout, p, sms, nullptr));
-        else VIT_TRY(launch_gemm<EPI_BIAS_RESIDUAL>(precision, ta, tb, p, sms, nullptr));
-        VIT_TRY(op_end("op_linear"));
-        CU_TRY(cudaMemcpy(y, dy, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
-    } else {
-        void* dy;
-        VIT_TRY(s.alloc(&dy, (size_t)m * n * 2, true));
-        GemmParams p{m, n, k, db, dy, nullptr, 0, 0};
-        CUtensorMap tout32;
-        VIT_TRY(make_tmap(&tout, precision, dy, n, m, GEMM_BK, GEMM_BM));
-        VIT_TRY(make_tmap(&tout32, precision, dy, n, m, GEMM_BK, 32));
-        if (epilogue == VIT_EPI_BIAS_GELU) {
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(precision, ta, tb, tout, tout32, p, sms, nullptr));
-            else VIT_TRY(launch_gemm<EPI_BIAS_GELU>(precision, ta, tb, p, sms, nullptr));
-        } else if (epilogue == VIT_EPI_BIAS) {
-            if (staged) VIT_TRY(launch_gemm_staged<EPI_BIAS>(precision, ta, tb, tout, tout32, p, sms, nullptr));
-            else VIT_TRY(launch_gemm<EPI_BIAS>(precision, ta, tb, p, sms, nullptr));
-        } else return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
-        VIT_TRY(op_end("op_linear"));
-        VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
-    }
-    return op_end("op_linear");
-}
-
-int vit_cuda_op_ln_linear(const float* x, const float* ln_w, const float* ln_b, const float* W, const float* b, float* y, int m,
-                          int n, int epilogue, int precision) {
-    int sms = 0;
-    VIT_TRY(op_begin(&sms));
-    if (!x || !ln_w || !ln_b || !W || !b || !y || m <= 0 || n <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    if (epilogue != VIT_EPI_BIAS && epilogue != VIT_EPI_BIAS_GELU) return set_err(VIT_E_ARG, "unknown epilogue %d", epilogue);
-    Scratch s;
-    float *dx, *dlw, *dlb, *dW, *db, *dcs, *dcv;
-    void *dxc, *dwf, *dy;
-    float2* dst;
-    const size_t srows = (static_cast<size_t>(m) + 255) / 256 * 256;
-    VIT_TRY(s.upload_f32(&dx, x, (size_t)m * kDim));
-    VIT_TRY(s.upload_f32(&dlw, ln_w, kDim));
-    VIT_TRY(s.upload_f32(&dlb, ln_b, kDim));
-    VIT_TRY(s.upload_f32(&dW, W, (size_t)n * kDim));
-    VIT_TRY(s.upload_f32(&db, b, n));
-    VIT_TRY(s.alloc(&dxc, (size_t)m * kDim * 2, true));
-    VIT_TRY(s.alloc(&dwf, (size_t)n * kDim * 2, true));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dcs), (size_t)n * 4));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dcv), (size_t)n * 4));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dst), srows * sizeof(float2), true));
-    VIT_TRY(s.alloc(&dy, (size_t)m * n * 2, true));
-    VIT_TRY(launch_fold_ln(precision, dW, dlw, dlb, db, dwf, dcs, dcv, n, nullptr));
-    VIT_TRY(launch_rowstats_cast(precision, dx, dxc, dst, m, nullptr));
-    CUtensorMap ta, tb, tout;
-    VIT_TRY(make_tmap(&ta, precision, dxc, kDim, m, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&tb, precision, dwf, kDim, n, GEMM_BK, 128));
-    CUtensorMap tout32;
-    VIT_TRY(make_tmap(&tout, precision, dy, n, m, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&tout32, precision, dy, n, m, GEMM_BK, 32));
-    GemmParams p{m, n, kDim, dcv, dy, nullptr, 0, 0};
-    p.colsum = dcs;
-    p.stats_in = dst;
-    p.stats_parts = 1;
-    p.stats_rows = static_cast<int>(srows);
-    if (epilogue == VIT_EPI_BIAS_GELU) VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(precision, ta, tb, tout, tout32, p, sms, nullptr));
-    else VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(precision, ta, tb, tout, tout32, p, sms, nullptr));
-    VIT_TRY(op_end("op_ln_linear"));
-    VIT_TRY(s.download_operand(y, dy, (size_t)m * n, precision));
-    return op_end("op_ln_linear");
-}
-
-int vit_cuda_op_linear_residual_stats(const float* x, const float* W, const float* b, const float* residual, float* y,
-                                      float* y_cast, float* row_sum, float* row_sumsq, int m, int k, int precision) {
-    int sms = 0;
-    VIT_TRY(op_begin(&sms));
-    if (!x || !W || !b || !residual || !y || !y_cast || !row_sum || !row_sumsq || m <= 0 || k <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    Scratch s;
-    void *dx, *dw, *dyc;
-    float *db, *dy;
-    float2* dst;
-    const size_t srows = (static_cast<size_t>(m) + 255) / 256 * 256;
-    VIT_TRY(s.upload_operand(&dx, x, (size_t)m * k, precision));
-    VIT_TRY(s.upload_operand(&dw, W, (size_t)kDim * k, precision));
-    VIT_TRY(s.upload_f32(&db, b, kDim));
-    VIT_TRY(s.upload_f32(&dy, residual, (size_t)m * kDim));
-    VIT_TRY(s.alloc(&dyc, (size_t)m * kDim * 2, true));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dst), 6 * srows * sizeof(float2), true));
-    CUtensorMap ta, tb, tout, tcast;
-    VIT_TRY(make_tmap(&ta, precision, dx, k, m, GEMM_BK, GEMM_BM));
-    VIT_TRY(make_tmap(&tb, precision, dw, k, kDim, GEMM_BK, 128));
-    VIT_TRY(make_tmap_f32(&tout, dy, kDim, m, GEMM_BM));
-    VIT_TRY(make_tmap(&tcast, precision, dyc, kDim, m, GEMM_BK, GEMM_BM));
-    GemmParams p{m, kDim, k, db, dy, dy, 0, 0};
-    p.stats_out = dst;
-    p.stats_rows = static_cast<int>(srows);
-    VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(precision, ta, tb, tout, tcast, p, sms, nullptr));
-    VIT_TRY(op_end("op_linear_residual_stats"));
-    CU_TRY(cudaMemcpy(y, dy, (size_t)m * kDim * 4, cudaMemcpyDeviceToHost));
-    VIT_TRY(s.download_operand(y_cast, dyc, (size_t)m * kDim, precision));
-    std::vector<float2> h(6 * srows);
-    CU_TRY(cudaMemcpy(h.data(), dst, h.size() * sizeof(float2), cudaMemcpyDeviceToHost));
-    for (int r = 0; r < m; ++r) {   // the consumer's summation order (gemm_sm100_staged_kernel, LN consumer)
-        float s1 = 0.f, s2 = 0.f;
-        for (int q = 0; q < 6; ++q) {
-            s1 += h[q * srows + r].x;
-            s2 += h[q * srows + r].y;
-        }
-        row_sum[r] = s1;
-        row_sumsq[r] = s2;
-    }
-    return op_end("op_linear_residual_stats");
-}
-
-int vit_cuda_op_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int precision) {
-    VIT_TRY(op_begin(nullptr));
-    if (!x || !w || !b || !y || rows <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    Scratch s;
-    float *dx, *dw, *db;
-    void* dy;
-    VIT_TRY(s.upload_f32(&dx, x, (size_t)rows * kDim));
-    VIT_TRY(s.upload_f32(&dw, w, kDim));
-    VIT_TRY(s.upload_f32(&db, b, kDim));
-    VIT_TRY(s.alloc(&dy, (size_t)rows * kDim * 2));
-    VIT_TRY(launch_layernorm(precision, dx, dw, db, dy, rows, nullptr));
-    VIT_TRY(op_end("op_layernorm"));
-    VIT_TRY(s.download_operand(y, dy, (size_t)rows * kDim, precision));
-    return op_end("op_layernorm");
-}
-
-static int op_attention_impl(const float* qkv, float* out, int batch, int tokens, int precision,
-                             unsigned long long* trace_out, int trace_len) {
-    int sms = 0;
-    VIT_TRY(op_begin(&sms));
-    if (!qkv || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    if (tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "attention: tokens=%d > %d not supported", tokens, ATTNL_MAX_TOKENS);
-    Scratch s;
-    const size_t rows = (size_t)batch * tokens;
-    const int kpad = (tokens + 15) / 16 * 16;
-    void *dqkv, *dout;
-    {   // Q, K in the operand precision; V in bf16 (as the in_proj epilogue stores it)
-        float* tmp = nullptr;
-        VIT_TRY(s.upload_f32(&tmp, qkv, rows * 3 * kDim));
-        VIT_TRY(s.alloc(&dqkv, rows * 3 * kDim * 2, true));
-        const int grid = static_cast<int>(std::min<size_t>((rows * 3 * kDim + 255) / 256, 148 * 16));
-        if (precision == VIT_PREC_FP16) convert_qkv_from_f32_kernel<__half><<<grid, 256>>>(tmp, static_cast<uint16_t*>(dqkv), rows * 3 * kDim);
-        else convert_qkv_from_f32_kernel<__nv_bfloat16><<<grid, 256>>>(tmp, static_cast<uint16_t*>(dqkv), rows * 3 * kDim);
-        VIT_TRY(check_launch("convert_qkv"));
-        CU_TRY(cudaDeviceSynchronize());
-    }
-    VIT_TRY(s.alloc(&dout, rows * kDim * 2, true));
-    CUtensorMap tq, tkv, tkv32;
-    VIT_TRY(make_tmap(&tq, precision, dqkv, 3 * kDim, rows, ATTN_DH, attention_load_box_rows(tokens)));
-    VIT_TRY(make_tmap_3d(&tkv, precision, dout, kDim, tokens, batch, 128));
-    VIT_TRY(make_tmap_3d(&tkv32, precision, dout, kDim, tokens, batch, 32));
-    AttnParams p{batch, tokens, kpad, dout, 0.125f * 1.4426950408889634f, attn_no_pingpong(), nullptr};
-    constexpr size_t kTraceLen = static_cast<size_t>(ATTN_TRACE_WARPS) * ATTN_TRACE_ITEMS * ATTN_TRACE_EVENTS;
-    if (trace_out) VIT_TRY(s.alloc(reinterpret_cast<void**>(&p.trace), kTraceLen * 8, true));
-    const char* ex = getenv("VIT_ATTN_EXACT");
-    bool exact = ex && atoi(ex) != 0;
-    VIT_TRY(launch_attention(precision, tq, tkv, tkv32, p, sms, nullptr, exact));
-    VIT_TRY(op_end("op_attention"));
-    if (!exact && !trace_out) {  // same contract as vit_cuda_forward: repeat with the exact softmax when flagged
-        bool flagged = false;
-        VIT_TRY(take_attn_range_flag(&flagged));
-        if (flagged) {
-            VIT_TRY(launch_attention(precision, tq, tkv, tkv32, p, sms, nullptr, true));
-            VIT_TRY(op_end("op_attention"));
-        }
-    }
-    if (trace_out)
-        CU_TRY(cudaMemcpy(trace_out, p.trace, std::min(kTraceLen, static_cast<size_t>(std::max(trace_len, 0))) * 8,
-                          cudaMemcpyDeviceToHost));
-    if (out) VIT_TRY(s.download_operand(out, dout, rows * kDim, precision));
-    return op_end("op_attention");
-}
-
-int vit_cuda_op_attention(const float* qkv, float* out, int batch, int tokens, int precision) {
-    if (!out) return set_err(VIT_E_ARG, "bad arguments");
-    return op_attention_impl(qkv, out, batch, tokens, precision, nullptr, 0);
-}
-
-int vit_cuda_debug_attention_trace(const float* qkv, int batch, int tokens, int precision, unsigned long long* trace,
-                                   int trace_len) {
-    if (!trace || trace_len <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    return op_attention_impl(qkv, nullptr, batch, tokens, precision, trace, trace_len);
-}
-
-int vit_cuda_op_embed(const float* images, const float* cls, const float* conv_w, const float* conv_b, const float* pos,
-                      float* out, int batch, int img_size, int precision) {
-    int sms = 0;
-    VIT_TRY(op_begin(&sms));
-    if (!images || !cls || !conv_w || !conv_b || !pos || !out || batch <= 0 || img_size % kPatch) return set_err(VIT_E_ARG, "bad arguments");
-    Scratch s;
-    const int g = img_size / kPatch, patches = g * g, tokens = patches + 1;
-    const size_t img_elems = (size_t)3 * img_size * img_size;
-    float *dimg, *dcls, *dcb, *dpos, *dx;
-    void *dw, *dpatch;
-    VIT_TRY(s.upload_f32(&dimg, images, batch * img_elems));
-    VIT_TRY(s.upload_f32(&dcls, cls, kDim));
-    VIT_TRY(s.upload_f32(&dcb, conv_b, kDim));
-    VIT_TRY(s.upload_f32(&dpos, pos, (size_t)tokens * kDim));
-    VIT_TRY(s.upload_operand(&dw, conv_w, (size_t)kDim * kDim, precision));
-    VIT_TRY(s.alloc(&dpatch, (size_t)batch * patches * kDim * 2, true));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dx), (size_t)batch * tokens * kDim * 4, true));
-    CUtensorMap ta, tb;
-    VIT_TRY(make_tmap(&tb, precision, dw, kDim, kDim, GEMM_BK, 128));
-    VIT_TRY(launch_patchify(precision, dimg, dpatch, batch, img_size, sms, nullptr));
-    if (gemm_impl() == 2) {
-        // the forward pass's path: conv_proj as the per-image EMBED kernel in its LayerNorm-producer form,
-        // class rows (with their copy and statistics) from cls_rows_ln_kernel
-        void* dxc;
-        float2* dst;
-        const size_t srows = ((size_t)batch * tokens + 255) / 256 * 256;
-        VIT_TRY(s.alloc(&dxc, (size_t)batch * tokens * kDim * 2, true));
-        VIT_TRY(s.alloc(reinterpret_cast<void**>(&dst), 6 * srows * sizeof(float2), true));
-        CUtensorMap tx3, txc3, tpos;
-        VIT_TRY(make_tmap_3d(&ta, precision, dpatch, kDim, patches, batch, GEMM_BM));
-        VIT_TRY(make_tmap_3d_f32(&tx3, dx, kDim, tokens, batch, GEMM_BM));
-        VIT_TRY(make_tmap_3d(&txc3, precision, dxc, kDim, tokens, batch, GEMM_BM));
-        VIT_TRY(make_tmap_f32(&tpos, dpos, kDim, tokens, GEMM_BM));
-        if (precision == VIT_PREC_FP16)
-            cls_rows_ln_kernel<__half><<<(batch + 7) / 8, 256>>>(dx, static_cast<__half*>(dxc), dst, (int)srows, dcls, dpos, batch, tokens);
-        else
-            cls_rows_ln_kernel<__nv_bfloat16><<<(batch + 7) / 8, 256>>>(dx, static_cast<__nv_bfloat16*>(dxc), dst, (int)srows, dcls, dpos, batch, tokens);
-        VIT_TRY(check_launch("cls_rows"));
-        GemmParams p{batch * ((patches + 255) / 256) * 256, kDim, kDim, dcb, dx, nullptr, patches, tokens};
-        p.stats_out = dst;
-        p.stats_rows = (int)srows;
-        VIT_TRY(launch_gemm_embed(precision, true, ta, tb, tx3, txc3, tpos, p, sms, nullptr));
-    } else {
-        VIT_TRY(make_tmap(&ta, precision, dpatch, kDim, (uint64_t)batch * patches, GEMM_BK, GEMM_BM));
-        cls_rows_kernel<<<(batch * kDim + 255) / 256, 256>>>(dx, dcls, dpos, batch, tokens);
-        VIT_TRY(check_launch("cls_rows"));
-        GemmParams p{batch * patches, kDim, kDim, dcb, dx, dpos, patches, tokens};
-        VIT_TRY(launch_gemm<EPI_PATCH_EMBED>(precision, ta, tb, p, sms, nullptr));
-    }
-    VIT_TRY(op_end("op_embed"));
-    CU_TRY(cudaMemcpy(out, dx, (size_t)batch * tokens * kDim * 4, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-int vit_cuda_op_head(const float* x, const float* ln_w, const float* ln_b, const float* head_w, const float* head_b,
-                     float* logits, int batch, int tokens) {
-    VIT_TRY(op_begin(nullptr));
-    if (!x || !ln_w || !ln_b || !head_w || !head_b || !logits || batch <= 0 || tokens <= 0) return set_err(VIT_E_ARG, "bad arguments");
-    Scratch s;
-    float *dx, *dlw, *dlb, *dhw, *dhb, *dcls, *dlog;
-    VIT_TRY(s.upload_f32(&dx, x, (size_t)batch * tokens * kDim));
-    VIT_TRY(s.upload_f32(&dlw, ln_w, kDim));
-    VIT_TRY(s.upload_f32(&dlb, ln_b, kDim));
-    VIT_TRY(s.upload_f32(&dhw, head_w, (size_t)kClasses * kDim));
-    VIT_TRY(s.upload_f32(&dhb, head_b, kClasses));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dcls), (size_t)batch * kDim * 4));
-    VIT_TRY(s.alloc(reinterpret_cast<void**>(&dlog), (size_t)batch * kClasses * 4));
-    head_ln_kernel<<<(batch + 7) / 8, 256>>>(dx, dlw, dlb, dcls, batch, tokens);
-    VIT_TRY(check_launch("head_ln"));
-    head_gemm_kernel<<<dim3((kClasses + HEAD_CLASSES - 1) / HEAD_CLASSES, std::min((batch + HEAD_IMGS - 1) / HEAD_IMGS, 32)), 256>>>(dcls, dhw, dhb, dlog, batch, kClasses);
-    VIT_TRY(check_launch("head_gemm"));
-    VIT_TRY(op_end("op_head"));
-    CU_TRY(cudaMemcpy(logits, dlog, (size_t)batch * kClasses * 4, cudaMemcpyDeviceToHost));
-    return 0;
-}
+#include "op_entry.inc"
 
 }  // extern "C"

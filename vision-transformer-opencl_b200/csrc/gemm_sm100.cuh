@@ -5,12 +5,10 @@
 // token-flattened batch: M = images * tokens.  W is the PyTorch [out,in] layout, i.e. already
 // the K-major "B^T" operand.
 //
-// Three kernels live here.  The engine runs everything on the LAST one:
-//   gemm_sm100_kernel         single-CTA 128 x 256 tiles, epilogue straight to global memory   (VIT_GEMM_IMPL=1, A/B reference)
-//   gemm_sm100_pair_kernel    CTA pair (cta_group::2) 256 x 256 tiles, same epilogue            (ditto)
-//   gemm_sm100_staged_kernel  CTA pair, staged TMA-store epilogue, fused bias / exact-erf GELU / fp32 residual, LayerNorm
-//                             folded in (producer + consumer forms), per-image EMBED addressing for conv_proj
-// Common structure (one persistent CTA per SM, warp specialised): a TMA producer (A tile 128x64 and W tile per
+// One kernel: gemm_sm100_staged_kernel -- CTA pair (cta_group::2, 256 x 256 tiles), staged TMA-store epilogue, fused bias /
+// exact-erf GELU / fp32 residual, LayerNorm folded in (producer + consumer forms), per-image EMBED addressing for conv_proj.
+// (Round 1's single-CTA and register-epilogue pair kernels were superseded by it and have been removed.)
+// Structure (one persistent CTA per SM, warp specialised): a TMA producer (A tile 128x64 and W tile per
 // stage, 128B swizzle), ONE thread issuing tcgen05.mma (kind::f16, fp32 accumulators in TMEM, two accumulator
 // stages), tcgen05.commit releasing shared-memory stages and publishing accumulators, and epilogue warps reading
 // the accumulators with tcgen05.ld while the next tile's main loop runs in the other TMEM stage.
@@ -23,17 +21,17 @@ namespace vit {
 enum : int {
     EPI_BIAS = 0,           // out[T]   = acc + bias
     EPI_BIAS_GELU = 1,      // out[T]   = gelu(acc + bias)
-    EPI_BIAS_RESIDUAL = 2,  // out[f32] = residual + acc + bias   (residual may alias out)
-    EPI_PATCH_EMBED = 3     // out[f32][(img*tokens + 1 + p)] = pos[1+p] + acc + bias  (conv_proj rows)
+    EPI_BIAS_RESIDUAL = 2   // out[f32] = residual + acc + bias   (residual may alias out)
 };
 
 struct GemmParams {
     int M, N, K;
     const float* bias;      // [N]
     void* out;              // row-major, leading dimension N
-    const float* residual;  // EPI_BIAS_RESIDUAL: [M][N] fp32; EPI_PATCH_EMBED: pos_embedding [tokens][N]
-    int patches;            // EPI_PATCH_EMBED: patches per image (196 / 576)
-    int tokens;             // EPI_PATCH_EMBED: tokens per image  (197 / 577)
+    const float* residual;  // EPI_BIAS_RESIDUAL: [M][N] fp32
+    int patches;            // EMBED (conv_proj): patches per image (196 / 576)
+    int tokens;             // EMBED (conv_proj): tokens per image  (197 / 577)
+    int grid_w;             // EMBED (conv_proj): patches per image row (14 / 24)
     int bf16_from_col;      // staged EPI_BIAS: output columns >= this are stored as bf16 whatever T is
                             // (the V block of in_proj: attention keeps P and V in bf16); <= 0: never
     // ---- LayerNorm folded into the GEMMs (staged kernel, LN = true), see gemm_sm100_staged_kernel
@@ -46,413 +44,18 @@ struct GemmParams {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int GEMM_MAX_N = 3072;
 constexpr int GEMM_NON_EPI_WARPS = 4;
 
-template <int BN, int STAGES>
-struct GemmSmem {
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BIAS_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = BIAS_OFF + GEMM_MAX_N * 4;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
-    static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
-};
-
-template <typename T, int BN, int STAGES, int EPI_WG, int EPI>
-__global__ void __launch_bounds__((GEMM_NON_EPI_WARPS + 4 * EPI_WG) * 32, 1)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const GemmParams p) {
-    using L = GemmSmem<BN, STAGES>;
-    static_assert(BN % 128 == 0 && BN <= 256, "BN");
-    static_assert(2 * BN <= 512, "two accumulator stages must fit in TMEM");
-    constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    constexpr int COLS_PER_WG = BN / EPI_WG;
-    static_assert(COLS_PER_WG % 32 == 0, "epilogue chunking");
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int tiles_n = p.N / BN;
-    const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
-    const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = p.K / GEMM_BK;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], EPI_WG * 128);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias[i];
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * GEMM_BM;
-                const int n0 = (tile % tiles_n) * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-#pragma unroll
-                    for (int h = 0; h < BN / 128; ++h)  // W maps use 128-row boxes (shared with the pair kernel)
-                        tma_load_2d(sa + L::A_BYTES + h * 128 * GEMM_BK * 2, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0 + h * 128);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<T>(GEMM_BM, BN, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + L::A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_f16(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
-                                 (kb | k) != 0);
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-                umma_commit(&tfull_bar[acc]);
-                if ((acc ^= 1) == 0) acc_phase ^= 1;
-            }
-        }
-    } else if (warp >= GEMM_NON_EPI_WARPS) {
-        // ------------------------------------------------------------ epilogue
-        const int ew = warp - GEMM_NON_EPI_WARPS;
-        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
-        const int wg = ew >> 2;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * GEMM_BM;
-            const int n0 = (tile % tiles_n) * BN + wg * COLS_PER_WG;
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * COLS_PER_WG;
-
-            size_t out_row = static_cast<size_t>(row);
-            const float* res_row = nullptr;
-            if constexpr (EPI == EPI_BIAS_RESIDUAL) {
-                res_row = p.residual + static_cast<size_t>(row) * p.N;
-            } else if constexpr (EPI == EPI_PATCH_EMBED) {
-                const int img = row / p.patches;
-                const int pp = row - img * p.patches;
-                out_row = static_cast<size_t>(img) * p.tokens + 1 + pp;
-                res_row = p.residual + static_cast<size_t>(1 + pp) * p.N;
-            }
-#pragma unroll 1
-            for (int c = 0; c < COLS_PER_WG / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                if (c == COLS_PER_WG / 32 - 1) {  // accumulator is in registers: hand TMEM back
-                    tc_fence_before();
-                    mbar_arrive(&tempty_bar[acc]);
-                }
-                const int col = n0 + c * 32;
-                const float* sb = s_bias + col;
-                if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v0 = __uint_as_float(r[2 * j]) + sb[2 * j];
-                        float v1 = __uint_as_float(r[2 * j + 1]) + sb[2 * j + 1];
-                        if constexpr (EPI == EPI_BIAS_GELU) {
-                            v0 = gelu_erf(v0);
-                            v1 = gelu_erf(v1);
-                        }
-                        packed[j] = pack2<T>(v0, v1);
-                    }
-                    if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + out_row * p.N + col);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                } else {
-                    if (row_ok) {
-                        const float4* rs = reinterpret_cast<const float4*>(res_row + col);
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.N + col);
-                        float4 rv[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rv[j] = rs[j];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 o;
-                            o.x = rv[j].x + (__uint_as_float(r[4 * j + 0]) + sb[4 * j + 0]);
-                            o.y = rv[j].y + (__uint_as_float(r[4 * j + 1]) + sb[4 * j + 1]);
-                            o.z = rv[j].z + (__uint_as_float(r[4 * j + 2]) + sb[4 * j + 2]);
-                            o.w = rv[j].w + (__uint_as_float(r[4 * j + 3]) + sb[4 * j + 3]);
-                            dst[j] = o;
-                        }
-                    }
-                }
-            }
-            if ((acc ^= 1) == 0) acc_phase ^= 1;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
-    }
-}
-
 // =============================================================================================
-// CTA-pair variant (the one the engine uses): two CTAs of a cluster cooperate on a 256 x 256
-// output tile with tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA loads only its own 128 rows
-// of A and its own 128 of the 256 W rows per K block (32 KB per stage instead of 48 KB), which
-// cuts the L2 -> SM operand traffic per FLOP by a third -- the limiter of the single-CTA kernel
-// (ncu: L2 throughput bound at ~50 % tensor-pipe utilisation).  Accumulators: 128 lanes x 256
-// columns per CTA, two stages.  The leader CTA issues all MMAs; completion is multicast to both
-// CTAs' barriers; the peer's epilogue releases accumulator stages by remote mbarrier arrives.
-template <int STAGES>
-struct GemmPairSmem {
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 128 rows of A
-    static constexpr int B_BYTES = 128 * GEMM_BK * 2;       // this CTA's half of the 256 W rows
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BIAS_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = BIAS_OFF + GEMM_MAX_N * 4;
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
-    static constexpr int DYN_BYTES = TOTAL + 1024;
-};
-
-template <typename T, int STAGES, int EPI_WG, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GEMM_NON_EPI_WARPS + 4 * EPI_WG) * 32, 1)
-gemm_sm100_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const GemmParams p) {
-    using L = GemmPairSmem<STAGES>;
-    constexpr int BN = 256;
-    constexpr int COLS_PER_WG = BN / EPI_WG;
-    constexpr int EPI_THREADS = EPI_WG * 128;
-
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1;
-    const int num_pairs = gridDim.x >> 1;
-    const int tiles_n = p.N / BN;
-    const int tiles_m = (p.M + 255) / 256;
-    const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = p.K / GEMM_BK;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
-        tma_prefetch_desc(&tmap_b);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 2 * EPI_THREADS / 32);  // one arrival per epilogue warp of both CTAs (used in the leader)
-        }
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias[i];
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA credit
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m0 = (tile / tiles_n) * 256 + rank * 128;
-                const int n0 = (tile % tiles_n) * BN + rank * 128;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-                    tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-                    tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = make_idesc<T>(256, BN, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + L::A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
-                                      (kb | k) != 0);
-                    umma_commit_pair(&empty_bar[stage], 0x3);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-                umma_commit_pair(&tfull_bar[acc], 0x3);
-                if ((acc ^= 1) == 0) acc_phase ^= 1;
-            }
-        }
-    } else if (warp >= GEMM_NON_EPI_WARPS) {
-        // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-        const int ew = warp - GEMM_NON_EPI_WARPS;
-        const int quarter = warp & 3;
-        const int wg = ew >> 2;
-        const uint32_t tempty_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0);
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            const int m0 = (tile / tiles_n) * 256 + rank * 128;
-            const int n0 = (tile % tiles_n) * BN + wg * COLS_PER_WG;
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < p.M;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + wg * COLS_PER_WG;
-
-            size_t out_row = static_cast<size_t>(row);
-            const float* res_row = nullptr;
-            if constexpr (EPI == EPI_BIAS_RESIDUAL) {
-                res_row = p.residual + static_cast<size_t>(row) * p.N;
-            } else if constexpr (EPI == EPI_PATCH_EMBED) {
-                const int img = row / p.patches;
-                const int pp = row - img * p.patches;
-                out_row = static_cast<size_t>(img) * p.tokens + 1 + pp;
-                res_row = p.residual + static_cast<size_t>(1 + pp) * p.N;
-            }
-#pragma unroll 1
-            for (int c = 0; c < COLS_PER_WG / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                if (c == COLS_PER_WG / 32 - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
-                }
-                const int col = n0 + c * 32;
-                const float* sb = s_bias + col;
-                if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v0 = __uint_as_float(r[2 * j]) + sb[2 * j];
-                        float v1 = __uint_as_float(r[2 * j + 1]) + sb[2 * j + 1];
-                        if constexpr (EPI == EPI_BIAS_GELU) {
-                            v0 = gelu_erf(v0);
-                            v1 = gelu_erf(v1);
-                        }
-                        packed[j] = pack2<T>(v0, v1);
-                    }
-                    if (row_ok) {
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(p.out) + out_row * p.N + col);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    }
-                } else {
-                    if (row_ok) {
-                        const float4* rs = reinterpret_cast<const float4*>(res_row + col);
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_row * p.N + col);
-                        float4 rv[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rv[j] = rs[j];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 o;
-                            o.x = rv[j].x + (__uint_as_float(r[4 * j + 0]) + sb[4 * j + 0]);
-                            o.y = rv[j].y + (__uint_as_float(r[4 * j + 1]) + sb[4 * j + 1]);
-                            o.z = rv[j].z + (__uint_as_float(r[4 * j + 2]) + sb[4 * j + 2]);
-                            o.w = rv[j].w + (__uint_as_float(r[4 * j + 3]) + sb[4 * j + 3]);
-                            dst[j] = o;
-                        }
-                    }
-                }
-            }
-            if ((acc ^= 1) == 0) acc_phase ^= 1;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();  // the peer may still multicast into / read from this CTA's smem until here
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc_pair<512>(tmem_base);
-    }
-}
-
-// =============================================================================================
-// CTA-pair GEMM with a staged epilogue (the kernel the engine uses for in_proj, out_proj, mlp_0
-// and mlp_3).  Main loop as in gemm_sm100_pair_kernel.  The epilogue no longer touches global
-// memory from registers (one thread per row => 32 different cache lines per warp instruction,
-// a latency-bound trickle, ncu profiles/r1_*): the 8 epilogue warps walk the 128 x 256 accumulator
+// CTA-pair GEMM with a staged epilogue (the kernel the engine uses for conv_proj, in_proj, out_proj,
+// mlp_0 and mlp_3).  Main loop: two CTAs of a cluster share one 256 x 256 output tile
+// (tcgen05.mma.cta_group::2, UMMA M = 256); each CTA TMA-loads only its own 128 rows of A and its own
+// 128 of the 256 W rows per K block (32 KB per stage), which cuts the L2 -> SM operand traffic per FLOP
+// by a third against a single-CTA 128 x 256 tile.  The leader CTA issues all MMAs; completion is
+// multicast to both CTAs' barriers; the peer's epilogue releases accumulator stages by remote
+// mbarrier arrives.  The epilogue never touches global memory from registers (one thread per row =>
+// 32 different cache lines per warp instruction, a latency-bound trickle, ncu profiles/r1_*): the
+// 8 epilogue warps walk the 128 x 256 accumulator
 // in column chunks that are exactly one 128-byte-per-row, 128B-swizzled shared-memory slot
 // (64 operand-precision columns, or 32 fp32 columns), and
 //   * results leave through TMA bulk stores issued by one thread per chunk;
@@ -502,17 +105,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GEMM_NON_EPI_WARPS 
 gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_cast,
                          const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
-    // EMBED (conv_proj, EPI_BIAS_RESIDUAL): row tiles never straddle images.  A is the patch matrix seen as
-    // [image][patch][768] (3-D map; an image takes ceil(patches / 256) row tiles, rows past p.patches are
-    // zero-filled), the "residual" is pos_embedding rows 1 + patch (tmap_res, 2-D, shared by all images), and
-    // the output goes to token row 1 + patch of the image through 3-D maps [image][token][768] that clip
-    // at the image's last token -- class_token / pos_emb / flatten_transpose of the reference
-    // (ViT_seq.c:52-101) as pure addressing.  p.M = images * tiles per image * 256.
+    // EMBED (conv_proj, EPI_BIAS_RESIDUAL): the patch embedding WITHOUT an im2col buffer (Conv2d + flatten_transpose +
+    // class_token + pos_emb, ViT_seq.c:25-101).  The A operand is the fp32 image itself, seen through a 5-D TMA map as
+    // [plane = image * 3 + channel][gy][gx][ky][kx]: a box {kx 16, ky 2, gx G, gy R/G, 1 plane} lands in shared memory
+    // as R = (128 / G) * G rows (one per patch, whole patch rows gy of the image) of 2 x 16 fp32 = 128 bytes, 128B-swizzled
+    // -- exactly a K-major operand tile of 32 tf32 K elements (K order (channel, ky, kx) = conv_proj.weight's row order).
+    // The MMA is kind::tf32 on the raw pixels (weights rounded to tf32 once at init).  A CTA's rows are consecutive
+    // patches [gy0 * G, gy0 * G + R) of ONE image: row tiles never straddle images, the "residual" is pos_embedding
+    // rows 1 + patch (tmap_res, 2-D, shared by all images), and the output goes to token row 1 + patch of the image through
+    // 3-D maps [image][token][768] with R-row boxes that clip at the image's last token.  Rows R..127 of the
+    // tile hold stale shared memory; MMA rows are independent and those rows are never stored.
+    // p.M = images * tiles per image * 256; T is the type of the operand-precision copy (LN producer).
     static_assert(!EMBED || EPI == EPI_BIAS_RESIDUAL, "EMBED is a residual-epilogue variant");
-    const int embed_tpi = EMBED ? (p.patches + 255) / 256 : 1;  // row tiles per image
+    constexpr int BK_ELEMS = EMBED ? 32 : GEMM_BK;               // K elements per 128-byte operand row: tf32 / 16-bit
+    const int embed_gyc = EMBED ? 128 / p.grid_w : 1;            // patch rows (gy) per CTA
+    const int embed_rows = EMBED ? embed_gyc * p.grid_w : 128;   // R: live rows of this CTA's tile
+    const int embed_tpi = EMBED ? (p.grid_w + 2 * embed_gyc - 1) / (2 * embed_gyc) : 1;  // pair tiles per image
     const uint32_t embed_rank = cluster_ctarank();
     auto embed_img = [&](int mt) { return mt / embed_tpi; };
-    auto embed_patch0 = [&](int mt) { return (mt % embed_tpi) * 256 + static_cast<int>(embed_rank) * 128; };  // this CTA's first patch
+    auto embed_gy0 = [&](int mt) { return ((mt % embed_tpi) * 2 + static_cast<int>(embed_rank)) * embed_gyc; };  // this CTA's first patch row
+    auto embed_patch0 = [&](int mt) { return embed_gy0(mt) * p.grid_w; };                                         // ... and first patch
     static_assert((CAST_BUFS > 0) == (LN && EPI == EPI_BIAS_RESIDUAL) && CAST_BUFS <= 2, "staging tiles of the operand-precision copy");
     // STAGED: the tile's parameters are put into shared memory one tile ahead by the loader warp (two buffers);
     // otherwise the epilogue threads load them themselves, from lines they prefetched into L1 a tile earlier.
@@ -555,7 +167,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int tiles_n = p.N / BN;
     const int tiles_m = (p.M + 255) / 256;
     const int num_tiles = tiles_m * tiles_n;
-    const int num_kb = p.K / GEMM_BK;
+    const int num_kb = p.K / BK_ELEMS;
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // swizzle atoms need 1 KB alignment
     if (warp == W_PRODUCER && lane == 0) {
@@ -606,10 +218,12 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-                    if constexpr (EMBED) tma_load_3d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, embed_patch0(tile / tiles_n), embed_img(tile / tiles_n));
-                    else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-                    tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+                    // (a TMA box counts its full size towards the barrier, zero-filled out-of-bounds parts included)
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (EMBED ? embed_rows * 128 + L::B_BYTES : L::STAGE_BYTES));
+                    if constexpr (EMBED)   // K block kb = channel kb / 8, kernel rows ky = 2 (kb % 8) + {0, 1}, all 16 kx
+                        tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
+                    else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK_ELEMS, m0);
+                    tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * BK_ELEMS, n0);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -618,7 +232,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
         if (rank == 0) {
-            constexpr uint32_t idesc = make_idesc<T>(256, BN, 0, 0);
+            constexpr uint32_t idesc = EMBED ? make_idesc_tf32(256, BN) : make_idesc<T>(256, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -634,9 +248,10 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
                         const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k)
-                            umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc,
-                                          (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {   // four K steps of 32 bytes per 128-byte operand row
+                            if constexpr (EMBED) umma_tf32_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
+                            else umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
+                        }
                         umma_commit_pair(&empty_bar[stage], 0x3);
                     }
                     __syncwarp();
@@ -928,7 +543,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if constexpr (kResidual && LN) {
                 if constexpr (EMBED) {
                     const int patch = embed_patch0(tile / tiles_n) + row;
-                    if (patch < p.patches)
+                    if (row < embed_rows && patch < p.patches)
                         p.stats_out[static_cast<size_t>(2 * (tile % tiles_n) + half) * p.stats_rows +
                                     static_cast<size_t>(embed_img(tile / tiles_n)) * p.tokens + 1 + patch] = make_float2(st_sum, st_sq);
                 } else if (m0 + row < p.M)

@@ -1,4 +1,4 @@
-// kernels_misc.cuh -- the HBM-bound kernels around the GEMMs: LayerNorm, patch extraction,
+// kernels_misc.cuh -- the HBM-bound kernels around the GEMMs: LayerNorm,
 // class-token rows, the fp32 classifier head and operand conversion.
 #pragma once
 
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256) fold_ln_weights_kernel(const float* __res
         const float w = W[static_cast<size_t>(n) * kDim + k];
         const T wp = from_float<T>(ln_w[k] * w);
         Wp[static_cast<size_t>(n) * kDim + k] = wp;
+        if (!isfinite(to_float<T>(wp)) && isfinite(ln_w[k] * w)) atomicOr(&g_status_flags, VIT_FLAG_WEIGHT_RANGE);
         s += to_float<T>(wp);
         c = fmaf(ln_b[k], w, c);
     }
@@ -111,39 +112,6 @@ __global__ void __launch_bounds__(256) fold_ln_weights_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// Patch extraction + cast: images [B][3][S][S] fp32 -> patches [B*G*G][768] in operand precision,
-// K order (ic, kh, kw) = the flattened conv_proj.weight row order (Conv2d, ViT_seq.c:33-41), patch
-// index oh*G+ow (flatten_transpose, ViT_seq.c:57-65).  One thread per float4 of the image, reads
-// fully coalesced, writes 8-byte pieces.
-template <typename T, int S_CT>   // S_CT: image size known at compile time (224, 384), or 0 for any size
-__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, T* __restrict__ patches,
-                                                       int batch, int S_rt) {
-    const int S = S_CT ? S_CT : S_rt;
-    const int G = S / 16, S4 = S / 4;
-    // blockIdx.y = image * 3 + channel; two float4 per thread (two loads in flight), no 64-bit divisions
-    const int plane = blockIdx.y;
-    const int bimg = plane / 3, c = plane - bimg * 3;
-    const float4* src = reinterpret_cast<const float4*>(img) + static_cast<size_t>(plane) * S * S4;
-    T* dst_img = patches + static_cast<size_t>(bimg) * G * G * kDim + c * 256;
-    const int n4 = S * S4;
-    const int i0 = (blockIdx.x * 256 + threadIdx.x) * 2;
-    float4 v[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        if (i0 + k < n4) v[k] = __ldcs(src + i0 + k);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int i = i0 + k;
-        if (i >= n4) break;
-        const int yy = i / S4, x = (i - yy * S4) * 4;
-        const int ph = yy >> 4, kh = yy & 15, pw = x >> 4, kw = x & 15;
-        uint2 o;
-        o.x = pack2<T>(v[k].x, v[k].y);
-        o.y = pack2<T>(v[k].z, v[k].w);
-        *reinterpret_cast<uint2*>(dst_img + static_cast<size_t>(ph * G + pw) * kDim + kh * 16 + kw) = o;
-    }
-}
-
 // Class-token rows: X[b*tokens][:] = class_token + pos_embedding[0]  (class_token + pos_emb,
 // ViT_seq.c:72-101).  The patch rows are written by the conv_proj GEMM epilogue.
 __global__ void cls_rows_kernel(float* __restrict__ X, const float* __restrict__ cls, const float* __restrict__ pos,
@@ -329,17 +297,34 @@ __global__ void __launch_bounds__(256) head_gemm_kernel(const float* __restrict_
             if (lane == 0) {
                 if (c0 < classes) logits[static_cast<size_t>(b0 + j) * classes + c0] = a0 + b0v;
                 if (c1 < classes) logits[static_cast<size_t>(b0 + j) * classes + c1] = a1 + b1v;
+                // An FP16 operand that overflowed anywhere upstream is inf, turns the fp32 residual row it feeds into inf / NaN
+                // for good, and reaches the class row through the next attention: it always ends up here.
+                if (!(fabsf(a0 + b0v) <= 3.0e38f) || !(fabsf(a1 + b1v) <= 3.0e38f)) atomicOr(&g_status_flags, VIT_FLAG_NONFINITE);
             }
         }
     }
 }
 
-// fp32 -> operand precision (weights at init, test inputs), and back (test outputs).
+// fp32 -> operand precision (weights at init, test inputs), and back (test outputs).  A finite value that does not
+// fit the operand type (FP16: |w| > 65504) raises VIT_FLAG_WEIGHT_RANGE.
 template <typename T>
 __global__ void convert_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x)
-        dst[i] = from_float<T>(src[i]);
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const T v = from_float<T>(src[i]);
+        dst[i] = v;
+        if (!isfinite(to_float<T>(v)) && isfinite(src[i])) atomicOr(&g_status_flags, VIT_FLAG_WEIGHT_RANGE);
+    }
+}
+// fp32 -> tf32 (round to nearest, ties away: cvt.rna), still stored as fp32: conv_proj.weight for the kind::tf32 MMA,
+// which ignores the 13 low mantissa bits of its operands.
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+        dst[i] = __uint_as_float(r);
+    }
 }
 // packed QKV activation [rows][2304] for the attention operator test: Q, K columns in T, V columns
 // (>= 1536) in bf16 -- the layout the in_proj epilogue produces

@@ -14,6 +14,13 @@ namespace vit {
 // Set (sticky) by any kernel watchdog before it traps; the host reads it after a failed sync.
 __device__ unsigned int g_watchdog_flag = 0;
 
+// Sticky per-device status word the kernels OR into and the host reads back after a pass (engine.cu):
+//   VIT_FLAG_ATTN_RANGE   the single-pass softmax saw a row leave its exponent window (attention_sm100.cuh)
+//   VIT_FLAG_NONFINITE    a logit is not finite (FP16 operand overflow somewhere upstream; kernels_misc.cuh, head_gemm_kernel)
+//   VIT_FLAG_WEIGHT_RANGE a finite fp32 weight became non-finite in the operand precision (convert / fold kernels)
+__device__ unsigned int g_status_flags = 0;
+constexpr unsigned int VIT_FLAG_ATTN_RANGE = 1u, VIT_FLAG_NONFINITE = 2u, VIT_FLAG_WEIGHT_RANGE = 4u;
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -156,6 +163,14 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// 5-D CTA-pair load: conv_proj reads its A operand straight from the fp32 image, seen as
+// [plane = image * 3 + channel][gy][gx][ky][kx] (dims listed outermost first; strides in engine.cu, make_tmap_image5d).
+__device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
@@ -222,6 +237,17 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same for kind::tf32 (fp32 values in shared memory, the low 13 mantissa bits ignored; K = 8 per instruction = 32 bytes,
+// so the shared-memory descriptors advance exactly as for 16-bit operands): conv_proj on the raw fp32 image.
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -372,6 +398,11 @@ template <typename T>
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
     return (1u << 4) | (umma_format<T>::v << 7) | (umma_format<T>::v << 10) | (a_mn_major << 15) |
            (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// kind::tf32: A and B format 2 (tf32), D f32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ small numeric helpers

@@ -60,6 +60,65 @@ ImageData* load_image_data(const char* filename) {
     return images;
 }
 
+/* ---- streaming reader for the same file format: bounded memory, caller-provided (e.g. pinned) buffers ---- */
+struct vit_image_stream {
+    FILE* f;
+    int n, c, h, w, next;
+};
+
+vit_image_stream* vit_image_stream_open(const char* filename, int* n, int* c, int* h, int* w) {
+    FILE* f = fopen(filename, "rb");
+    if (!f) {
+        fprintf(stderr, "vit_image_stream_open: cannot open %s: %s\n", filename, strerror(errno));
+        return NULL;
+    }
+    int32_t header[4];
+    if (fread(header, sizeof(int32_t), 4, f) != 4 || header[0] <= 0 || header[1] <= 0 || header[2] <= 0 || header[3] <= 0) {
+        fprintf(stderr, "vit_image_stream_open: %s: bad header\n", filename);
+        fclose(f);
+        return NULL;
+    }
+    /* the header's image count must be backed by the file (the reference trusts it, Network.c:60-64) */
+    struct stat sb;
+    const size_t need = 16 + (size_t)header[0] * header[1] * header[2] * header[3] * sizeof(float);
+    if (fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode) && (size_t)sb.st_size < need) {
+        fprintf(stderr, "vit_image_stream_open: %s: %lld bytes, header promises %zu\n", filename, (long long)sb.st_size, need);
+        fclose(f);
+        return NULL;
+    }
+    vit_image_stream* s = (vit_image_stream*)calloc(1, sizeof(*s));
+    if (!s) {
+        fclose(f);
+        return NULL;
+    }
+    s->f = f;
+    s->n = header[0], s->c = header[1], s->h = header[2], s->w = header[3];
+    if (n) *n = s->n;
+    if (c) *c = s->c;
+    if (h) *h = s->h;
+    if (w) *w = s->w;
+    return s;
+}
+
+int vit_image_stream_read(vit_image_stream* s, float* dst, int max_images) {
+    if (!s || !dst || max_images < 0) return -1;
+    const int left = s->n - s->next;
+    const int take = left < max_images ? left : max_images;
+    const size_t per = (size_t)s->c * s->h * s->w;
+    if (take > 0 && fread(dst, sizeof(float), per * take, s->f) != per * take) {
+        fprintf(stderr, "vit_image_stream_read: short read at image %d\n", s->next);
+        return -1;
+    }
+    s->next += take;
+    return take;
+}
+
+void vit_image_stream_close(vit_image_stream* s) {
+    if (!s) return;
+    fclose(s->f);
+    free(s);
+}
+
 void free_image_data(ImageData* images) {
     if (!images) return;
     const int n = images[0].n;

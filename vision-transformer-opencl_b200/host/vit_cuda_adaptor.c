@@ -10,12 +10,35 @@
 #include <stdlib.h>
 #include <string.h>
 
-static vit_host_config g_cfg = {1, 256, VIT_PREC_BF16};
+static vit_host_config g_cfg = {1, 256, VIT_PREC_AUTO};
 static int g_cfg_from_env_done = 0;
 static int g_engine_up = 0;
 static int g_engine_img = 0;
 static const Network* g_engine_weights = NULL;
+static uint64_t g_engine_fingerprint = 0;
 static int g_status = 0;
+
+/* The reference hands the same static Network[152] array to every call (Main.c:29,57), so the array's address says
+ * nothing about its contents: a caller that reloads other weights into it must get a new upload.  Fingerprint =
+ * FNV-1a over every tensor's data pointer, size and 64 evenly spaced elements (about 10 k floats, microseconds). */
+static uint64_t weights_fingerprint(const Network* networks) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int i = 0; i < VIT_NUM_TENSORS; ++i) {
+        const uint64_t meta[2] = {(uint64_t)(uintptr_t)networks[i].data, (uint64_t)networks[i].size};
+        for (int k = 0; k < 2; ++k) h = (h ^ meta[k]) * 0x100000001b3ull;
+        if (!networks[i].data || networks[i].size == 0) continue;
+        const size_t step = networks[i].size / 64 ? networks[i].size / 64 : 1;
+        for (size_t j = 0; j < networks[i].size; j += step) {
+            uint32_t bits;
+            memcpy(&bits, &networks[i].data[j], 4);
+            h = (h ^ bits) * 0x100000001b3ull;
+        }
+        uint32_t last;
+        memcpy(&last, &networks[i].data[networks[i].size - 1], 4);
+        h = (h ^ last) * 0x100000001b3ull;
+    }
+    return h;
+}
 
 void vit_host_set_config(const vit_host_config* cfg) {
     if (!cfg) return;
@@ -31,7 +54,11 @@ static void config_from_env(void) {
     const char* s;
     if ((s = getenv("VIT_GPUS")) && atoi(s) > 0) g_cfg.n_gpus = atoi(s);
     if ((s = getenv("VIT_MAX_BATCH")) && atoi(s) > 0) g_cfg.max_batch_per_gpu = atoi(s);
-    if ((s = getenv("VIT_PRECISION")) && strcmp(s, "fp16") == 0) g_cfg.precision = VIT_PREC_FP16;
+    if ((s = getenv("VIT_PRECISION"))) {
+        if (strcmp(s, "fp16") == 0) g_cfg.precision = VIT_PREC_FP16;
+        else if (strcmp(s, "bf16") == 0) g_cfg.precision = VIT_PREC_BF16;
+        else if (strcmp(s, "auto") == 0) g_cfg.precision = VIT_PREC_AUTO;
+    }
 }
 
 int initialize_cuda(void) {
@@ -46,13 +73,18 @@ void Release_cuda(void) {
     vit_cuda_free();
     g_engine_up = 0;
     g_engine_weights = NULL;
+    g_engine_fingerprint = 0;
 }
 
-static void fail(float** prb, int n, const char* what) {
-    fprintf(stderr, "ViT_cuda: %s: %s\n", what, vit_cuda_last_error());
+/* every failure path: message on stderr, prb filled with NaN (the header's promise), never exit() */
+static void fail(float** prb, int n, const char* what, const char* detail) {
+    fprintf(stderr, "ViT_cuda: %s: %s\n", what, detail);
     for (int i = 0; i < n; ++i)
-        for (int j = 0; j < VIT_NUM_CLASSES; ++j) prb[i][j] = NAN;
+        if (prb && prb[i])
+            for (int j = 0; j < VIT_NUM_CLASSES; ++j) prb[i][j] = NAN;
 }
+
+void vit_host_invalidate_weights(void) { g_engine_fingerprint = 0, g_engine_weights = NULL; }
 
 void ViT_cuda(ImageData* image, Network* networks, float** prb) {
     config_from_env();
@@ -60,21 +92,25 @@ void ViT_cuda(ImageData* image, Network* networks, float** prb) {
     const int img = image[0].h;
     g_status = VIT_E_ARG;
     if (n <= 0 || image[0].c != 3 || image[0].h != image[0].w) {
-        fprintf(stderr, "ViT_cuda: unsupported image batch %d x %d x %d x %d\n", n, image[0].c, image[0].h, image[0].w);
+        char msg[128];
+        snprintf(msg, sizeof(msg), "%d x %d x %d x %d", n, image[0].c, image[0].h, image[0].w);
+        fail(prb, n > 0 ? n : 0, "unsupported image batch", msg);
         return;
     }
     /* the reference hands the weights over on every call; upload them once per weight set */
-    if (!g_engine_up || g_engine_img != img || g_engine_weights != networks) {
+    const uint64_t fp = weights_fingerprint(networks);
+    if (!g_engine_up || g_engine_img != img || g_engine_weights != networks || g_engine_fingerprint != fp) {
         if (g_engine_up) vit_cuda_free();
         g_engine_up = 0;
         g_status = vit_cuda_init_ex(networks, VIT_NUM_TENSORS, img, g_cfg.max_batch_per_gpu, g_cfg.n_gpus, NULL, g_cfg.precision);
         if (g_status != 0) {
-            fail(prb, n, "init");
+            fail(prb, n, "init", vit_cuda_last_error());
             return;
         }
         g_engine_up = 1;
         g_engine_img = img;
         g_engine_weights = networks;
+        g_engine_fingerprint = fp;
     }
     /* image[i].data are separate allocations (Network.c:80): the engine gathers them pass by pass into its own
      * pinned staging buffers, overlapped with the kernels of the previous pass */
@@ -84,11 +120,12 @@ void ViT_cuda(ImageData* image, Network* networks, float** prb) {
         free(ptrs);
         free(logits);
         g_status = VIT_E_NOMEM;
+        fail(prb, n, "forward", "out of host memory");
         return;
     }
     for (int i = 0; i < n; ++i) ptrs[i] = image[i].data;
     g_status = vit_cuda_forward_scattered(ptrs, n, logits, NULL);
-    if (g_status != 0) fail(prb, n, "forward");
+    if (g_status != 0) fail(prb, n, "forward", vit_cuda_last_error());
     else
         for (int i = 0; i < n; ++i) vit_softmax(logits + (size_t)i * VIT_NUM_CLASSES, prb[i], VIT_NUM_CLASSES);
     free(ptrs);

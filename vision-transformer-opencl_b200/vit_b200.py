@@ -16,7 +16,9 @@ LIB_PATH = PKG_DIR / "lib" / "libvit_b200.so"
 
 NUM_TENSORS = 152
 NUM_CLASSES = 1000
-PREC_BF16, PREC_FP16 = 0, 1
+PREC_BF16, PREC_FP16, PREC_AUTO = 0, 1, 2
+PREC_NAMES = {0: "bf16", 1: "fp16", 2: "auto"}
+OPT_ATTENTION_EXACT, OPT_CLASS_ROW_PRUNING, OPT_LN_FUSED, OPT_PDL, OPT_GRAPHS, OPT_HOST_THREADS = range(6)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PROF_CATEGORIES = ["patchify", "embed_gemm", "layernorm", "qkv_gemm", "attention", "out_gemm", "fc1_gemm", "fc2_gemm", "head"]
 
@@ -67,6 +69,10 @@ _sig("vit_cuda_free", None)
 _sig("vit_cuda_last_error", C.c_char_p)
 _sig("vit_cuda_launch_count", C.c_longlong)
 _sig("vit_cuda_info", C.c_int, C.POINTER(C.c_longlong), C.c_int)
+_sig("vit_cuda_set_option", C.c_int, C.c_int, C.c_int)
+_sig("vit_cuda_get_option", C.c_int, C.c_int, _i32p)
+_sig("vit_cuda_save_weight_cache", C.c_int, C.c_char_p)
+_sig("vit_cuda_init_from_cache", C.c_int, C.c_char_p, C.c_int, C.c_int, _i32p)
 _sig("vit_cuda_set_attention_exact", C.c_int, C.c_int)
 _sig("vit_cuda_set_class_row_pruning", C.c_int, C.c_int)
 _sig("vit_cuda_timer_start", C.c_int, C.c_int)
@@ -85,7 +91,7 @@ _sig("vit_cuda_op_ln_linear", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
 _sig("vit_cuda_op_linear_residual_stats", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_op_attention", C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_debug_attention_trace", C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int)
-_sig("vit_cuda_op_embed", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
+_sig("vit_cuda_op_embed", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_op_head", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int)
 # ---- include/vit_host.h
 _sig("load_image_data", C.POINTER(ImageData), C.c_char_p)
@@ -176,15 +182,31 @@ def as_network(weights: list[np.ndarray]):
 class Engine:
     """vit_cuda_init / vit_cuda_forward / vit_cuda_free as a context manager."""
 
-    def __init__(self, weights: list[np.ndarray], img_size: int = 224, max_batch: int = 64, n_gpus: int = 1,
-                 device_ids: list[int] | None = None, precision: int = PREC_BF16):
+    def __init__(self, weights: list[np.ndarray] | None, img_size: int = 224, max_batch: int = 64, n_gpus: int = 1,
+                 device_ids: list[int] | None = None, precision: int = PREC_AUTO, cache: str | None = None):
+        """weights: the 152 fp32 tensors (vit_cuda_init_ex), or None with cache = path of a file written by
+        save_weight_cache (vit_cuda_init_from_cache; image size and precision policy come from the file)."""
         self.img_size, self.max_batch, self.n_gpus = img_size, max_batch, n_gpus
-        net = as_network(weights)
         ids = None
         if device_ids is not None:
             ids = (C.c_int * n_gpus)(*device_ids)
-        _check(lib.vit_cuda_init_ex(net, NUM_TENSORS, img_size, max_batch, n_gpus, ids, precision))
+        if weights is None:
+            _check(lib.vit_cuda_init_from_cache(os.fsencode(cache), max_batch, n_gpus, ids))
+        else:
+            net = as_network(weights)
+            _check(lib.vit_cuda_init_ex(net, NUM_TENSORS, img_size, max_batch, n_gpus, ids, precision))
         self._up = True
+
+    def save_weight_cache(self, path: str):
+        _check(lib.vit_cuda_save_weight_cache(os.fsencode(path)))
+
+    def set_option(self, option: int, value: int):
+        _check(lib.vit_cuda_set_option(option, value))
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int()
+        _check(lib.vit_cuda_get_option(option, C.byref(v)))
+        return v.value
 
     def forward(self, images: np.ndarray, want_top1: bool = False):
         n = images.shape[0]
@@ -231,11 +253,14 @@ class Engine:
         return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(PROF_CATEGORIES)}
 
     def info(self) -> dict:
-        v = (C.c_longlong * 11)()
-        _check(lib.vit_cuda_info(v, 11))
+        v = (C.c_longlong * 14)()
+        _check(lib.vit_cuda_info(v, 14))
         keys = ["sm_count", "cc_major", "cc_minor", "max_batch", "tokens", "precision", "n_gpus", "workspace_mib",
-                "attention_exact", "attention_fallbacks", "class_row_pruning"]
-        return dict(zip(keys, [int(x) for x in v]))
+                "attention_exact", "attention_fallbacks", "class_row_pruning", "precision_policy", "precision_fallbacks", "weights_mib"]
+        d = dict(zip(keys, [int(x) for x in v]))
+        d["precision"] = PREC_NAMES[d["precision"]]            # the operand type the next pass runs in
+        d["precision_policy"] = PREC_NAMES[d["precision_policy"]]
+        return d
 
     def set_class_row_pruning(self, on: bool):
         """Last layer: everything behind the attention for the class rows only (default on)."""
@@ -347,11 +372,15 @@ def attention_trace(qkv, batch, tokens, precision=PREC_BF16):
     return tr
 
 
-def op_embed(images, cls, conv_w, conv_b, pos, precision=PREC_BF16):
+def op_embed(images, cls, conv_w, conv_b, pos, precision=PREC_BF16, want_cast=False):
+    """conv_proj (tf32, straight from the fp32 image) + class token + position embedding; want_cast: also the
+    operand-precision copy of the rows that the kernel emits for the first LayerNorm-folded GEMM."""
     batch, _, s, _ = images.shape
     out = np.empty((batch * tokens_for(s), 768), dtype=np.float32)
-    _check(lib.vit_cuda_op_embed(fptr(images), fptr(cls), fptr(conv_w), fptr(conv_b), fptr(pos), fptr(out), batch, s, precision))
-    return out
+    cast = np.empty_like(out) if want_cast else None
+    _check(lib.vit_cuda_op_embed(fptr(images), fptr(cls), fptr(conv_w), fptr(conv_b), fptr(pos), fptr(out),
+                                 fptr(cast) if want_cast else None, batch, s, precision))
+    return (out, cast) if want_cast else out
 
 
 def op_head(x, ln_w, ln_b, head_w, head_b, batch, tokens):
