@@ -32,6 +32,7 @@ struct GemmParams {
     int patches;            // EMBED (conv_proj): patches per image (196 / 576)
     int tokens;             // EMBED (conv_proj): tokens per image  (197 / 577)
     int grid_w;             // EMBED (conv_proj): patches per image row (14 / 24)
+    int embed_variant;      // EMBED: 0 = one {16, 2, G, R/G} box per K block into 128B-swizzled rows; 1 = two {16, 1, G, R/G} boxes into 64B-swizzled sub-tiles
     int bf16_from_col;      // staged EPI_BIAS: output columns >= this are stored as bf16 whatever T is
                             // (the V block of in_proj: attention keeps P and V in bf16); <= 0: never
     // ---- LayerNorm folded into the GEMMs (staged kernel, LN = true), see gemm_sm100_staged_kernel
@@ -220,9 +221,14 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     // (a TMA box counts its full size towards the barrier, zero-filled out-of-bounds parts included)
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (EMBED ? embed_rows * 128 + L::B_BYTES : L::STAGE_BYTES));
-                    if constexpr (EMBED)   // K block kb = channel kb / 8, kernel rows ky = 2 (kb % 8) + {0, 1}, all 16 kx
-                        tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
-                    else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK_ELEMS, m0);
+                    if constexpr (EMBED) {   // K block kb = channel kb / 8, kernel rows ky = 2 (kb % 8) + {0, 1}, all 16 kx
+                        if (p.embed_variant == 0) {
+                            tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
+                        } else {   // one 64-byte-row sub-tile (8 KB) per kernel row ky
+                            tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
+                            tma_load_5d_pair(sa + 8192, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2 + 1, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
+                        }
+                    } else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK_ELEMS, m0);
                     tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * BK_ELEMS, n0);
                 }
                 __syncwarp();
@@ -249,7 +255,11 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {   // four K steps of 32 bytes per 128-byte operand row
-                            if constexpr (EMBED) umma_tf32_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
+                            if constexpr (EMBED) {
+                                const uint64_t adesc = p.embed_variant == 0 ? desc_kmajor_sw128(a_addr, k)
+                                                                            : make_smem_desc(a_addr + (k >> 1) * 8192u + (k & 1) * 32u, 16u, 512u, kLayoutSw64);
+                                umma_tf32_pair(d_tmem, adesc, desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
+                            }
                             else umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
                         }
                         umma_commit_pair(&empty_bar[stage], 0x3);

@@ -360,7 +360,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Shared-memory matrix descriptor (tcgen05 "version 1"), fields in 16-byte units:
 //   [0,14) start address, [16,30) leading byte offset, [32,46) stride byte offset,
 //   [46,48) version = 1, [49,52) base offset, [61,64) layout (0 none, 2 = 128B swizzle).
-constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2;
+constexpr uint32_t kLayoutNone = 0, kLayoutSw128 = 2, kLayoutSw64 = 4;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout) {
     uint64_t d = 0;
@@ -442,28 +442,6 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return y;
 }
 
-// GELU with the exact (erf) definition the reference uses, 0.5*x*(1+erf(x/sqrt 2))
-// (ViT_seq.c:231-233).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32
-// round-off level) on two MUFU ops instead of libdevice erff's branchy ~25 instructions:
-// the mlp_0 epilogue applies this to 3072 values per token and must hide under the MMA.
-__device__ __forceinline__ float gelu_erf(float x) {
-    // With z = |x|/sqrt2, t = 1/(1 + p z), erfc(z) = poly(t) * exp(-z^2):
-    //   gelu(x) = max(x, 0) - |x| * [0.5 * poly(t)] * exp2(-(x * sqrt(log2e / 2))^2)
-    // (for x < 0 this is 0.5 x erfc(|z|), for x > 0 it is x - 0.5 x erfc(z)); the 0.5 is folded into
-    // the coefficients.  10 FMA-pipe + 2 MUFU + 1 ALU instruction, no cancellation at either tail.
-    const float ax = fabsf(x);
-    const float t = fast_rcp(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.0f));
-    const float u = x * 0.84932180028801904f;  // sqrt(log2(e) / 2)
-    const float e = fast_exp2(-(u * u));
-    float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-    q = fmaf(q, t, 0.5f * 1.421413741f);
-    q = fmaf(q, t, 0.5f * -0.284496736f);
-    q = fmaf(q, t, 0.5f * 0.254829592f);
-    const float pe = q * (t * e);
-    return fmaf(-ax, pe, fmaxf(x, 0.0f));
-}
-
-
 // ------------------------------------------------------------------ packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2)
 // One instruction issue does two IEEE fp32 operations (same rounding as the scalar forms); the GELU and
 // softmax epilogues are bound by issue slots, not by the FMA pipe.
@@ -485,21 +463,26 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
-// gelu_erf on two values: the same operations in the same order as the scalar form above (bit-identical
-// results), with the fp32 multiplies / FMAs issued in pairs.
+// GELU with the exact (erf) definition the reference uses, 0.5*x*(1+erf(x/sqrt 2)) (ViT_seq.c:231-233), on two values.
+// With z = |x|/sqrt2 and t = 1/(1 + p z), Abramowitz-Stegun 7.1.25 gives erfc(z) = (a1 t + a2 t^2 + a3 t^3) exp(-z^2)
+// with |error| <= 2.5e-5, and
+//     gelu(x) = 0.5 x + |x| * (0.5 - 0.5 erfc(z))
+// (x > 0: x - 0.5 x erfc;  x < 0: 0.5 x erfc(|z|)).  Measured against the fp64 definition over [-12, 12]: max |error| 2.6e-5,
+// i.e. below the half-ulp of the FP16 / BF16 value it is rounded to wherever |gelu| > 0.06, and 100x inside the operator
+// test's 3e-4.  Cost per PAIR of values: 9 packed FMA-pipe instructions + 4 MUFU (rcp, ex2) + 2 ALU -- the mlp_0 epilogue
+// applies this to 3072 values per token under the MMA of the next tile, and every instruction it does not issue is power
+// the tensor pipe gets instead (round 1's five-term 7.1.26 form: 12 + 4 + 4; mlp_0 ran 110 us per launch behind mlp_3).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
-    const float2 nax = make_float2(__uint_as_float(__float_as_uint(x.x) | 0x80000000u), __uint_as_float(__float_as_uint(x.y) | 0x80000000u));  // -|x|
-    const float2 d = fma2(nax, splat2(-(0.3275911f * 0.70710678118654752f)), splat2(1.0f));
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 d = fma2(ax, splat2(0.47047f * 0.70710678118654752f), splat2(1.0f));
     const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
-    const float2 u = mul2(x, splat2(0.84932180028801904f));
+    const float2 u = mul2(x, splat2(0.84932180028801904f));  // sqrt(log2(e) / 2): exp(-x^2 / 2) = 2^-(u^2)
     const float2 w = mul2(u, u);
     const float2 e = make_float2(fast_exp2(-w.x), fast_exp2(-w.y));
-    float2 q = fma2(splat2(0.5f * 1.061405429f), t, splat2(0.5f * -1.453152027f));
-    q = fma2(q, t, splat2(0.5f * 1.421413741f));
-    q = fma2(q, t, splat2(0.5f * -0.284496736f));
-    q = fma2(q, t, splat2(0.5f * 0.254829592f));
-    const float2 pe = mul2(q, mul2(t, e));
-    return fma2(nax, pe, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+    float2 q = fma2(splat2(-0.5f * 0.7478556f), t, splat2(-0.5f * -0.0958798f));   // -0.5 (a3 t + a2) ...
+    q = fma2(q, t, splat2(-0.5f * 0.3480242f));                                     // ... t + a1): -0.5 erfc / (t e)
+    const float2 r = fma2(q, mul2(t, e), splat2(0.5f));                             // 0.5 - 0.5 erfc(z)  in [0, 0.5)
+    return fma2(ax, r, mul2(x, splat2(0.5f)));
 }
 
 }  // namespace vit
