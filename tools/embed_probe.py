@@ -56,7 +56,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         probe(int(sys.argv[1]))
     else:
-        for variant in ("0", "1"):
-            for S in ("224", "384", "32"):
-                print(f"== VIT_EMBED_VARIANT={variant}, {S}x{S}", flush=True)
-                subprocess.run([sys.executable, __file__, S], env=dict(os.environ, VIT_EMBED_VARIANT=variant))
+        for S in ("224", "384", "32"):
+            print(f"== {S}x{S}", flush=True)
+            subprocess.run([sys.executable, __file__, S])

@@ -118,18 +118,14 @@ int make_tmap_3d_f32(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1,
 }
 // The fp32 images [nb][3][S][S] as the A operand of conv_proj (no im2col buffer): dimensions, innermost first,
 // kx (16, contiguous), ky (16, stride S), gx (G, stride 16), gy (G, stride 16 S), plane = image * 3 + channel
-// (stride S * S).  A box {16, 2, G, 128 / G, 1} is (128 / G) * G patch rows of 2 x 16 pixels = 128 bytes each.
-int embed_variant() {   // TEMPORARY (bring-up): VIT_EMBED_VARIANT selects the A-operand staging of conv_proj
-    const char* s = getenv("VIT_EMBED_VARIANT");
-    return s ? atoi(s) : 0;
-}
+// (stride S * S).  A box {16, 1, G, 128 / G, 1} is one kernel row (16 pixels = 64 bytes, 64B swizzle) of (128 / G) * G
+// patches; the kernel loads two of them per K block (gemm_sm100_staged_kernel, EMBED).
 int make_tmap_image5d(CUtensorMap* m, const float* images, int S, int nb) {
     const uint64_t G = S / kPatch, gyc = 128 / G;
     const cuuint64_t dims[5] = {16, 16, G, G, static_cast<cuuint64_t>(3) * nb};
     const cuuint64_t strides[4] = {static_cast<cuuint64_t>(S) * 4, 16 * 4, static_cast<cuuint64_t>(16) * S * 4, static_cast<cuuint64_t>(S) * S * 4};
-    const bool v1 = embed_variant() == 1;
-    const cuuint32_t box[5] = {16, v1 ? 1u : 2u, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(gyc), 1};
-    return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, images, dims, strides, box, v1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    const cuuint32_t box[5] = {16, 1, static_cast<cuuint32_t>(G), static_cast<cuuint32_t>(gyc), 1};
+    return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, images, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 // rows of a conv_proj CTA tile = box rows of its 3-D store maps (gemm_sm100_staged_kernel, EMBED)
 int embed_rows_per_cta(int S) { return (128 / (S / kPatch)) * (S / kPatch); }
@@ -830,7 +826,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
     }
     {   // conv_proj: tf32 GEMM straight from the fp32 image; class_token offset / pos_emb / token layout are TMA addressing
         ProfScope ps(c, pf, VIT_PROF_EMBED_GEMM);
-        GemmParams p{nb * embed_tiles_per_image(e.img) * 256, kDim, kDim, c.conv_b, c.x, nullptr, e.patches, e.tokens, e.grid, embed_variant()};
+        GemmParams p{nb * embed_tiles_per_image(e.img) * 256, kDim, kDim, c.conv_b, c.x, nullptr, e.patches, e.tokens, e.grid};
         if (fused) {
             p.stats_out = c.pstats;
             p.stats_rows = stats_rows;
@@ -848,7 +844,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
         }
         {
             ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
-            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 0, 0, 2 * kDim};  // V block stored as bf16
+            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 0, 2 * kDim};  // V block stored as bf16
             if (fused) {
                 p.bias = L.qkv_c;
                 p.colsum = W.qkv_s;

@@ -32,7 +32,6 @@ struct GemmParams {
     int patches;            // EMBED (conv_proj): patches per image (196 / 576)
     int tokens;             // EMBED (conv_proj): tokens per image  (197 / 577)
     int grid_w;             // EMBED (conv_proj): patches per image row (14 / 24)
-    int embed_variant;      // EMBED: 0 = one {16, 2, G, R/G} box per K block into 128B-swizzled rows; 1 = two {16, 1, G, R/G} boxes into 64B-swizzled sub-tiles
     int bf16_from_col;      // staged EPI_BIAS: output columns >= this are stored as bf16 whatever T is
                             // (the V block of in_proj: attention keeps P and V in bf16); <= 0: never
     // ---- LayerNorm folded into the GEMMs (staged kernel, LN = true), see gemm_sm100_staged_kernel
@@ -65,6 +64,7 @@ constexpr int GEMM_NON_EPI_WARPS = 4;
 //     residual stream move as full 128-byte rows, asynchronously, under the next tile's MMAs.
 // Slots form a ring shared by loader, epilogue warps and the storing thread.
 constexpr int GEMM_SLOT_BYTES = 128 * 128;
+constexpr int EMBED_SUBTILE_BYTES = 128 * 64;   // conv_proj A operand: 128 rows of 16 tf32 (one kernel row of a patch)
 
 // PRE_BYTES: per-tile parameters staged one tile ahead by the loader warp of the non-residual kernels
 // (bias, and for the LayerNorm consumer the column sums and the 128 rows' (rstd, -rstd * mean)), two buffers.
@@ -108,14 +108,18 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
     // EMBED (conv_proj, EPI_BIAS_RESIDUAL): the patch embedding WITHOUT an im2col buffer (Conv2d + flatten_transpose +
     // class_token + pos_emb, ViT_seq.c:25-101).  The A operand is the fp32 image itself, seen through a 5-D TMA map as
-    // [plane = image * 3 + channel][gy][gx][ky][kx]: a box {kx 16, ky 2, gx G, gy R/G, 1 plane} lands in shared memory
-    // as R = (128 / G) * G rows (one per patch, whole patch rows gy of the image) of 2 x 16 fp32 = 128 bytes, 128B-swizzled
-    // -- exactly a K-major operand tile of 32 tf32 K elements (K order (channel, ky, kx) = conv_proj.weight's row order).
-    // The MMA is kind::tf32 on the raw pixels (weights rounded to tf32 once at init).  A CTA's rows are consecutive
-    // patches [gy0 * G, gy0 * G + R) of ONE image: row tiles never straddle images, the "residual" is pos_embedding
-    // rows 1 + patch (tmap_res, 2-D, shared by all images), and the output goes to token row 1 + patch of the image through
-    // 3-D maps [image][token][768] with R-row boxes that clip at the image's last token.  Rows R..127 of the
-    // tile hold stale shared memory; MMA rows are independent and those rows are never stored.
+    // [plane = image * 3 + channel][gy][gx][ky][kx]: a box {kx 16, ky 1, gx G, gy R/G, 1 plane} lands in shared memory
+    // as R = (128 / G) * G rows (one per patch, whole patch rows gy of the image) of 16 fp32 = 64 bytes, 64B-swizzled --
+    // a K-major operand sub-tile of 16 tf32 K elements.  Two such boxes (kernel rows ky, ky + 1) make one K block of 32,
+    // matching the 128-byte rows of the weight tile (K order (channel, ky, kx) = conv_proj.weight's row order); the A and B
+    // descriptors of an MMA carry their own swizzle modes.  (Measured on the hardware, tools/embed_probe.py: ONE box
+    // {16, 2, G, R/G} under the 128B swizzle does NOT give 128-byte rows -- a box whose inner extent is 64 bytes keeps a
+    // 128-byte row pitch and leaves the second half of every row unwritten.)  The MMA is kind::tf32 on the raw pixels
+    // (weights rounded to tf32 once at init).  A CTA's rows are consecutive patches [gy0 * G, gy0 * G + R) of ONE
+    // image: row tiles never straddle images, the "residual" is pos_embedding rows 1 + patch (tmap_res, 2-D, shared by all
+    // images), and the output goes to token row 1 + patch of the image through 3-D maps [image][token][768] with R-row
+    // boxes that clip at the image's last token.  Rows R..127 of the tile hold stale shared memory; MMA rows are
+    // independent and those rows are never stored.
     // p.M = images * tiles per image * 256; T is the type of the operand-precision copy (LN producer).
     static_assert(!EMBED || EPI == EPI_BIAS_RESIDUAL, "EMBED is a residual-epilogue variant");
     constexpr int BK_ELEMS = EMBED ? 32 : GEMM_BK;               // K elements per 128-byte operand row: tf32 / 16-bit
@@ -221,13 +225,12 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     // (a TMA box counts its full size towards the barrier, zero-filled out-of-bounds parts included)
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (EMBED ? embed_rows * 128 + L::B_BYTES : L::STAGE_BYTES));
-                    if constexpr (EMBED) {   // K block kb = channel kb / 8, kernel rows ky = 2 (kb % 8) + {0, 1}, all 16 kx
-                        if (p.embed_variant == 0) {
-                            tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
-                        } else {   // one 64-byte-row sub-tile (8 KB) per kernel row ky
-                            tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
-                            tma_load_5d_pair(sa + 8192, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2 + 1, 0, embed_gy0(tile / tiles_n), embed_img(tile / tiles_n) * 3 + (kb >> 3));
-                        }
+                    if constexpr (EMBED) {
+                        // K block kb = channel kb / 8, kernel rows ky = 2 (kb % 8) + {0, 1}, all 16 kx: one sub-tile per kernel row
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            tma_load_5d_pair(sa + h * EMBED_SUBTILE_BYTES, &tmap_a, &full_bar[stage], 0, (kb & 7) * 2 + h, 0, embed_gy0(tile / tiles_n),
+                                             embed_img(tile / tiles_n) * 3 + (kb >> 3));
                     } else tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK_ELEMS, m0);
                     tma_load_2d_pair(sa + L::A_BYTES, &tmap_b, &full_bar[stage], kb * BK_ELEMS, n0);
                 }
@@ -255,11 +258,8 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {   // four K steps of 32 bytes per 128-byte operand row
-                            if constexpr (EMBED) {
-                                const uint64_t adesc = p.embed_variant == 0 ? desc_kmajor_sw128(a_addr, k)
-                                                                            : make_smem_desc(a_addr + (k >> 1) * 8192u + (k & 1) * 32u, 16u, 512u, kLayoutSw64);
-                                umma_tf32_pair(d_tmem, adesc, desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
-                            }
+                            if constexpr (EMBED)   // A: K steps 0, 1 in the first 64B-swizzled sub-tile, 2, 3 in the second; B: 128B-swizzled rows
+                                umma_tf32_pair(d_tmem, desc_kmajor_sw64(a_addr + (k >> 1) * EMBED_SUBTILE_BYTES, k & 1), desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
                             else umma_f16_pair(d_tmem, desc_kmajor_sw128(a_addr, k), desc_kmajor_sw128(b_addr, k), idesc, (kb | k) != 0);
                         }
                         umma_commit_pair(&empty_bar[stage], 0x3);

@@ -377,6 +377,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t tile_addr, uint32_t k_step) {
     return make_smem_desc(tile_addr + k_step * 32u, 16u, 1024u, kLayoutSw128);
 }
+// K-major operand tile stored as rows of 64 bytes with 64B swizzle (TMA box {64 bytes, rows}, CU_TENSOR_MAP_SWIZZLE_64B,
+// 512B-aligned): 8-row groups are 512 B apart; a K step of 32 bytes is half a row.
+__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t tile_addr, uint32_t k_step) {
+    return make_smem_desc(tile_addr + k_step * 32u, 16u, 512u, kLayoutSw64);
+}
 // MN-major operand (e.g. V[key][dh] used as B with N = dh = 64, K = keys): rows of 128 bytes
 // are K indices, 8-row groups 1024 B apart (SBO); one 64-wide MN atom so LBO is unused.
 // Stepping K by 16 keys adds 2048 B.
