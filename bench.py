@@ -11,6 +11,7 @@ weights replicated, no collective on the data path).  Under torchrun (N > 1) eve
 GPU; torch.distributed is used only for the barrier and the max-over-ranks reduction.
 """
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -21,6 +22,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "vision-transformer-opencl_b200"))
+faulthandler.enable()      # a native crash prints the Python stack to stderr instead of dying silently
 
 import numpy as np
 

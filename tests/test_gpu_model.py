@@ -306,6 +306,7 @@ def test_precision_auto_falls_back_to_bf16_on_fp16_overflow(vit, oracle, weights
         got = eng.forward(imgs)
         info = eng.info()
         assert info["precision_policy"] == "auto" and info["precision_fallbacks"] == 1 and info["precision"] == "fp16", info
+        assert info["attention_fallbacks"] == 0 and info["attention_exact"] == 0, info    # the softmax was not the cause
         for _ in range(2):
             assert np.array_equal(eng.forward(imgs), want)
         assert eng.info()["precision_fallbacks"] == 3 and eng.info()["precision"] == "bf16"   # needed three times: stays on BF16
@@ -318,17 +319,24 @@ def test_precision_auto_falls_back_to_bf16_on_fp16_overflow(vit, oracle, weights
     with vit.Engine(w, 224, max_batch=4) as eng:      # device-resident API
         d_imgs, d_logits = vit.dev_alloc(0, imgs.nbytes), vit.dev_alloc(0, 4 * 1000 * 4)
         vit.dev_upload(0, d_imgs, imgs)
-        eng.enqueue_device(d_imgs, 4, d_logits)
-        with pytest.raises(vit.VitCudaError) as ei:
-            eng.sync()
-        assert ei.value.code == -6 and "BF16" in str(ei.value)
-        eng.enqueue_device(d_imgs, 4, d_logits)
-        eng.sync()
+        # NaN rows also trip the softmax's range check, so the engine may first try the exact softmax (VIT_E_RANGE #1), find
+        # the logits still non-finite, take that switch back and move to BF16 (VIT_E_RANGE #2); then the pass stands
+        messages = []
+        for _ in range(4):
+            eng.enqueue_device(d_imgs, 4, d_logits)
+            try:
+                eng.sync()
+                break
+            except vit.VitCudaError as ex:
+                assert ex.code == -6
+                messages.append(str(ex))
+        assert 1 <= len(messages) <= 2 and "BF16" in messages[-1], messages
         out = np.empty((4, 1000), dtype=np.float32)
         vit.dev_download(0, out, d_logits)
         vit.dev_free(0, d_imgs)
         vit.dev_free(0, d_logits)
-        assert eng.info()["precision"] == "bf16"
+        info = eng.info()
+        assert info["precision"] == "bf16" and info["attention_exact"] == 0 and info["attention_fallbacks"] == 0, info
     assert np.array_equal(out, want)
     big = [a.copy() for a in weights224]
     big[4 + 12 * 3 + 4][5] = 1.0e6                     # layer 3 out_proj.weight: not representable in FP16
@@ -450,7 +458,7 @@ def test_single_pass_softmax_matches_exact_and_falls_back(vit, weights224, ref16
     wild[6][:1536 * 768] *= 16.0   # layer 0 in_proj (flat [2304][768]): Q and K rows -> scores x 256
     with vit.Engine(wild, 224, max_batch=8) as eng:
         got = eng.forward(imgs)
-        assert eng.info()["attention_fallbacks"] == 1
+        assert eng.info()["attention_fallbacks"] == 1 and eng.info()["precision_fallbacks"] == 0 and eng.info()["precision"] == "fp16"
         eng.set_attention_exact(True)
         want = eng.forward(imgs)
     assert np.isfinite(got).all() and np.array_equal(got, want)

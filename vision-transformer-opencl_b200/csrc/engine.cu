@@ -502,6 +502,7 @@ struct Engine {
     int policy = VIT_PREC_AUTO;     // what the caller asked for
     int prec = VIT_PREC_FP16;       // operand precision of the next pass (VIT_PREC_BF16 / VIT_PREC_FP16)
     bool resident[2] = {false, false};   // which operand sets the arena holds
+    bool exact_on_trial = false;         // vit_cuda_sync switched to the exact softmax when BOTH flags were up (see decide_retry)
     std::vector<DeviceCtx> ctx;
 };
 Engine g_eng;
@@ -1004,6 +1005,31 @@ int collect_flags(DeviceCtx& c, unsigned int* flags) {
     return 0;
 }
 
+// What to do about the flags a pass (enqueued in mode `used`) came back with.  Both causes produce both symptoms: a softmax
+// that overflowed makes logits non-finite, and an FP16 operand that overflowed puts NaN rows into the attention, whose row
+// sums then trip the softmax's range check.  So when both flags are up the exact softmax is tried FIRST, on trial; if the
+// logits are still non-finite afterwards, it was the FP16 range: the softmax switch is taken back and the BF16 operand set is
+// used instead.  Returns 1 if the work must be repeated (mode switched), 0 if the results stand, < 0 on a hard error.
+int decide_retry(Engine& e, unsigned int flags, const PassMode& used, bool* exact_on_trial) {
+    const bool attn = (flags & VIT_FLAG_ATTN_RANGE) && !used.attn_exact;
+    const bool fp16_nonfinite = (flags & VIT_FLAG_NONFINITE) && used.prec == VIT_PREC_FP16;
+    if (attn) {
+        g_opt.attn_exact = 1;
+        *exact_on_trial = fp16_nonfinite;
+        return 1;
+    }
+    if (fp16_nonfinite) {
+        if (*exact_on_trial) g_opt.attn_exact = 0;   // the exact softmax did not cure it
+        *exact_on_trial = false;
+        if (e.policy == VIT_PREC_FP16)
+            return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow): use VIT_PREC_AUTO or VIT_PREC_BF16");
+        e.prec = VIT_PREC_BF16;
+        return 1;
+    }
+    *exact_on_trial = false;
+    return 0;
+}
+
 void read_env_options() {
     g_opt.attn_exact = env_flag("VIT_ATTN_EXACT", 0);
     g_opt.prune_last = env_flag("VIT_PRUNE_LAST", 1);
@@ -1242,21 +1268,24 @@ int vit_cuda_sync(int gpu_slot) {
     if (!check) return 0;
     unsigned int flags = 0;
     VIT_TRY(collect_flags(c, &flags));
-    if (flags & VIT_FLAG_ATTN_RANGE) {
-        g_opt.attn_exact = 1;  // device-resident callers re-enqueue; the engine stays on the exact softmax
-        ++e.attn_fallbacks;
+    // the mode the flagged work was enqueued in: the engine's current one (a caller that changes options between enqueue
+    // and sync gets the conservative reading)
+    const PassMode used = current_mode(e);
+    const bool exact_before = used.attn_exact;
+    const int prec_before = e.prec;
+    const int again = decide_retry(e, flags, used, &e.exact_on_trial);
+    if (again < 0) return again;
+    if (again == 0) return 0;
+    if (!exact_before && g_opt.attn_exact.load()) {
+        ++e.attn_fallbacks;   // device-resident callers re-enqueue; the engine stays on the exact softmax
         return set_err(VIT_E_RANGE, "attention: a row's scores left the single-pass softmax's exponent window; every pass enqueued on slot %d "
                                     "since its last sync is invalid.  The engine has switched to the exact two-pass softmax: enqueue them again", gpu_slot);
     }
-    if (flags & VIT_FLAG_NONFINITE) {
-        if (e.policy == VIT_PREC_AUTO && e.prec == VIT_PREC_FP16) {
-            e.prec = VIT_PREC_BF16;
-            ++e.prec_fallbacks;
-            return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow): every pass enqueued on slot %d since its last sync is "
-                                        "invalid.  The engine has switched to BF16 operands: enqueue them again", gpu_slot);
-        }
-        if (e.policy == VIT_PREC_FP16)
-            return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow) on slot %d: use VIT_PREC_AUTO or VIT_PREC_BF16", gpu_slot);
+    if (prec_before == VIT_PREC_FP16 && e.prec == VIT_PREC_BF16) {
+        if (exact_before && !g_opt.attn_exact.load()) --e.attn_fallbacks;   // the softmax switch was on trial and is taken back
+        ++e.prec_fallbacks;
+        return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow): every pass enqueued on slot %d since its last sync is "
+                                    "invalid.  The engine has switched to BF16 operands: enqueue them again", gpu_slot);
     }
     return 0;
 }
@@ -1485,29 +1514,29 @@ int forward_host(const float* images_nchw, const float* const* image_ptrs, int n
     if (!logits_out || n < 0) return set_err(VIT_E_ARG, "bad arguments");
     if (n == 0) return 0;
     // A flagged call is repeated: with the exact two-pass softmax (a row left the single-pass softmax's exponent window)
-    // and / or, under VIT_PREC_AUTO, with the BF16 operand set (an FP16 operand overflowed -- 8-bit exponent instead of 5).
-    // Either switch becomes permanent once it has been needed in three calls: the data evidently does it regularly.
-    bool temp_exact = false, temp_bf16 = false;
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    // and / or, under VIT_PREC_AUTO, with the BF16 operand set (an FP16 operand overflowed -- 8-bit exponent instead of 5);
+    // decide_retry picks the order.  A switch that was needed becomes permanent once it has been needed in three calls (the
+    // data evidently does it regularly); until then the next call starts from the fast configuration again.
+    const bool exact0 = g_opt.attn_exact.load() != 0;
+    const int prec0 = e.prec;
+    bool trial = false;
+    for (int attempt = 0;; ++attempt) {
         unsigned int flags = 0;
+        const PassMode used = current_mode(e);
         VIT_TRY(forward_host_once(images_nchw, image_ptrs, n, logits_out, &flags));
-        bool again = false;
-        if ((flags & VIT_FLAG_ATTN_RANGE) && !g_opt.attn_exact.load()) {
-            ++e.attn_fallbacks;
-            g_opt.attn_exact = 1;
-            temp_exact = again = true;
+        const int again = decide_retry(e, flags, used, &trial);
+        if (again < 0) {
+            g_opt.attn_exact = exact0 ? 1 : 0;
+            return again;
         }
-        if ((flags & VIT_FLAG_NONFINITE) && e.prec == VIT_PREC_FP16) {
-            if (e.policy == VIT_PREC_FP16)
-                return set_err(VIT_E_RANGE, "non-finite logits with FP16 operands (overflow): use VIT_PREC_AUTO or VIT_PREC_BF16");
-            ++e.prec_fallbacks;
-            e.prec = VIT_PREC_BF16;
-            temp_bf16 = again = true;
-        }
-        if (!again) break;
+        if (again == 0 || attempt == 3) break;
     }
-    if (temp_exact && e.attn_fallbacks < 3) g_opt.attn_exact = 0;
-    if (temp_bf16 && e.prec_fallbacks < 3) e.prec = VIT_PREC_FP16;
+    if (!exact0 && g_opt.attn_exact.load()) {
+        if (++e.attn_fallbacks < 3) g_opt.attn_exact = 0;
+    }
+    if (prec0 == VIT_PREC_FP16 && e.prec == VIT_PREC_BF16) {
+        if (++e.prec_fallbacks < 3) e.prec = VIT_PREC_FP16;
+    }
     if (top1_out)
         for (int i = 0; i < n; ++i) {
             const float* row = logits_out + static_cast<size_t>(i) * kClasses;
