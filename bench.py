@@ -321,6 +321,7 @@ def variants(V, args, prec, peaks):
                 if i >= 50:
                     host_ms.append((time.perf_counter() - t1) * 1e3)
             info = eng.info()
+            top1_shipped = int(h_log.argmax())     # before the pinned buffer goes away
             V.dev_free(0, d_img)
             V.dev_free(0, d_log)
             V.pinned_free(ip)
@@ -329,7 +330,7 @@ def variants(V, args, prec, peaks):
                     "dtype": info["precision"], "precision_fallbacks": info["precision_fallbacks"], "runs": 1000, "warmup": 50,
                     "device_ms_median": float(np.median(dev_ms)), "device_ms_p99": float(np.percentile(dev_ms, 99)),
                     "host_to_host_ms_median": float(np.median(host_ms)), "host_to_host_ms_p99": float(np.percentile(host_ms, 99)),
-                    "h2d_bytes": int(img.nbytes), "d2h_bytes": 4000, "top1": int(h_log.argmax())})
+                    "h2d_bytes": int(img.nbytes), "d2h_bytes": 4000, "top1": top1_shipped})
     else:
         out.append({"variant": "configs[1]: batch-1 latency on the reference's shipped Network/ tensors", "unavailable": "baseline/_ref/Network absent (run __graft_entry__.build() where /root/reference is mounted)"})
     return out
