@@ -30,8 +30,9 @@ PARITY_IMAGES = 64     # images of the timed batch checked against the oracle in
 FLOP_PER_IMAGE_224 = 35_127_656_448  # matmul-only, 2 FLOP/MAC, un-padded 197 tokens
 FLOP_PER_IMAGE = {224: FLOP_PER_IMAGE_224, 384: 110_968_700_928}  # 384: BASELINE.json configs[4] (577 tokens)
 # per-launch algorithmic FLOPs of one GEMM over `rows` token rows
-# DRAM bytes of one launch at B = 1024 from the ncu --set full capture committed under profiles/ (r1_ncu_layer_final.txt)
-NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_197_838_000, "out_gemm": 1_812_946_000, "fc1_gemm": 1_507_901_000, "fc2_gemm": 2_845_759_000}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one launch at B = 1024, FP16 operands, from the ncu --set full
+# capture committed under profiles/ (r2_ncu_layer.txt)
+NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_199_795_000, "out_gemm": 1_812_853_000, "fc1_gemm": 1_546_320_000, "fc2_gemm": 2_839_363_000}
 GEMM_FLOP_PER_ROW = {"qkv_gemm": 2 * 768 * 2304, "out_gemm": 2 * 768 * 768, "fc1_gemm": 2 * 768 * 3072, "fc2_gemm": 2 * 3072 * 768}
 
 
@@ -510,7 +511,7 @@ def run_ours(args):
                                    "sustained": flop_per_image * value / n_gpus / 1e12 / peaks["bf16_tflops_sustained"], "peaks": peaks["source"]},
             "roofline": {"kernel": f"gemm_sm100_staged_kernel ({dom})", "bound": "tensor", "achieved": dom_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": dom_tflops / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom) if (B, S) == (1024, 224) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_ncu_layer_final.txt" if (B, S) == (1024, 224) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r2_ncu_layer.txt" if (B, S) == (1024, 224) else None,
                          "algorithmic_flop_per_launch": GEMM_FLOP_PER_ROW[dom] * rows,
                          "peak_kind": f"bf16_tflops_sustained ({peaks['source']})",
                          "ms_per_launch": dom_ms, "launches": prof[dom]["launches"]},
