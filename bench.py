@@ -222,14 +222,16 @@ def abi_inproc(V, weights, S, B, G, steps, prec, per_process_e2e):
         h_log, lp = V.pinned_empty((n, 1000))
         for g in range(G):
             V.synth_images(B, S, 7, first_index=g * B, out=h_imgs[g * B:(g + 1) * B])
-        for _ in range(2):
+        for _ in range(4):       # the pass schedule adapts to the copy rate it measures in its first calls
             eng.forward_raw(ip, n, lp)
         t0 = time.perf_counter()
         for _ in range(steps):
             eng.forward_raw(ip, n, lp)
         dt = time.perf_counter() - t0
+        info = eng.info()
         res["pinned"] = {"value": n * steps / dt, "unit": "images/s", "ms_per_call": dt / steps * 1e3,
-                         "vs_one_process_per_gpu_e2e": n * steps / dt / per_process_e2e}
+                         "vs_one_process_per_gpu_e2e": n * steps / dt / per_process_e2e,
+                         "pass_growth_percent_slot0": info["pass_growth_percent"], "h2d_mb_per_s_slot0": info["h2d_mb_per_s"]}
         checksum = int(h_log.argmax(1).sum())
         eng.set_option(V.OPT_HOST_THREADS, 0)
         eng.forward_raw(ip, n, lp)
@@ -422,13 +424,14 @@ def run_ours(args):
     eng.profile_enable(False)
 
     # ---- end to end through vit_cuda_forward: pinned host images in, host logits out, every step
-    for _ in range(2):
+    for _ in range(4):       # the pass schedule adapts to the copy rate it measures in its first calls
         eng.forward_raw(h_imgs_ptr, B, h_logits_ptr)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         eng.forward_raw(h_imgs_ptr, B, h_logits_ptr)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_info = eng.info()
     e2e_value = n_gpus * B * args.steps / e2e_s
     top1 = h_logits.argmax(1)
     h_logits_full = h_logits.copy()     # logits of the timed (all-rows) configuration; rank 0's first images go to the parity block
@@ -517,7 +520,8 @@ def run_ours(args):
                          "ms_per_launch": dom_ms, "launches": prof[dom]["launches"]},
             "step_breakdown_ms": step_ms_by_cat, "ms_per_step_with_launch_events": ms_profiled,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h_imgs.nbytes), "d2h_bytes_per_step": int(h_logits.nbytes),
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+                    "ms_per_step": e2e_s / args.steps * 1e3, "pass_growth_percent": e2e_info["pass_growth_percent"],
+                    "h2d_mb_per_s": e2e_info["h2d_mb_per_s"]},
             "gpu_launches": int(launches), "clocks": clocks, "engine": eng.info(), "top1_checksum": int(top1.sum()),
         }
         out["class_row_pruning"] = {

@@ -106,6 +106,12 @@ int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, 
  * vit_cuda_forward_scattered): 64 images, then passes of 128 -- the host-side gather runs at about the rate
  * the GPU consumes images, so equal passes keep every gather hidden under the previous pass's kernels. */
 int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* first, int* count, int cap);
+/* The general form: every pass after the first may be growth_percent / 100 times the previous one (clamped to 100..300).
+ * vit_cuda_forward derives the factor per GPU from the copy and kernel times it measured in its previous calls (how much
+ * faster a pass's host-to-device copy is than its kernels, minus a 15 % reserve): 300 for a lone GPU on PCIe Gen5, less when
+ * several GPUs pull from the same host memory at once -- a pass whose copy is slower than the previous pass's kernels would
+ * otherwise wait for it (measured at 8 GPUs in one process: 47.8 ms per 8192 images with the fixed factor 3). */
+int vit_cuda_pass_schedule_growth(int n_images, int max_batch, int staged, int growth_percent, int* first, int* count, int cap);
 
 /* Device-resident variant for one GPU slot (0 <= gpu_slot < n_gpus): d_images and d_logits
  * are device pointers on that GPU, n <= max_batch_per_gpu.  Work is enqueued on the
@@ -172,7 +178,8 @@ int vit_cuda_get_option(int option, int* value);
 /* Facts about the engine/device, for logs: fills up to n entries of
  * {sm_count, cc_major, cc_minor, max_batch, tokens, active operand precision (VIT_PREC_BF16 / FP16), n_gpus,
  *  ws_bytes>>20, attention_exact, attention_fallbacks, class_row_pruning, precision policy (VIT_PREC_*),
- *  precision_fallbacks, weight_bytes>>20}. */
+ *  precision_fallbacks, weight_bytes>>20, pass-schedule growth percent of slot 0 (see vit_cuda_pass_schedule_growth),
+ *  measured H2D copy rate of slot 0 in MB/s (0 until measured)}. */
 int vit_cuda_info(long long* out, int n);
 
 /* CUDA-event stopwatch on a slot's stream: start records an event, stop records a second one,

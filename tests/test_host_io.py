@@ -127,6 +127,18 @@ def test_pass_schedule_covers_the_shard_with_a_small_first_pass(vit):
         assert [f for f, _ in sched] == list(np.cumsum([0] + [c for _, c in sched[:-1]]))
     assert vit.pass_schedule(0, 8) == []
     assert vit.pass_schedule(1024, 1024) == [(0, 32), (32, 96), (128, 288), (416, 608)]
+    # growth factor below 3 (several GPUs sharing the host's copy bandwidth): same invariants, gentler ramp, always progress
+    for growth in (100, 134, 150, 200, 250, 300, 1000, -5):
+        g = min(300, max(100, growth))
+        for n, mb in [(1024, 1024), (1000, 100), (33, 1024), (5000, 999)]:
+            sched = vit.pass_schedule(n, mb, growth_percent=growth) if n / min(mb, 32) < 40 or g > 100 else None
+            if sched is None:
+                continue
+            assert sum(c for _, c in sched) == n and sched[0][1] <= 32
+            for i in range(1, len(sched)):
+                assert sched[i][0] == sched[i - 1][0] + sched[i - 1][1] and 0 < sched[i][1] <= mb
+                assert sched[i][1] <= max(sched[i - 1][1] + 1, sched[i - 1][1] * g // 100)
+    assert vit.pass_schedule(1024, 1024, growth_percent=200) == [(0, 32), (32, 64), (96, 128), (224, 256), (480, 512), (992, 32)]
     with pytest.raises(vit.VitCudaError):
         vit.pass_schedule(100000, 1)   # more than 64 passes
 

@@ -477,6 +477,10 @@ struct DeviceCtx {
     unsigned int* d_flags = nullptr;
     unsigned int* h_flags = nullptr;
     bool pending_fast_softmax = false, pending_fp16 = false;   // work enqueued since the flags were last read
+    // copy rate vs kernel rate of the passes of the last host calls (pinned input), for the pass schedule's growth factor:
+    // timing events around every pass's H2D copy and kernels, read after the call; exponential averages in ms per image
+    std::vector<cudaEvent_t> tm_events;      // 4 per pass: copy start / stop, kernels start / stop
+    double h2d_ms_per_image = 0, kernel_ms_per_image = 0;
     char err[512] = "";   // failure text of this slot's feeding thread
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
@@ -602,6 +606,7 @@ void destroy_ctx(DeviceCtx& c) {
         if (c.ev_logits[i]) cudaEventDestroy(c.ev_logits[i]);
     }
     if (c.h_flags) cudaFreeHost(c.h_flags);
+    for (cudaEvent_t ev : c.tm_events) cudaEventDestroy(ev);
     for (auto& g : c.graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     c.graphs.clear();
@@ -1300,13 +1305,17 @@ int vit_cuda_forward_device(int gpu_slot, const float* d_images, int n, float* d
     return vit_cuda_sync(gpu_slot);
 }
 
-int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* first, int* count, int cap) {
+int vit_cuda_pass_schedule_growth(int n_images, int max_batch, int staged, int growth_percent, int* first, int* count, int cap) {
     if (n_images < 0 || max_batch <= 0 || !first || !count || cap <= 0) return set_err(VIT_E_ARG, "bad schedule arguments");
+    const int growth = std::min(300, std::max(100, growth_percent));
     int n = 0;
-    // pinned input: the copy of a pass is ~3.4x faster than its kernels -> passes may triple.  Staged input (pageable or
-    // one allocation per image): the host-side gather runs at about the rate the GPU consumes images, so the passes
-    // after the first stay at 128 images -- each gather hides under the kernels of the pass before it.
-    for (int done = 0, sz = staged ? 64 : 32; done < n_images; sz = staged ? std::min(max_batch, 128) : std::min(max_batch, 3 * sz)) {
+    // pinned input: the copy of a pass is `growth` times faster than its kernels -> every pass may be that much larger than
+    // the one whose kernels hide its copy (300 %: a lone GPU on PCIe Gen5; less when several GPUs share the host's memory
+    // and root complexes).  Staged input (pageable or one allocation per image): the host-side gather runs at about the rate
+    // the GPU consumes images, so the passes after the first stay at 128 images -- each gather hides under the kernels of the
+    // pass before it.
+    for (int done = 0, sz = staged ? 64 : 32; done < n_images;
+         sz = staged ? std::min(max_batch, 128) : std::min(max_batch, std::max(sz + 1, static_cast<int>(static_cast<long long>(sz) * growth / 100)))) {
         const int nb = std::min(std::min(sz, max_batch), n_images - done);
         if (n == cap) return set_err(VIT_E_ARG, "pass schedule of %d images with max_batch %d needs more than %d passes", n_images, max_batch, cap);
         first[n] = done;
@@ -1315,6 +1324,10 @@ int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* firs
         ++n;
     }
     return n;
+}
+
+int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* first, int* count, int cap) {
+    return vit_cuda_pass_schedule_growth(n_images, max_batch, staged, 300, first, count, cap);
 }
 
 int vit_cuda_pass_schedule(int n_images, int max_batch, int* first, int* count, int cap) {
@@ -1351,8 +1364,15 @@ struct HostJob {
     bool images_pinned, logits_pinned;
     PassMode mode;
     int gather_threads;                // host threads a slot may use to gather a staged pass
-    const std::vector<int>*pass_first, *pass_count;
+    int per_gpu;                       // images of a full shard
 };
+
+// Growth factor (percent) of the pass schedule for pinned input on this slot: how much faster a pass's H2D copy is than its
+// kernels, from the previous calls' measurements, with a 15 % reserve; 300 (a lone GPU on PCIe Gen5) until measured.
+int schedule_growth(const DeviceCtx& c) {
+    if (c.h2d_ms_per_image <= 0 || c.kernel_ms_per_image <= 0) return 300;
+    return std::min(300, std::max(100, static_cast<int>(85.0 * c.kernel_ms_per_image / c.h2d_ms_per_image)));
+}
 
 // One slot's shard of a host call: its passes, H2D copies on the copy stream into alternating image buffers under the
 // kernels of the previous pass, logits back per pass; ends with the slot's stream synchronised and its status flags read.
@@ -1368,11 +1388,27 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
     int lo, hi;
     vit_cuda_shard_range(job.n, G, g, &lo, &hi);
     const bool staged = job.image_ptrs || !job.images_pinned;
-    const int n_pass = static_cast<int>(job.pass_first->size());
+    // Pass schedule of the shard: the H2D copy of pass i+1 (copy stream, second image buffer) hides under the kernels of
+    // pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB) -- and every later pass may be
+    // `growth` times the previous one, up to the workspace size.  A lone GPU on PCIe Gen5 copies images ~3.4x faster than the
+    // kernels consume them (1024 images: 32 + 96 + 288 + 608); eight GPUs pulling from one host at once do not (measured
+    // ~25 GB/s each: the 608-image pass then waits 10 ms for its copy), so the factor follows the measured rates.
+    const int worst = job.per_gpu / std::min(e.max_batch, 32) + 40;
+    std::vector<int> pass_first(worst), pass_count(worst);
+    const int n_pass = vit_cuda_pass_schedule_growth(job.per_gpu, e.max_batch, staged ? 1 : 0, schedule_growth(c), pass_first.data(), pass_count.data(), worst);
+    if (n_pass < 0) return n_pass;
+    const bool timing = !staged && !e.profiling;
+    if (timing)
+        while (c.tm_events.size() < static_cast<size_t>(4 * n_pass)) {
+            cudaEvent_t ev;
+            CU_TRY(cudaEventCreate(&ev));
+            c.tm_events.push_back(ev);
+        }
+    int n_timed = 0;
     for (int pass = 0; pass < n_pass; ++pass) {
-        const int first = lo + (*job.pass_first)[pass];
+        const int first = lo + pass_first[pass];
         if (first >= hi) break;
-        const int nb = std::min((*job.pass_count)[pass], hi - first);
+        const int nb = std::min(pass_count[pass], hi - first);
         const int buf = pass & 1;
         // H2D of this pass overlaps the previous pass's compute (other image buffer)
         if (pass >= 2) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_done[buf], 0));
@@ -1407,11 +1443,16 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
         } else {
             src = job.images_nchw + static_cast<size_t>(first) * img_elems;
         }
+        if (timing) CU_TRY(cudaEventRecord(c.tm_events[4 * pass], c.copy_stream));
         CU_TRY(cudaMemcpyAsync(c.images[buf], src, static_cast<size_t>(nb) * img_elems * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+        if (timing) CU_TRY(cudaEventRecord(c.tm_events[4 * pass + 1], c.copy_stream));
         if (staged) CU_TRY(cudaEventRecord(c.ev_stage[buf], c.copy_stream));
         CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
         CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
+        if (timing) CU_TRY(cudaEventRecord(c.tm_events[4 * pass + 2], c.stream));
         VIT_TRY(enqueue_forward(c, e, job.mode, c.images[buf], nb, c.logits));
+        if (timing) CU_TRY(cudaEventRecord(c.tm_events[4 * pass + 3], c.stream));
+        n_timed = pass + 1;
         CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
         if (job.logits_pinned) {
             CU_TRY(cudaMemcpyAsync(job.logits_out + static_cast<size_t>(first) * kClasses, c.logits,
@@ -1434,6 +1475,29 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
     const cudaError_t se = cudaStreamSynchronize(c.stream);
     if (se != cudaSuccess) return watchdog_or_cuda_error(se, "forward");
     for (int buf = 0; buf < 2; ++buf) VIT_TRY(drain_logits(c, buf, job.logits_out));
+    if (timing) {
+        // rates of this call's passes of >= 64 images (small passes are latency, not rate), folded into the running averages
+        double h2d_ms = 0, k_ms = 0;
+        long long imgs = 0;
+        for (int pass = 0; pass < n_timed; ++pass) {
+            const int nb = std::min(pass_count[pass], hi - lo - pass_first[pass]);
+            if (nb < 64) continue;
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, c.tm_events[4 * pass], c.tm_events[4 * pass + 1]) != cudaSuccess ||
+                cudaEventElapsedTime(&b, c.tm_events[4 * pass + 2], c.tm_events[4 * pass + 3]) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            h2d_ms += a;
+            k_ms += b;
+            imgs += nb;
+        }
+        if (imgs > 0 && h2d_ms > 0 && k_ms > 0) {
+            const double w = c.h2d_ms_per_image > 0 ? 0.5 : 1.0;
+            c.h2d_ms_per_image = (1 - w) * c.h2d_ms_per_image + w * h2d_ms / imgs;
+            c.kernel_ms_per_image = (1 - w) * c.kernel_ms_per_image + w * k_ms / imgs;
+        }
+    }
     return collect_flags(c, flags_out);
 }
 
@@ -1452,10 +1516,6 @@ int forward_host_once(const float* images_nchw, const float* const* image_ptrs, 
     if (e.tokens > ATTNL_MAX_TOKENS) return set_err(VIT_E_ARG, "img_size %d (%d tokens): at most %d tokens are supported", e.img, e.tokens, ATTNL_MAX_TOKENS);
     const int G = static_cast<int>(e.ctx.size());
     const int per_gpu = (n + G - 1) / G;  // contiguous shards
-    // Pass schedule of a shard: the H2D copy of pass i+1 (copy stream, second image buffer) hides under the
-    // kernels of pass i, so only the FIRST pass's copy is exposed -- it is kept small (32 images, 19 MB), and
-    // every later pass may be three times the previous one (PCIe Gen5 moves images ~3.4x faster than
-    // the kernels consume them) up to the workspace size.  1024 images: 32 + 96 + 288 + 608.
     HostJob job;
     job.images_nchw = images_nchw;
     job.image_ptrs = image_ptrs;
@@ -1467,15 +1527,7 @@ int forward_host_once(const float* images_nchw, const float* const* image_ptrs, 
     job.images_pinned = images_nchw && cudaPointerGetAttributes(&pa, images_nchw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
     cudaGetLastError();
     job.mode = current_mode(e);
-    // any number of passes (a tiny max_batch with a large n): size the schedule arrays for the worst case
-    const int worst = per_gpu / std::min(e.max_batch, 32) + 8;
-    std::vector<int> pass_first(worst), pass_count(worst);
-    const int n_sched = vit_cuda_pass_schedule_ex(per_gpu, e.max_batch, (image_ptrs || !job.images_pinned) ? 1 : 0, pass_first.data(), pass_count.data(), worst);
-    if (n_sched < 0) return n_sched;
-    pass_first.resize(n_sched);
-    pass_count.resize(n_sched);
-    job.pass_first = &pass_first;
-    job.pass_count = &pass_count;
+    job.per_gpu = per_gpu;
     // gathering threads: up to eight per slot, all slots together at most half the host's cores
     const int hw = std::max(2, static_cast<int>(std::thread::hardware_concurrency()));
     job.gather_threads = std::max(1, std::min(8, hw / (2 * G)));
@@ -1571,11 +1623,13 @@ int vit_cuda_info(long long* out, int n) {
     const DeviceCtx& c = g_eng.ctx[0];
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, c.device));
-    const long long v[14] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
+    const double img_mb = 3.0 * g_eng.img * g_eng.img * 4 / 1e6;
+    const long long v[16] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
                              (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20), g_opt.attn_exact.load() ? 1 : 0,
                              g_eng.attn_fallbacks, g_opt.prune_last.load() ? 1 : 0, g_eng.policy, g_eng.prec_fallbacks,
-                             (long long)(c.arena_bytes >> 20)};
-    for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
+                             (long long)(c.arena_bytes >> 20), schedule_growth(c),
+                             c.h2d_ms_per_image > 0 ? (long long)(img_mb / c.h2d_ms_per_image * 1e3) : 0};
+    for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
     return 0;
 }
 

@@ -61,6 +61,7 @@ _sig("vit_cuda_shard_range", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p)
 _sig("vit_cuda_forward_scattered", C.c_int, C.POINTER(_f32p), C.c_int, C.c_void_p, C.c_void_p)
 _sig("vit_cuda_pass_schedule", C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_pass_schedule_ex", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
+_sig("vit_cuda_pass_schedule_growth", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_forward_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_enqueue_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_sync", C.c_int, C.c_int)
@@ -253,10 +254,11 @@ class Engine:
         return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(PROF_CATEGORIES)}
 
     def info(self) -> dict:
-        v = (C.c_longlong * 14)()
-        _check(lib.vit_cuda_info(v, 14))
+        v = (C.c_longlong * 16)()
+        _check(lib.vit_cuda_info(v, 16))
         keys = ["sm_count", "cc_major", "cc_minor", "max_batch", "tokens", "precision", "n_gpus", "workspace_mib",
-                "attention_exact", "attention_fallbacks", "class_row_pruning", "precision_policy", "precision_fallbacks", "weights_mib"]
+                "attention_exact", "attention_fallbacks", "class_row_pruning", "precision_policy", "precision_fallbacks", "weights_mib",
+                "pass_growth_percent", "h2d_mb_per_s"]
         d = dict(zip(keys, [int(x) for x in v]))
         d["precision"] = PREC_NAMES[d["precision"]]            # the operand type the next pass runs in
         d["precision_policy"] = PREC_NAMES[d["precision_policy"]]
@@ -288,9 +290,9 @@ def shard_range(n: int, n_gpus: int, g: int) -> tuple[int, int]:
     return lo.value, hi.value
 
 
-def pass_schedule(n_images: int, max_batch: int, staged: bool = False) -> list[tuple[int, int]]:
+def pass_schedule(n_images: int, max_batch: int, staged: bool = False, growth_percent: int = 300) -> list[tuple[int, int]]:
     first, count = (C.c_int * 64)(), (C.c_int * 64)()
-    n = lib.vit_cuda_pass_schedule_ex(n_images, max_batch, 1 if staged else 0, first, count, 64)
+    n = lib.vit_cuda_pass_schedule_growth(n_images, max_batch, 1 if staged else 0, growth_percent, first, count, 64)
     if n < 0:
         _check(n)
     return [(first[i], count[i]) for i in range(n)]
