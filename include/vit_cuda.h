@@ -287,6 +287,11 @@ int vit_cuda_op_head(const float* x, const float* ln_w, const float* ln_b,
                      const float* head_w, const float* head_b, float* logits,
                      int batch, int tokens);
 
+/* One whole encoder block of the INITIALISED engine (its weights of block `layer`, its image size, its current precision
+ * and options) on slot 0: x [batch*tokens][768] fp32 -> y, the same five kernels in the same configuration as the forward
+ * pass runs them, all rows.  Replaces Encoder, ViT_seq.c:271-302 / Encoder_opencl, ViT_opencl.c:732-782. */
+int vit_cuda_op_encoder_block(const float* x, float* y, int batch, int layer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -423,6 +423,32 @@ def test_operand_weight_cache_round_trip(vit, weights224, ref16, tmp_path):
         assert eng.info()["precision_policy"] == "bf16" and np.array_equal(eng.forward(imgs), want_bf)
 
 
+@pytest.mark.parametrize("layer", [0, 7, 11])
+def test_encoder_block_against_the_oracle(vit, oracle, weights224, shipped224, layer):
+    """Encoder (ViT_seq.c:271-302; pre-LN block: r = x + MHA(LN1 x), out = r + MLP(LN2 r)) as the forward pass runs it --
+    in_proj with LayerNorm folded in, fused attention, out_proj + residual, mlp_0 with LayerNorm folded in + GELU, mlp_3 +
+    residual -- on one block in isolation, against the oracle's restatement on the same fp32 input.  Synthetic weights and
+    the reference's shipped tensors (real LayerNorm gains / biases, out_proj); folded and unfolded LayerNorm; both operand
+    types.  The block's output carries the input through the residual path, so the bound is on the block's own
+    contribution: FP16 1e-2 + 2e-3 |ref|, BF16 6e-2 + 1.2e-2 |ref| (the 8x coarser operands)."""
+    rng = np.random.default_rng(100 + layer)
+    batch, tokens = 3, 197
+    x = (rng.standard_normal((batch * tokens, 768)) * 1.3 + 0.2 * rng.standard_normal((1, 768))).astype(np.float32)
+    for w, name in ((weights224, "synthetic"), (shipped224[0], "shipped")):
+        lw = w[4 + 12 * layer: 16 + 12 * layer]
+        ref = np.concatenate([oracle.encoder_block(np.ascontiguousarray(x[i * tokens:(i + 1) * tokens]), lw) for i in range(batch)])
+        for prec, atol, rtol in ((vit.PREC_FP16, 1e-2, 2e-3), (vit.PREC_BF16, 6e-2, 1.2e-2)):
+            with vit.Engine(w, 224, max_batch=4, precision=prec) as eng:
+                got = vit.op_encoder_block(x, batch, layer)
+                eng.set_option(vit.OPT_LN_FUSED, 0)
+                unfused = vit.op_encoder_block(x, batch, layer)
+                eng.set_option(vit.OPT_LN_FUSED, 1)
+            for out, what in ((got, "folded"), (unfused, "separate LayerNorm")):
+                err = np.abs(out - ref)
+                print(f"layer {layer} {name} prec {prec} {what}: max err {err.max():.4f}, |delta| of the block {np.abs(ref - x).max():.2f}")
+                assert np.all(err <= atol + rtol * np.abs(ref)), f"layer {layer} {name} prec {prec} {what}: max err {err.max():.4f}"
+
+
 def test_batch_position_independence(vit, weights224, ref16):
     """An image's logits must not depend on its position in the batch or on the pass size
     (needed for bit-identical results across GPU counts)."""

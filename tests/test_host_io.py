@@ -219,3 +219,33 @@ def test_host_only_library_has_the_same_assets_and_no_cuda(vit):
     assert np.array_equal(H.synth_images(3, 224, 7, first_index=5), vit.synth_images(3, 224, 7, first_index=5))
     ldd = subprocess.run(["ldd", str(H.LIB_PATH)], capture_output=True, text=True).stdout
     assert "cuda" not in ldd.lower() and "vit_b200" not in ldd
+
+
+def test_cli_sequential_backend_runs_the_callers_reference_build(vit, oracle, tmp_path):
+    """vit_main --backend seq --seq-lib LIB (the Main.c:48-53 path): the driver loads ViT_seq() from a shared library the
+    CALLER supplies -- here the reference's own ViT_seq.c as compiled by oracle/Makefile -- runs it on the loaded images and
+    weights and writes the Main.c:71 result file; same top-1 / probability as calling that library directly.  No GPU."""
+    import subprocess
+    from pathlib import Path
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libvit_ref.so not built (needs /root/reference)")
+    exe = Path(vit.PKG_DIR) / "bin" / "vit_main"
+    ref_lib = Path(oracle.__file__).resolve().parent / "_ref" / "libvit_ref.so"
+    n = 2
+    w = vit.synth_weights(224, 42)
+    imgs = vit.synth_images(n, 224, 7)
+    img_file, wdir, res = tmp_path / "input-2.bin", tmp_path / "Network", tmp_path / "seq_result.txt"
+    assert vit.lib.save_image_data(str(img_file).encode(), vit.fptr(imgs), n, 3, 224, 224) == 0
+    assert vit.lib.save_weights(str(wdir).encode(), vit.as_network(w), 152, 224) == 0
+    out = subprocess.run([str(exe), "--backend", "seq", "--seq-lib", str(ref_lib), "--images", str(img_file), "--weights", str(wdir),
+                          "--result", str(res)], capture_output=True, timeout=900)
+    stdout = out.stdout.decode(errors="replace")           # the reference's ViT_seq prints a non-UTF-8 progress line per image
+    assert out.returncode == 0, stdout + out.stderr.decode(errors="replace")
+    assert "Sequential time" in stdout
+    probs = oracle.ref_vit_seq(w, imgs)
+    lines = res.read_text().splitlines()
+    assert len(lines) == n
+    for i, ln in enumerate(lines):
+        assert ln == f"[{i}] label: {int(probs[i].argmax())} / prob: {probs[i].max():.6f}"
+    bad = subprocess.run([str(exe), "--backend", "seq", "--images", str(img_file), "--weights", str(wdir)], capture_output=True, text=True)
+    assert bad.returncode == 2 and "--seq-lib" in bad.stderr

@@ -812,11 +812,117 @@ PassMode current_mode(const Engine& e) {
     return PassMode{e.prec, g_opt.attn_exact.load() != 0, g_opt.ln_fused.load() != 0, g_opt.prune_last.load() != 0, g_opt.pdl.load() != 0};
 }
 
+// One encoder block (Encoder, ViT_seq.c:271-302) for nb images on c.stream: in_proj (LayerNorm 1 folded in) -> attention ->
+// out_proj + residual -> mlp_0 (LayerNorm 2 folded in, GELU) -> mlp_3 + residual, on c.x in place.  `tail_for_head`: this is the
+// last block of a forward -- with class-row pruning everything behind its attention runs on the class rows only (returns 1:
+// the result is in c.x_c), and its mlp_3 need not emit the copy / statistics for a next block.  Returns 0 normally, < 0 on error.
+int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int l, int nb, bool tail_for_head) {
+    cudaStream_t st = c.stream;
+    const int prec = m.prec;
+    const int rows = nb * e.tokens;
+    const bool pf = e.profiling;
+    const bool fused = m.ln_fused;
+    const int stats_rows = static_cast<int>(c.stats_rows);
+    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, nullptr};
+    const LayerW& L = c.layer[l];
+    const OperandW& W = L.op[prec];
+    if (!fused) {
+        ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
+        VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
+    }
+    {
+        ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
+        GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 0, 2 * kDim};  // V block stored as bf16
+        if (fused) {
+            p.bias = L.qkv_c;
+            p.colsum = W.qkv_s;
+            p.stats_in = c.pstats;
+            p.stats_parts = 6;
+            p.stats_rows = stats_rows;
+            VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, W.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
+        } else VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, W.tm_qkv_w, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
+    }
+    if (tail_for_head && fused && m.prune_last) {
+        // Last layer: only the class token reaches the head, and no token reads another one after the attention.
+        // Attention for the class query alone (all keys and values), then out_proj / LayerNorm / MLP on the compact
+        // [nb][768] class rows: 1/197 of the rows of the other layers.
+        {
+            ProfScope ps(c, pf, VIT_PROF_ATTENTION);
+            if (prec == VIT_PREC_FP16)
+                cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__half*>(c.ao_c), c.x_c, e.tokens);
+            else
+                cls_attention_kernel<__nv_bfloat16><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__nv_bfloat16*>(c.ao_c), c.x_c, e.tokens);
+            VIT_TRY(check_launch("cls_attention"));
+        }
+        const int srows_c = static_cast<int>(c.stats_rows_c);
+        {
+            ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
+            GemmParams p{nb, kDim, kDim, L.out_b, c.x_c, c.x_c};
+            p.stats_out = c.pstats_c;
+            p.stats_rows = srows_c;
+            VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao_c, W.tm_out_w, c.tm_x_c, c.tm_xn_c, p, c.sm_count, st));
+        }
+        {
+            ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
+            GemmParams p{nb, kHidden, kDim, L.fc1_c, c.hid_c, nullptr};
+            p.colsum = W.fc1_s;
+            p.stats_in = c.pstats_c;
+            p.stats_parts = 6;
+            p.stats_rows = srows_c;
+            VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn_c, W.tm_fc1_wf, c.tm_hid_c, c.tm_hid_c32, p, c.sm_count, st));
+        }
+        {
+            ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
+            GemmParams p{nb, kDim, kHidden, L.fc2_b, c.x_c, c.x_c};
+            VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid_c, W.tm_fc2_w, c.tm_x_c, c.tm_x_c, p, c.sm_count, st));
+        }
+        return 1;
+    }
+    {
+        ProfScope ps(c, pf, VIT_PROF_ATTENTION);
+        VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, c.tm_kv32, ap, c.sm_count, st, m.attn_exact));
+    }
+    {
+        ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
+        GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x};
+        if (fused) {
+            p.stats_out = c.pstats;
+            p.stats_rows = stats_rows;
+            VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
+        } else VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_x, p, c.sm_count, st));
+    }
+    if (!fused) {
+        ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
+        VIT_TRY(launch_layernorm(prec, c.x, L.ln2_w, L.ln2_b, c.xn, rows, st));
+    }
+    {
+        ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
+        GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr};
+        if (fused) {
+            p.bias = L.fc1_c;
+            p.colsum = W.fc1_s;
+            p.stats_in = c.pstats;
+            p.stats_parts = 6;
+            p.stats_rows = stats_rows;
+            VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, W.tm_fc1_wf, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
+        } else VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, W.tm_fc1_w, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
+    }
+    {
+        ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
+        GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x};
+        if (fused && !tail_for_head) {   // the last layer's output only feeds the class-row LayerNorm of the head
+            p.stats_out = c.pstats;
+            p.stats_rows = stats_rows;
+            VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
+        } else VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_x, p, c.sm_count, st));
+    }
+    return 0;
+}
+
 // Enqueue the whole forward for nb images already resident in d_images (fp32 NCHW) on c.stream.
 int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, const float* d_images, int nb, float* d_logits) {
     cudaStream_t st = c.stream;
     const int prec = m.prec;
-    const int rows = nb * e.tokens;
     VIT_TRY(ensure_maps(c, e, nb, prec));
     const CUtensorMap* tm_img = nullptr;
     VIT_TRY(image_map(c, e, d_images, nb, &tm_img));
@@ -839,102 +945,11 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
         }
         VIT_TRY(launch_gemm_embed(prec, fused, *tm_img, c.tm_conv_w, c.tm_x3, c.tm_xn3, c.tm_pos, p, c.sm_count, st));
     }
-    AttnParams ap{nb, e.tokens, (e.tokens + 15) / 16 * 16, c.ao, 0.125f * 1.4426950408889634f, nullptr};
     bool pruned_tail = false;
     for (int l = 0; l < kDepth; ++l) {
-        const LayerW& L = c.layer[l];
-        const OperandW& W = L.op[prec];
-        if (!fused) {
-            ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
-            VIT_TRY(launch_layernorm(prec, c.x, L.ln1_w, L.ln1_b, c.xn, rows, st));
-        }
-        {
-            ProfScope ps(c, pf, VIT_PROF_QKV_GEMM);
-            GemmParams p{rows, 3 * kDim, kDim, L.qkv_b, c.qkv, nullptr, 0, 0, 0, 2 * kDim};  // V block stored as bf16
-            if (fused) {
-                p.bias = L.qkv_c;
-                p.colsum = W.qkv_s;
-                p.stats_in = c.pstats;
-                p.stats_parts = 6;
-                p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS>(prec, c.tm_xn, W.tm_qkv_wf, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
-            } else VIT_TRY(launch_gemm_staged<EPI_BIAS>(prec, c.tm_xn, W.tm_qkv_w, c.tm_qkv_st, c.tm_qkv_st32, p, c.sm_count, st));
-        }
-        if (l == kDepth - 1 && fused && m.prune_last) {
-            // Last layer: only the class token reaches the head, and no token reads another one after the attention.
-            // Attention for the class query alone (all keys and values), then out_proj / LayerNorm / MLP on the compact
-            // [nb][768] class rows: 1/197 of the rows of the other layers.
-            {
-                ProfScope ps(c, pf, VIT_PROF_ATTENTION);
-                if (prec == VIT_PREC_FP16)
-                    cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__half*>(c.ao_c), c.x_c, e.tokens);
-                else
-                    cls_attention_kernel<__nv_bfloat16><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__nv_bfloat16*>(c.ao_c), c.x_c, e.tokens);
-                VIT_TRY(check_launch("cls_attention"));
-            }
-            const int srows_c = static_cast<int>(c.stats_rows_c);
-            {
-                ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
-                GemmParams p{nb, kDim, kDim, L.out_b, c.x_c, c.x_c};
-                p.stats_out = c.pstats_c;
-                p.stats_rows = srows_c;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao_c, W.tm_out_w, c.tm_x_c, c.tm_xn_c, p, c.sm_count, st));
-            }
-            {
-                ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
-                GemmParams p{nb, kHidden, kDim, L.fc1_c, c.hid_c, nullptr};
-                p.colsum = W.fc1_s;
-                p.stats_in = c.pstats_c;
-                p.stats_parts = 6;
-                p.stats_rows = srows_c;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn_c, W.tm_fc1_wf, c.tm_hid_c, c.tm_hid_c32, p, c.sm_count, st));
-            }
-            {
-                ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
-                GemmParams p{nb, kDim, kHidden, L.fc2_b, c.x_c, c.x_c};
-                VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid_c, W.tm_fc2_w, c.tm_x_c, c.tm_x_c, p, c.sm_count, st));
-            }
-            pruned_tail = true;
-            break;
-        }
-        {
-            ProfScope ps(c, pf, VIT_PROF_ATTENTION);
-            VIT_TRY(launch_attention(prec, c.tm_q, c.tm_kv, c.tm_kv32, ap, c.sm_count, st, m.attn_exact));
-        }
-        {
-            ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
-            GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x};
-            if (fused) {
-                p.stats_out = c.pstats;
-                p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
-            } else VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_x, p, c.sm_count, st));
-        }
-        if (!fused) {
-            ProfScope ps(c, pf, VIT_PROF_LAYERNORM);
-            VIT_TRY(launch_layernorm(prec, c.x, L.ln2_w, L.ln2_b, c.xn, rows, st));
-        }
-        {
-            ProfScope ps(c, pf, VIT_PROF_FC1_GEMM);
-            GemmParams p{rows, kHidden, kDim, L.fc1_b, c.hid, nullptr};
-            if (fused) {
-                p.bias = L.fc1_c;
-                p.colsum = W.fc1_s;
-                p.stats_in = c.pstats;
-                p.stats_parts = 6;
-                p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_GELU>(prec, c.tm_xn, W.tm_fc1_wf, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
-            } else VIT_TRY(launch_gemm_staged<EPI_BIAS_GELU>(prec, c.tm_xn, W.tm_fc1_w, c.tm_hid, c.tm_hid32, p, c.sm_count, st));
-        }
-        {
-            ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
-            GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x};
-            if (fused && l + 1 < kDepth) {   // the last layer's output only feeds the class-row LayerNorm of the head
-                p.stats_out = c.pstats;
-                p.stats_rows = stats_rows;
-                VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
-            } else VIT_TRY(launch_gemm_staged<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_x, p, c.sm_count, st));
-        }
+        const int r = enqueue_encoder_layer(c, e, m, l, nb, l == kDepth - 1);
+        if (r < 0) return r;
+        pruned_tail = r == 1;
     }
     ProfScope ps(c, pf, VIT_PROF_HEAD);
     if (pruned_tail) head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);

@@ -12,9 +12,12 @@
  *            [--operand-cache FILE]     start from / write the engine's operand-precision weight cache
  *   vit_main --synthetic N [--img 224] ...     seeded synthetic images + weights (no files needed)
  *
- * There is no --backend seq: the CPU implementation in this repository is the test oracle (oracle/), which the product
- * must not execute; the reference's own ViT_seq() is compared through tests/ and bench.py --impl reference.
+ *   vit_main --backend seq --seq-lib libvit_ref.so ...    the reference's CPU path (Main.c:48-53): ViT_seq() is taken from
+ *                                       a shared library the caller supplies -- the reference's own ViT_seq.c compiled by them
+ *                                       (same ImageData / Network layouts).  This program contains no CPU implementation of
+ *                                       the forward pass and never falls back to one.
  */
+#include <dlfcn.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -69,7 +72,7 @@ static void* read_chunk(void* arg) {
 
 int main(int argc, char** argv) {
     const char *images_path = NULL, *weights_dir = NULL, *result_path = "cuda_result.txt", *answer_path = NULL, *cache_out = NULL,
-               *operand_cache = NULL;
+               *operand_cache = NULL, *backend = "cuda", *seq_lib = NULL;
     int n_limit = 0, synthetic = 0, img = 224, timing = 0, stream_chunk = 0;
     vit_host_config cfg = {1, 256, VIT_PREC_AUTO};
     for (int i = 1; i < argc; ++i) {
@@ -89,10 +92,12 @@ int main(int argc, char** argv) {
         else if (!strcmp(a, "--precision") && v) cfg.precision = parse_precision(v), ++i;
         else if (!strcmp(a, "--stream") && v) stream_chunk = atoi(v), ++i;
         else if (!strcmp(a, "--timing")) timing = 1;
+        else if (!strcmp(a, "--backend") && v) backend = v, ++i;
+        else if (!strcmp(a, "--seq-lib") && v) seq_lib = v, ++i;
         else {
             fprintf(stderr, "usage: %s (--images FILE --weights DIR|CACHEFILE | --synthetic N [--img S]) [--n N] [--gpus G] "
                             "[--max-batch B] [--precision auto|fp16|bf16] [--result FILE] [--answer FILE] [--timing] [--stream CHUNK] "
-                            "[--operand-cache FILE] [--save-weight-cache FILE]\n", argv[0]);
+                            "[--operand-cache FILE] [--save-weight-cache FILE] [--backend cuda|seq --seq-lib LIB]\n", argv[0]);
             return 2;
         }
     }
@@ -100,8 +105,25 @@ int main(int argc, char** argv) {
         fprintf(stderr, "need --images and --weights, or --synthetic N\n");
         return 2;
     }
+    const int use_seq = !strcmp(backend, "seq");
+    if (!use_seq && strcmp(backend, "cuda")) {
+        fprintf(stderr, "--backend must be cuda or seq\n");
+        return 2;
+    }
+    void (*ref_vit_seq)(ImageData*, Network*, float**) = NULL;
+    if (use_seq) {
+        if (!seq_lib || stream_chunk > 0 || operand_cache) {
+            fprintf(stderr, "--backend seq needs --seq-lib LIB (a build of the reference's ViT_seq.c) and neither --stream nor --operand-cache\n");
+            return 2;
+        }
+        void* h = dlopen(seq_lib, RTLD_NOW | RTLD_LOCAL);
+        if (!h || !(*(void**)(&ref_vit_seq) = dlsym(h, "ViT_seq"))) {
+            fprintf(stderr, "--seq-lib %s: %s\n", seq_lib, dlerror());
+            return 1;
+        }
+    }
     vit_host_set_config(&cfg);
-    if (initialize_cuda() != 0) return 1;
+    if (!use_seq && initialize_cuda() != 0) return 1;
 
     /* ---- weights: the operand cache if it exists, else the reference's Network/ directory (or an fp32 blob) */
     static Network network[VIT_NUM_TENSORS];
@@ -172,6 +194,25 @@ int main(int argc, char** argv) {
     float* logits = (float*)malloc((size_t)n * VIT_NUM_CLASSES * sizeof(float));
 
     printf("=====================Start========================\n");
+    if (use_seq) {
+        /* Main.c:48-53: the sequential CPU path, from the caller's build of the reference */
+        if (img != 224) {
+            fprintf(stderr, "--backend seq: the reference's ViT_seq hard-codes 224x224 (ViT_seq.c:10)\n");
+            return 1;
+        }
+        const double t0 = now_s();
+        ref_vit_seq(images, network, probabilities);
+        printf("Sequential time: %f sec, %d images, %.3f images/s\n", now_s() - t0, n, n / (now_s() - t0));
+        if (write_results(result_path, probabilities, n) != 0) return 1;
+        int cmp_rc = 0;
+        if (answer_path) {
+            const int cmp = comparator_files(result_path, answer_path, n);
+            if (cmp == 0) printf("Comparator: the two files match on %d lines.\n", n);
+            else printf("Comparator: %d differences.\n", cmp);
+            cmp_rc = cmp == 0 ? 0 : 3;
+        }
+        return cmp_rc;
+    }
     if (stream || engine_from_cache) {
         /* these two modes talk to the engine directly (the reference signature has no way to pass a file or a cache) */
         if (!engine_from_cache) {

@@ -93,6 +93,7 @@ _sig("vit_cuda_op_linear_residual_stats", C.c_int, _f32p, _f32p, _f32p, _f32p, _
 _sig("vit_cuda_op_attention", C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
 _sig("vit_cuda_debug_attention_trace", C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int)
 _sig("vit_cuda_op_embed", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int)
+_sig("vit_cuda_op_encoder_block", C.c_int, _f32p, _f32p, C.c_int, C.c_int)
 _sig("vit_cuda_op_head", C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int)
 # ---- include/vit_host.h
 _sig("load_image_data", C.POINTER(ImageData), C.c_char_p)
@@ -383,6 +384,13 @@ def op_embed(images, cls, conv_w, conv_b, pos, precision=PREC_BF16, want_cast=Fa
     _check(lib.vit_cuda_op_embed(fptr(images), fptr(cls), fptr(conv_w), fptr(conv_b), fptr(pos), fptr(out),
                                  fptr(cast) if want_cast else None, batch, s, precision))
     return (out, cast) if want_cast else out
+
+
+def op_encoder_block(x, batch, layer):
+    """One encoder block of the initialised engine (vit_cuda_op_encoder_block): x [batch*tokens][768] fp32 -> same shape."""
+    y = np.empty_like(x)
+    _check(lib.vit_cuda_op_encoder_block(fptr(x), fptr(y), batch, layer))
+    return y
 
 
 def op_head(x, ln_w, ln_b, head_w, head_b, batch, tokens):
