@@ -430,14 +430,14 @@ def test_encoder_block_against_the_oracle(vit, oracle, weights224, shipped224, l
     residual -- on one block in isolation, against the oracle's restatement on the same fp32 input.  Synthetic weights and
     the reference's shipped tensors (real LayerNorm gains / biases, out_proj); folded and unfolded LayerNorm; both operand
     types.  The block's output carries the input through the residual path, so the bound is on the block's own
-    contribution: FP16 1e-2 + 2e-3 |ref|, BF16 6e-2 + 1.2e-2 |ref| (the 8x coarser operands)."""
+    contribution (|y - x| up to ~4.5): FP16 5e-3 + 1e-3 |ref| (measured max 0.0021), BF16 3e-2 + 6e-3 |ref| (measured 0.015)."""
     rng = np.random.default_rng(100 + layer)
     batch, tokens = 3, 197
     x = (rng.standard_normal((batch * tokens, 768)) * 1.3 + 0.2 * rng.standard_normal((1, 768))).astype(np.float32)
     for w, name in ((weights224, "synthetic"), (shipped224[0], "shipped")):
         lw = w[4 + 12 * layer: 16 + 12 * layer]
         ref = np.concatenate([oracle.encoder_block(np.ascontiguousarray(x[i * tokens:(i + 1) * tokens]), lw) for i in range(batch)])
-        for prec, atol, rtol in ((vit.PREC_FP16, 1e-2, 2e-3), (vit.PREC_BF16, 6e-2, 1.2e-2)):
+        for prec, atol, rtol in ((vit.PREC_FP16, 5e-3, 1e-3), (vit.PREC_BF16, 3e-2, 6e-3)):
             with vit.Engine(w, 224, max_batch=4, precision=prec) as eng:
                 got = vit.op_encoder_block(x, batch, layer)
                 eng.set_option(vit.OPT_LN_FUSED, 0)
