@@ -191,7 +191,7 @@ int vit_cuda_timer_stop(int gpu_slot, float* ms);
  * by an event pair on the slot's stream; vit_cuda_profile_read synchronises, returns the summed
  * milliseconds and launch count per category (VIT_PROF_*) since the last read, and resets. */
 enum {
-    VIT_PROF_PATCHIFY = 0,   /* class-token rows (there is no patch extraction: conv_proj reads the image) */
+    VIT_PROF_CLASS_ROWS = 0,   /* class-token rows (there is no patch extraction: conv_proj reads the image) */
     VIT_PROF_EMBED_GEMM,     /* conv_proj GEMM (tf32, straight from the fp32 image) */
     VIT_PROF_LAYERNORM,      /* ln_1 + ln_2 */
     VIT_PROF_QKV_GEMM,       /* in_proj */

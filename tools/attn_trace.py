@@ -2,7 +2,7 @@
 """Timeline of the attention kernel: runs it with the debug trace (CTA 0, first 16 units) and prints when
 each pipeline event happened (SM clock cycles relative to the first event).
     python tools/attn_trace.py [batch=160] [tokens=197]
-Streaming kernel (default): a unit is one 128-row query tile.  Persistent kernel (VIT_ATTN_IMPL=2): see
+Streaming kernel (default): a unit is one 128-row query tile.  (Round 1 also had a two-slot persistent kernel; it is gone.)  See
 git history of this tool."""
 import sys
 from pathlib import Path

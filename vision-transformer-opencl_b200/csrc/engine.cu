@@ -933,7 +933,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
     const bool fused = m.ln_fused;
     const int stats_rows = static_cast<int>(c.stats_rows);
     {   // class-token rows (class_token + pos_emb, ViT_seq.c:72-101)
-        ProfScope ps(c, pf, VIT_PROF_PATCHIFY);
+        ProfScope ps(c, pf, VIT_PROF_CLASS_ROWS);
         VIT_TRY(launch_cls_rows(prec, fused, c.x, c.xn, c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens, st));
     }
     {   // conv_proj: tf32 GEMM straight from the fp32 image; class_token offset / pos_emb / token layout are TMA addressing
@@ -1543,9 +1543,10 @@ int forward_host_once(const float* images_nchw, const float* const* image_ptrs, 
     cudaGetLastError();
     job.mode = current_mode(e);
     job.per_gpu = per_gpu;
-    // gathering threads: up to eight per slot, all slots together at most half the host's cores
+    // gathering threads: up to eight per slot; with several slots all of the host's cores (the slots' feeding threads sit in
+    // the gather themselves), with one slot half of them
     const int hw = std::max(2, static_cast<int>(std::thread::hardware_concurrency()));
-    job.gather_threads = std::max(1, std::min(8, hw / (2 * G)));
+    job.gather_threads = std::max(1, std::min(8, G > 1 ? hw / G : hw / 2));
 
     std::vector<int> rc(G, 0);
     std::vector<unsigned int> fl(G, 0);
