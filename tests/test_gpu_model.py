@@ -549,6 +549,44 @@ def test_reference_signature_adaptor(vit, weights224, ref16, oracle, tmp_path):
     assert vit.lib.comparator_files(str(res).encode(), str(ans).encode(), n) == 0
 
 
+def test_adaptor_notices_weights_reloaded_into_the_same_array(vit, weights224, ref16):
+    """The reference hands ONE static Network[152] array to every call (Main.c:29,57), so the array's address says nothing
+    about its contents.  ViT_cuda() fingerprints the tensors (pointers, sizes, 64 sampled elements each) and uploads again
+    when they changed; vit_host_invalidate_weights() forces it for an edit the sample cannot see."""
+    imgs, _ = ref16
+    n = 2
+    w = [a.copy() for a in weights224]
+    net = vit.as_network(w)
+    arr = (vit.ImageData * n)()
+    for i in range(n):
+        arr[i].n, arr[i].c, arr[i].h, arr[i].w = n, 3, 224, 224
+        arr[i].data = vit.fptr(imgs[i])
+    probs = np.zeros((n, 1000), dtype=np.float32)
+    rows = (C.POINTER(C.c_float) * n)(*[vit.fptr(probs[i]) for i in range(n)])
+    vit.lib.vit_host_invalidate_weights.restype = None
+    assert vit.lib.initialize_cuda() == 0
+    vit.lib.ViT_cuda(arr, net, rows)
+    assert vit.lib.ViT_cuda_status() == 0
+    first = probs.copy()
+    w[151][:] = 0.0
+    w[151][::2] = 30.0                  # a reload into the same buffers: every even class gets +30 on its logit
+    vit.lib.ViT_cuda(arr, net, rows)
+    assert vit.lib.ViT_cuda_status() == 0
+    assert np.all(probs.argmax(1) % 2 == 0) and not np.allclose(probs, first)
+    second = probs.copy()
+    w[151][7] = 100.0                   # one element between the sampled ones: not seen ...
+    vit.lib.ViT_cuda(arr, net, rows)
+    assert np.array_equal(probs, second)
+    vit.lib.vit_host_invalidate_weights()   # ... until the caller says so
+    vit.lib.ViT_cuda(arr, net, rows)
+    assert vit.lib.ViT_cuda_status() == 0 and np.all(probs.argmax(1) == 7)
+    # failure paths fill prb with NaN and set the status, never exit()
+    arr[0].c = 4
+    vit.lib.ViT_cuda(arr, net, rows)
+    assert vit.lib.ViT_cuda_status() != 0 and np.isnan(probs).all()
+    vit.lib.Release_cuda()
+
+
 def test_errors_are_reported_not_fatal(vit, weights224):
     bad = [w for w in weights224]
     bad[6] = bad[6][:-1].copy()
