@@ -32,7 +32,7 @@ FLOP_PER_IMAGE = {224: FLOP_PER_IMAGE_224, 384: 110_968_700_928}  # 384: BASELIN
 # per-launch algorithmic FLOPs of one GEMM over `rows` token rows
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one launch at B = 1024, FP16 operands, from the ncu --set full
 # capture committed under profiles/ (r2_ncu_layer.txt)
-NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_199_795_000, "out_gemm": 1_812_853_000, "fc1_gemm": 1_546_320_000, "fc2_gemm": 2_839_363_000}
+NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_198_461_000, "out_gemm": 1_813_036_000, "fc1_gemm": 1_576_539_000, "fc2_gemm": 3_055_351_000}
 GEMM_FLOP_PER_ROW = {"qkv_gemm": 2 * 768 * 2304, "out_gemm": 2 * 768 * 768, "fc1_gemm": 2 * 768 * 3072, "fc2_gemm": 2 * 3072 * 768}
 
 
