@@ -1,4 +1,6 @@
-"""Minimax fit of x * Phi(x) by x * sigmoid(x (a + b x^2 + c x^4 + d x^6)) (the GELU of the mlp_0 epilogue, csrc/ptx.cuh gelu_erf2):\nNelder-Mead on the maximum absolute error over [-8.5, 8.5] with a penalty that keeps the polynomial monotone out to |x| = 300."""
+#!/usr/bin/env python
+"""Minimax fit of x * Phi(x) by x * sigmoid(x (a + b x^2 + c x^4 + d x^6)) (the GELU of the mlp_0 epilogue, csrc/ptx.cuh gelu_erf2):
+Nelder-Mead on the maximum absolute error over [-8.5, 8.5] with a penalty that keeps the polynomial monotone out to |x| = 300."""
 import numpy as np
 from scipy.special import erf, ndtr, log_ndtr
 from scipy.optimize import minimize
