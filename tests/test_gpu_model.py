@@ -382,6 +382,46 @@ def test_engine_options_unfused_layernorm_pdl_graphs(vit, weights224, ref16):
     vit.lib.vit_cuda_set_option(vit.OPT_LN_FUSED, 1)
 
 
+def test_fp16_residual_stream_option(vit, oracle, weights224, shipped224, ref16):
+    """VIT_OPT_RESIDUAL16: with FP16 operands the residual stream itself is held in FP16 (the rows out_proj / mlp_3 update in
+    place are the next GEMM's operand).  Every residual add is then rounded, so this is its own numerical configuration: it
+    is held to the stated tolerance against the oracle (synthetic and shipped tensors, pruned and all rows), must stay
+    independent of batch position and pass size, and must be ignored -- same bits as without it -- for BF16 operands."""
+    imgs, ref = ref16
+    with vit.Engine(weights224, 224, max_batch=16) as eng:
+        base = eng.forward(imgs)
+        eng.set_option(vit.OPT_RESIDUAL16, 1)
+        got, top1 = eng.forward(imgs, want_top1=True)
+        one = eng.forward(np.ascontiguousarray(imgs[5:6]))
+        rev = eng.forward(np.ascontiguousarray(imgs[::-1]))[::-1]
+        eng.set_class_row_pruning(False)
+        full, top1_full = eng.forward(imgs, want_top1=True)
+        blk = vit.op_encoder_block(np.ascontiguousarray(np.random.default_rng(5).standard_normal((2 * 197, 768)).astype(np.float32)), 2, 3)
+        eng.set_option(vit.OPT_RESIDUAL16, 0)
+        eng.set_class_row_pruning(True)
+        assert np.array_equal(eng.forward(imgs), base)
+    print("fp16 residual", _report(got, ref), "| all rows", _report(full, ref), "| fp32 residual", _report(base, ref))
+    assert np.isfinite(blk).all()
+    _assert_strict(got, top1, ref, "fp16 residual stream")
+    _assert_strict(full, top1_full, ref, "fp16 residual stream, all rows")
+    assert np.array_equal(got[5:6], one) and np.array_equal(got, rev)
+    w, _ = shipped224
+    im8 = vit.synth_images(8, 224, 7)
+    ref8 = oracle.forward(w, im8, 224)
+    with vit.Engine(w, 224, max_batch=8) as eng:
+        eng.set_option(vit.OPT_RESIDUAL16, 1)
+        got8, top8 = eng.forward(im8, want_top1=True)
+        eng.set_option(vit.OPT_RESIDUAL16, 0)
+    print("fp16 residual, shipped tensors", _report(got8, ref8))
+    _assert_strict(got8, top8, ref8, "fp16 residual stream, shipped tensors")
+    with vit.Engine(weights224, 224, max_batch=16, precision=vit.PREC_BF16) as eng:
+        a = eng.forward(imgs)
+        eng.set_option(vit.OPT_RESIDUAL16, 1)
+        b = eng.forward(imgs)
+        eng.set_option(vit.OPT_RESIDUAL16, 0)
+    assert np.array_equal(a, b)
+
+
 def test_operand_weight_cache_round_trip(vit, weights224, ref16, tmp_path):
     """vit_cuda_save_weight_cache / vit_cuda_init_from_cache: an engine started from the cache file (one read, one
     host-to-device copy, no conversion, no LayerNorm folding) returns the same bits; a truncated or corrupted file and a

@@ -136,7 +136,7 @@ int embed_tiles_per_image(int S) {
 
 // ------------------------------------------------------------------------------------ run-time switches
 struct Options {
-    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1};
+    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1}, residual16{0};
 };
 Options g_opt;
 
@@ -186,13 +186,13 @@ int configure_smem(K kern, std::atomic<unsigned>& done_mask, int bytes) {
 }
 
 constexpr int kStagedStages = 5, kStagedSlots = 4;
-template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false, int kEpiWarps = 8>
+template <typename T, int EPI, bool LN, int STAGES, int SLOTS, int CAST, bool PSTAGED = (EPI != EPI_BIAS_RESIDUAL), bool EMBED = false, int kEpiWarps = 8, bool RES16 = false>
 int launch_gemm_staged_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tcast,
                            const GemmParams& p, int sm_count, cudaStream_t st, const CUtensorMap* tres = nullptr) {
     constexpr int kPreFloats = !PSTAGED ? 0 : (LN ? 256 + 256 + 2 * 128 : 256);
     using L = GemmStagedSmem<STAGES, SLOTS, CAST, kPreFloats * 4>;
     static_assert(L::DYN_BYTES <= 232448, "shared memory budget");
-    auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED, EMBED>;
+    auto kern = gemm_sm100_staged_kernel<T, STAGES, SLOTS, EPI, kEpiWarps, LN, CAST, PSTAGED, EMBED, RES16>;
     static std::atomic<unsigned> configured{0};
     VIT_TRY(configure_smem(kern, configured, L::DYN_BYTES));
     if (p.N % kGemmBN || p.K % GEMM_BK || p.M <= 0)
@@ -258,6 +258,15 @@ int launch_gemm_staged_ln(int prec, const CUtensorMap& ta, const CUtensorMap& tb
                           const GemmParams& p, int sm_count, cudaStream_t st) {
     return prec == VIT_PREC_FP16 ? launch_gemm_staged_t<__half, EPI, true>(ta, tb, tout, taux, p, sm_count, st)
                                  : launch_gemm_staged_t<__nv_bfloat16, EPI, true>(ta, tb, tout, taux, p, sm_count, st);
+}
+
+// The residual GEMM on a 16-bit residual stream (RES16): trow = load / store map of the rows in the operand type (64-column,
+// 128-row boxes: the same map the next GEMM loads its A operand through), updated in place; p.stats_out as for the fp32 form.
+int launch_gemm_residual16(int prec, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& trow, const GemmParams& p, int sm_count,
+                           cudaStream_t st) {
+    if (prec == VIT_PREC_FP16)
+        return launch_gemm_staged_cfg<__half, EPI_BIAS_RESIDUAL, true, 5, 4, 0, false, false, 8, true>(ta, tb, trow, trow, p, sm_count, st);
+    return launch_gemm_staged_cfg<__nv_bfloat16, EPI_BIAS_RESIDUAL, true, 5, 4, 0, false, false, 8, true>(ta, tb, trow, trow, p, sm_count, st);
 }
 
 template <typename T, bool EXACT>
@@ -490,7 +499,7 @@ struct DeviceCtx {
         int nb = 0, prec = 0;
         const float* images = nullptr;
         float* logits = nullptr;
-        bool attn_exact = false, ln_fused = true, prune_last = true, pdl = true;
+        bool attn_exact = false, ln_fused = true, prune_last = true, pdl = true, res16 = false;
         long long launches = 0;
         cudaGraphExec_t exec = nullptr;
     };
@@ -807,9 +816,12 @@ struct ProfScope {
 struct PassMode {
     int prec;
     bool attn_exact, ln_fused, prune_last, pdl;
+    bool res16;   // residual stream in the operand type (FP16 operands + folded LayerNorm only), VIT_OPT_RESIDUAL16
 };
 PassMode current_mode(const Engine& e) {
-    return PassMode{e.prec, g_opt.attn_exact.load() != 0, g_opt.ln_fused.load() != 0, g_opt.prune_last.load() != 0, g_opt.pdl.load() != 0};
+    const bool fused = g_opt.ln_fused.load() != 0;
+    return PassMode{e.prec, g_opt.attn_exact.load() != 0, fused, g_opt.prune_last.load() != 0, g_opt.pdl.load() != 0,
+                    g_opt.residual16.load() != 0 && fused && e.prec == VIT_PREC_FP16};
 }
 
 // One encoder block (Encoder, ViT_seq.c:271-302) for nb images on c.stream: in_proj (LayerNorm 1 folded in) -> attention ->
@@ -849,9 +861,10 @@ int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int 
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
             if (prec == VIT_PREC_FP16)
-                cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__half*>(c.ao_c), c.x_c, e.tokens);
+                cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, m.res16 ? static_cast<const __half*>(c.xn) : nullptr,
+                                                                 static_cast<__half*>(c.ao_c), c.x_c, e.tokens);
             else
-                cls_attention_kernel<__nv_bfloat16><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, static_cast<__nv_bfloat16*>(c.ao_c), c.x_c, e.tokens);
+                cls_attention_kernel<__nv_bfloat16><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, nullptr, static_cast<__nv_bfloat16*>(c.ao_c), c.x_c, e.tokens);
             VIT_TRY(check_launch("cls_attention"));
         }
         const int srows_c = static_cast<int>(c.stats_rows_c);
@@ -885,7 +898,11 @@ int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int 
     {
         ProfScope ps(c, pf, VIT_PROF_OUT_GEMM);
         GemmParams p{rows, kDim, kDim, L.out_b, c.x, c.x};
-        if (fused) {
+        if (m.res16) {
+            p.stats_out = c.pstats;
+            p.stats_rows = stats_rows;
+            VIT_TRY(launch_gemm_residual16(prec, c.tm_ao, W.tm_out_w, c.tm_xn, p, c.sm_count, st));
+        } else if (fused) {
             p.stats_out = c.pstats;
             p.stats_rows = stats_rows;
             VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_ao, W.tm_out_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
@@ -910,7 +927,11 @@ int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int 
     {
         ProfScope ps(c, pf, VIT_PROF_FC2_GEMM);
         GemmParams p{rows, kDim, kHidden, L.fc2_b, c.x, c.x};
-        if (fused && !tail_for_head) {   // the last layer's output only feeds the class-row LayerNorm of the head
+        if (m.res16) {   // (the last block's statistics are not needed, but one kernel variant serves all blocks)
+            p.stats_out = c.pstats;
+            p.stats_rows = stats_rows;
+            VIT_TRY(launch_gemm_residual16(prec, c.tm_hid, W.tm_fc2_w, c.tm_xn, p, c.sm_count, st));
+        } else if (fused && !tail_for_head) {   // the last layer's output only feeds the class-row LayerNorm of the head
             p.stats_out = c.pstats;
             p.stats_rows = stats_rows;
             VIT_TRY(launch_gemm_staged_ln<EPI_BIAS_RESIDUAL>(prec, c.tm_hid, W.tm_fc2_w, c.tm_x, c.tm_xn, p, c.sm_count, st));
@@ -952,8 +973,9 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
         pruned_tail = r == 1;
     }
     ProfScope ps(c, pf, VIT_PROF_HEAD);
-    if (pruned_tail) head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);
-    else head_ln_kernel<<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
+    if (pruned_tail) head_ln_kernel<float><<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);
+    else if (m.res16) head_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(static_cast<const __half*>(c.xn), c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
+    else head_ln_kernel<float><<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
     VIT_TRY(check_launch("head_ln"));
     head_gemm_kernel<<<dim3((kClasses + HEAD_CLASSES - 1) / HEAD_CLASSES, std::min((nb + HEAD_IMGS - 1) / HEAD_IMGS, 32)), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
                                                                                 kClasses);
@@ -971,7 +993,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const PassMode& m, const floa
         return enqueue_forward_kernels(c, e, m, d_images, nb, d_logits);
     for (auto& g : c.graphs)
         if (g.nb == nb && g.prec == m.prec && g.images == d_images && g.logits == d_logits && g.attn_exact == m.attn_exact &&
-            g.ln_fused == m.ln_fused && g.prune_last == m.prune_last && g.pdl == m.pdl) {
+            g.ln_fused == m.ln_fused && g.prune_last == m.prune_last && g.pdl == m.pdl && g.res16 == m.res16) {
             CU_TRY(cudaGraphLaunch(g.exec, c.stream));
             g_launches.fetch_add(g.launches, std::memory_order_relaxed);
             return 0;
@@ -1000,6 +1022,7 @@ int enqueue_forward(DeviceCtx& c, const Engine& e, const PassMode& m, const floa
     g.ln_fused = m.ln_fused;
     g.prune_last = m.prune_last;
     g.pdl = m.pdl;
+    g.res16 = m.res16;
     g.launches = captured;
     const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -1057,6 +1080,7 @@ void read_env_options() {
     g_opt.pdl = env_flag("VIT_PDL", 1);
     g_opt.graphs = env_flag("VIT_GRAPHS", 1);
     g_opt.host_threads = env_flag("VIT_HOST_THREADS", 1);
+    g_opt.residual16 = env_flag("VIT_RESIDUAL16", 0);
 }
 
 int configure_engine(Engine& e, int img_size, int max_batch_per_gpu, int n_gpus, const int* device_ids, int precision) {
@@ -1239,6 +1263,7 @@ int vit_cuda_set_option(int option, int value) {
         case VIT_OPT_PDL: g_opt.pdl = v; break;
         case VIT_OPT_GRAPHS: g_opt.graphs = v; break;
         case VIT_OPT_HOST_THREADS: g_opt.host_threads = v; break;
+        case VIT_OPT_RESIDUAL16: g_opt.residual16 = v; break;
         default: return set_err(VIT_E_ARG, "unknown option %d", option);
     }
     return 0;
@@ -1252,6 +1277,7 @@ int vit_cuda_get_option(int option, int* value) {
         case VIT_OPT_PDL: *value = g_opt.pdl; break;
         case VIT_OPT_GRAPHS: *value = g_opt.graphs; break;
         case VIT_OPT_HOST_THREADS: *value = g_opt.host_threads; break;
+        case VIT_OPT_RESIDUAL16: *value = g_opt.residual16; break;
         default: return set_err(VIT_E_ARG, "unknown option %d", option);
     }
     return 0;

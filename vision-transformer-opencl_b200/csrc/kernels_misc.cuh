@@ -159,14 +159,24 @@ __global__ void __launch_bounds__(256) cls_rows_ln_kernel(float* __restrict__ X,
 // One block per image, one warp per head:  s_j = q . k_j / 8 (lanes over keys), softmax in fp32 (exact maximum,
 // as ViT_seq.c:178-191), o = sum_j p_j v_j (lanes over the 64 output columns).  Also gathers the image's fp32
 // class row of the residual stream into the compact [batch][768] buffer the pruned layer tail works on.
+// X16 != nullptr: the residual stream is held in the operand type (16-bit rows, RES16 forward); the class row is widened.
 template <typename T>
-__global__ void __launch_bounds__(384) cls_attention_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ X,
+__global__ void __launch_bounds__(384) cls_attention_kernel(const uint16_t* __restrict__ qkv, const float* __restrict__ X, const T* __restrict__ X16,
                                                            T* __restrict__ ao_c, float* __restrict__ x_c, int tokens) {
     __shared__ float sp[12][640];           // one row of scores / probabilities per head
     const int img = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t row0 = static_cast<size_t>(img) * tokens;
-    if (threadIdx.x < kDim / 4)
-        reinterpret_cast<float4*>(x_c + static_cast<size_t>(img) * kDim)[threadIdx.x] = reinterpret_cast<const float4*>(X + row0 * kDim)[threadIdx.x];
+    if (threadIdx.x < kDim / 4) {
+        float4 v;
+        if (X16) {
+            const uint2 u = reinterpret_cast<const uint2*>(X16 + row0 * kDim)[threadIdx.x];
+            const float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y);
+            v = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            v = reinterpret_cast<const float4*>(X + row0 * kDim)[threadIdx.x];
+        }
+        reinterpret_cast<float4*>(x_c + static_cast<size_t>(img) * kDim)[threadIdx.x] = v;
+    }
     const uint16_t* qrow = qkv + row0 * 2304 + head * 64;
     float q[64];
 #pragma unroll
@@ -223,16 +233,28 @@ __global__ void __launch_bounds__(384) cls_attention_kernel(const uint16_t* __re
 // ---------------------------------------------------------------------------------------------
 // Final LayerNorm on the class rows only (the reference normalises all rows and keeps row 0,
 // ViT_seq.c:429-433), fp32 out.  One warp per image.
-__global__ void __launch_bounds__(256) head_ln_kernel(const float* __restrict__ X, const float* __restrict__ w,
+// TIn = float (fp32 residual rows) or the operand type (RES16 forward: 16-bit residual rows).
+template <typename TIn>
+__global__ void __launch_bounds__(256) head_ln_kernel(const TIn* __restrict__ X, const float* __restrict__ w,
                                                       const float* __restrict__ b, float* __restrict__ out,
                                                       int batch, int tokens) {
     const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (img >= batch) return;
     const int lane = threadIdx.x & 31;
-    const float4* xr = reinterpret_cast<const float4*>(X + static_cast<size_t>(img) * tokens * kDim);
     float4 v[6];
+    if constexpr (sizeof(TIn) == 4) {
+        const float4* xr = reinterpret_cast<const float4*>(X + static_cast<size_t>(img) * tokens * kDim);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+        for (int i = 0; i < 6; ++i) v[i] = xr[lane + 32 * i];
+    } else {
+        const uint2* xr = reinterpret_cast<const uint2*>(X + static_cast<size_t>(img) * tokens * kDim);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const uint2 u = xr[lane + 32 * i];
+            const float2 a = unpack2<TIn>(u.x), c2 = unpack2<TIn>(u.y);
+            v[i] = make_float4(a.x, a.y, c2.x, c2.y);
+        }
+    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);

@@ -427,6 +427,16 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 template <typename T>
+__device__ __forceinline__ float2 unpack2(uint32_t u);
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+template <typename T>
 __device__ __forceinline__ float to_float(T v);
 template <>
 __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }

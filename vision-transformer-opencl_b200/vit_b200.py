@@ -18,7 +18,7 @@ NUM_TENSORS = 152
 NUM_CLASSES = 1000
 PREC_BF16, PREC_FP16, PREC_AUTO = 0, 1, 2
 PREC_NAMES = {0: "bf16", 1: "fp16", 2: "auto"}
-OPT_ATTENTION_EXACT, OPT_CLASS_ROW_PRUNING, OPT_LN_FUSED, OPT_PDL, OPT_GRAPHS, OPT_HOST_THREADS = range(6)
+OPT_ATTENTION_EXACT, OPT_CLASS_ROW_PRUNING, OPT_LN_FUSED, OPT_PDL, OPT_GRAPHS, OPT_HOST_THREADS, OPT_RESIDUAL16 = range(7)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PROF_CATEGORIES = ["class_rows", "embed_gemm", "layernorm", "qkv_gemm", "attention", "out_gemm", "fc1_gemm", "fc2_gemm", "head"]
 
