@@ -46,13 +46,14 @@ enum {
                                 vit_cuda_init_ex with VIT_PREC_FP16: a weight does not fit FP16. */
 };
 
-/* GEMM-operand storage type.  Accumulation, residual stream, LayerNorm statistics,
- * softmax and the classifier head are always fp32. */
+/* GEMM-operand storage type.  Accumulation, LayerNorm statistics, softmax and the classifier head are always fp32,
+ * and so is the residual stream unless VIT_OPT_RESIDUAL16 is switched on. */
 enum {
     VIT_PREC_BF16 = 0,       /* BF16 operands, kind::f16 tcgen05, FP32 accumulate.  max |dlogit| vs ViT_seq ~0.03 on
                                 random-init weights: outside the stated 2e-2 + 1e-2 |ref| on ~0.3 % of the logits. */
     VIT_PREC_FP16 = 1,       /* FP16 operands (same tensor-core rate, 3 more mantissa bits; meets the stated tolerance
-                                with a 5x margin).  Values beyond 65504 overflow: init fails with VIT_E_RANGE if a
+                                with a 3x margin: max |dlogit| 0.006; ~5 % slower than BF16 because its multipliers
+                                draw more power in a power-bound step).  Values beyond 65504 overflow: init fails with VIT_E_RANGE if a
                                 weight does, and a forward whose activations do fails with VIT_E_RANGE. */
     VIT_PREC_AUTO = 2        /* default (vit_cuda_init, ViT_cuda): FP16 operands, with the BF16 operand set resident
                                 beside them (+0.17 GB).  An FP16 overflow anywhere makes a logit non-finite, which the
