@@ -47,7 +47,7 @@ enum {
 };
 
 /* GEMM-operand storage type.  Accumulation, LayerNorm statistics, softmax and the classifier head are always fp32,
- * and so is the residual stream unless VIT_OPT_RESIDUAL16 is switched on. */
+ * and so is the residual stream of the rows the head reads (see VIT_OPT_RESIDUAL16 for the other rows). */
 enum {
     VIT_PREC_BF16 = 0,       /* BF16 operands, kind::f16 tcgen05, FP32 accumulate.  max |dlogit| vs ViT_seq ~0.03 on
                                 random-init weights: outside the stated 2e-2 + 1e-2 |ref| on ~0.3 % of the logits. */
@@ -172,9 +172,12 @@ enum {
     VIT_OPT_GRAPHS            = 4,  /* default 1: passes of <= 8 images replay a captured CUDA graph */
     VIT_OPT_HOST_THREADS      = 5,  /* default 1: vit_cuda_forward feeds every GPU from its own host thread (n_gpus > 1);
                                        0: one thread issues for all GPUs in turn */
-    VIT_OPT_RESIDUAL16        = 6   /* default 0.  1: with FP16 operands and folded LayerNorm the residual stream itself is kept
-                                       in FP16 (the rows out_proj / mlp_3 update ARE the next GEMM's operand; no fp32 row, no
-                                       separate copy): -21 % HBM traffic per step, every residual add rounded to FP16 */
+    VIT_OPT_RESIDUAL16        = 6   /* default 1: with FP16 operands and folded LayerNorm the patch rows' residual stream is kept in
+                                       FP16 (the rows out_proj / mlp_3 update ARE the next GEMM's operand; no fp32 row beside
+                                       them: -21 % HBM traffic per step), while each image's class-token row -- the one row the
+                                       head reads -- keeps an fp32 master copy that the same epilogues update.  Measured against
+                                       ViT_seq this is as close as the fp32 stream (max |dlogit| 0.0053 vs 0.0060 on the bench's
+                                       parity block).  Ignored for BF16 operands.  0: fp32 residual stream for every row. */
 };
 int vit_cuda_set_option(int option, int value);
 int vit_cuda_get_option(int option, int* value);

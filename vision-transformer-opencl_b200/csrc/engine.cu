@@ -136,7 +136,7 @@ int embed_tiles_per_image(int S) {
 
 // ------------------------------------------------------------------------------------ run-time switches
 struct Options {
-    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1}, residual16{0};
+    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1}, residual16{1};
 };
 Options g_opt;
 
@@ -358,12 +358,12 @@ int launch_fold_ln(int prec, const float* W, const float* ln_w, const float* ln_
 }
 
 int launch_cls_rows(int prec, bool ln, float* x, void* xn, float2* pstats, int stats_rows, const float* cls, const float* pos, int nb,
-                    int tokens, cudaStream_t st) {
+                    int tokens, cudaStream_t st, float* cls_rows32 = nullptr) {
     if (!ln) cls_rows_kernel<<<(nb * kDim + 255) / 256, 256, 0, st>>>(x, cls, pos, nb, tokens);
     else if (prec == VIT_PREC_FP16)
-        cls_rows_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(x, static_cast<__half*>(xn), pstats, stats_rows, cls, pos, nb, tokens);
+        cls_rows_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(x, static_cast<__half*>(xn), pstats, stats_rows, cls, pos, nb, tokens, cls_rows32);
     else
-        cls_rows_ln_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(xn), pstats, stats_rows, cls, pos, nb, tokens);
+        cls_rows_ln_kernel<__nv_bfloat16><<<(nb + 7) / 8, 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(xn), pstats, stats_rows, cls, pos, nb, tokens, cls_rows32);
     return check_launch("cls_rows");
 }
 
@@ -816,7 +816,7 @@ struct ProfScope {
 struct PassMode {
     int prec;
     bool attn_exact, ln_fused, prune_last, pdl;
-    bool res16;   // residual stream in the operand type (FP16 operands + folded LayerNorm only), VIT_OPT_RESIDUAL16
+    bool res16;   // residual stream in the operand type, class rows with an fp32 master copy (FP16 operands + folded LayerNorm only), VIT_OPT_RESIDUAL16
 };
 PassMode current_mode(const Engine& e) {
     const bool fused = g_opt.ln_fused.load() != 0;
@@ -861,8 +861,8 @@ int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int 
         {
             ProfScope ps(c, pf, VIT_PROF_ATTENTION);
             if (prec == VIT_PREC_FP16)
-                cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, m.res16 ? static_cast<const __half*>(c.xn) : nullptr,
-                                                                 static_cast<__half*>(c.ao_c), c.x_c, e.tokens);
+                cls_attention_kernel<__half><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), m.res16 ? nullptr : c.x, nullptr,   // RES16: c.x_c already
+                                                                 static_cast<__half*>(c.ao_c), c.x_c, e.tokens);                       // holds the fp32 class rows
             else
                 cls_attention_kernel<__nv_bfloat16><<<nb, 384, 0, st>>>(static_cast<const uint16_t*>(c.qkv), c.x, nullptr, static_cast<__nv_bfloat16*>(c.ao_c), c.x_c, e.tokens);
             VIT_TRY(check_launch("cls_attention"));
@@ -901,6 +901,8 @@ int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int 
         if (m.res16) {
             p.stats_out = c.pstats;
             p.stats_rows = stats_rows;
+            p.tokens = e.tokens;
+            p.cls_rows32 = c.x_c;
             VIT_TRY(launch_gemm_residual16(prec, c.tm_ao, W.tm_out_w, c.tm_xn, p, c.sm_count, st));
         } else if (fused) {
             p.stats_out = c.pstats;
@@ -930,6 +932,8 @@ int enqueue_encoder_layer(DeviceCtx& c, const Engine& e, const PassMode& m, int 
         if (m.res16) {   // (the last block's statistics are not needed, but one kernel variant serves all blocks)
             p.stats_out = c.pstats;
             p.stats_rows = stats_rows;
+            p.tokens = e.tokens;
+            p.cls_rows32 = c.x_c;
             VIT_TRY(launch_gemm_residual16(prec, c.tm_hid, W.tm_fc2_w, c.tm_xn, p, c.sm_count, st));
         } else if (fused && !tail_for_head) {   // the last layer's output only feeds the class-row LayerNorm of the head
             p.stats_out = c.pstats;
@@ -955,7 +959,8 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
     const int stats_rows = static_cast<int>(c.stats_rows);
     {   // class-token rows (class_token + pos_emb, ViT_seq.c:72-101)
         ProfScope ps(c, pf, VIT_PROF_CLASS_ROWS);
-        VIT_TRY(launch_cls_rows(prec, fused, c.x, c.xn, c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens, st));
+        // (RES16: the class rows additionally start their fp32 master copy in the compact buffer c.x_c)
+        VIT_TRY(launch_cls_rows(prec, fused, c.x, c.xn, c.pstats, stats_rows, c.cls, c.pos, nb, e.tokens, st, m.res16 ? c.x_c : nullptr));
     }
     {   // conv_proj: tf32 GEMM straight from the fp32 image; class_token offset / pos_emb / token layout are TMA addressing
         ProfScope ps(c, pf, VIT_PROF_EMBED_GEMM);
@@ -974,7 +979,7 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
     }
     ProfScope ps(c, pf, VIT_PROF_HEAD);
     if (pruned_tail) head_ln_kernel<float><<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);
-    else if (m.res16) head_ln_kernel<__half><<<(nb + 7) / 8, 256, 0, st>>>(static_cast<const __half*>(c.xn), c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
+    else if (m.res16) head_ln_kernel<float><<<(nb + 7) / 8, 256, 0, st>>>(c.x_c, c.lnf_w, c.lnf_b, c.cls_ln, nb, 1);   // the fp32 master copies of the class rows
     else head_ln_kernel<float><<<(nb + 7) / 8, 256, 0, st>>>(c.x, c.lnf_w, c.lnf_b, c.cls_ln, nb, e.tokens);
     VIT_TRY(check_launch("head_ln"));
     head_gemm_kernel<<<dim3((kClasses + HEAD_CLASSES - 1) / HEAD_CLASSES, std::min((nb + HEAD_IMGS - 1) / HEAD_IMGS, 32)), 256, 0, st>>>(c.cls_ln, c.head_w, c.head_b, d_logits, nb,
@@ -1080,7 +1085,7 @@ void read_env_options() {
     g_opt.pdl = env_flag("VIT_PDL", 1);
     g_opt.graphs = env_flag("VIT_GRAPHS", 1);
     g_opt.host_threads = env_flag("VIT_HOST_THREADS", 1);
-    g_opt.residual16 = env_flag("VIT_RESIDUAL16", 0);
+    g_opt.residual16 = env_flag("VIT_RESIDUAL16", 1);
 }
 
 int configure_engine(Engine& e, int img_size, int max_batch_per_gpu, int n_gpus, const int* device_ids, int precision) {

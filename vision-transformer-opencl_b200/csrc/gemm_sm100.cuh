@@ -40,6 +40,7 @@ struct GemmParams {
     int stats_parts;          // consumer: number of partials per row to add up (6 after a residual GEMM, 1 after rowstats_cast)
     int stats_rows;           // row capacity of the stats arrays (stride between parts)
     const float* colsum;      // consumer: s[n] = sum_k W'[n][k] of the folded, rounded weights W' = ln_w (.) W
+    float* cls_rows32;        // RES16: [M / tokens][N] fp32 master copy of the class-token rows (row % tokens == 0), updated in place
 };
 
 constexpr int GEMM_BM = 128;
@@ -429,6 +430,11 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
             float st_sum = 0.f, st_sq = 0.f;   // LN producer: partial row statistics over this thread's 128 columns
+            [[maybe_unused]] float* cls32 = nullptr;   // RES16: this thread's row is a class-token row -> its fp32 master row
+            if constexpr (RES16) {
+                const int grow = m0 + row;
+                if (p.cls_rows32 && grow < p.M && grow % p.tokens == 0) cls32 = p.cls_rows32 + static_cast<size_t>(grow / p.tokens) * p.N;
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
@@ -461,11 +467,17 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         uint4* q = reinterpret_cast<uint4*>(srow + (((half * PIECES + j) ^ sw) << 4));
                         const uint4 u = *q;
                         uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        // A class-token row keeps an fp32 master copy: it is the one row the head reads, its residual adds
+                        // go straight into the logits (the other rows reach it only through the attention's averages).
+                        float2* m32 = cls32 ? reinterpret_cast<float2*>(cls32 + n0 + c * CHUNK_COLS + half * COLS_PER_WARP + 8 * j) : nullptr;
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            const float2 xr = unpack2<T>(w[h]);
-                            w[h] = pack2<T>(xr.x + (__uint_as_float(r[8 * j + 2 * h]) + bcol[8 * j + 2 * h]),
-                                            xr.y + (__uint_as_float(r[8 * j + 2 * h + 1]) + bcol[8 * j + 2 * h + 1]));
+                            float2 xr = unpack2<T>(w[h]);
+                            if (m32) xr = m32[h];
+                            xr.x += __uint_as_float(r[8 * j + 2 * h]) + bcol[8 * j + 2 * h];
+                            xr.y += __uint_as_float(r[8 * j + 2 * h + 1]) + bcol[8 * j + 2 * h + 1];
+                            if (m32) m32[h] = xr;
+                            w[h] = pack2<T>(xr.x, xr.y);
                             const float2 v = unpack2<T>(w[h]);   // statistics of the row as stored
                             st_sum += v.x + v.y;
                             st_sq = fmaf(v.x, v.x, fmaf(v.y, v.y, st_sq));

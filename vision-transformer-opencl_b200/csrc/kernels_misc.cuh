@@ -128,7 +128,8 @@ __global__ void cls_rows_kernel(float* __restrict__ X, const float* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) cls_rows_ln_kernel(float* __restrict__ X, T* __restrict__ Xc, float2* __restrict__ stats,
                                                           int stats_rows, const float* __restrict__ cls,
-                                                          const float* __restrict__ pos, int batch, int tokens) {
+                                                          const float* __restrict__ pos, int batch, int tokens,
+                                                          float* __restrict__ cls_rows32 = nullptr /* RES16: compact fp32 class rows */) {
     const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (img >= batch) return;
     const int lane = threadIdx.x & 31;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256) cls_rows_ln_kernel(float* __restrict__ X,
         const float4 a = reinterpret_cast<const float4*>(cls)[lane + 32 * i], b = reinterpret_cast<const float4*>(pos)[lane + 32 * i];
         const float4 v = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
         reinterpret_cast<float4*>(X + r * kDim)[lane + 32 * i] = v;
+        if (cls_rows32) reinterpret_cast<float4*>(cls_rows32 + static_cast<size_t>(img) * kDim)[lane + 32 * i] = v;
         uint2 o;
         o.x = pack2<T>(v.x, v.y);
         o.y = pack2<T>(v.z, v.w);
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(384) cls_attention_kernel(const uint16_t* __re
     __shared__ float sp[12][640];           // one row of scores / probabilities per head
     const int img = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t row0 = static_cast<size_t>(img) * tokens;
-    if (threadIdx.x < kDim / 4) {
+    if (threadIdx.x < kDim / 4 && (X16 || X)) {   // (neither: x_c already holds the fp32 class rows, RES16 forward)
         float4 v;
         if (X16) {
             const uint2 u = reinterpret_cast<const uint2*>(X16 + row0 * kDim)[threadIdx.x];
