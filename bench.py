@@ -33,7 +33,7 @@ FLOP_PER_IMAGE = {224: FLOP_PER_IMAGE_224, 384: 110_968_700_928}  # 384: BASELIN
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one launch at B = 1024, FP16 operands, from the ncu --set full
 # capture committed under profiles/ (r2_ncu_layer_res16.txt: the default configuration, patch rows' residual stream in FP16;
 # r2_ncu_layer.txt holds the fp32-stream capture: out_proj 1.813 GB, mlp_3 3.055 GB)
-NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_197_557_000, "out_gemm": 904_660_000, "fc1_gemm": 1_512_365_000, "fc2_gemm": 1_887_698_000}
+NCU_TRAFFIC_BYTES = {"qkv_gemm": 1_197_473_000, "out_gemm": 903_505_000, "fc1_gemm": 1_508_485_000, "fc2_gemm": 1_882_722_000}
 GEMM_FLOP_PER_ROW = {"qkv_gemm": 2 * 768 * 2304, "out_gemm": 2 * 768 * 768, "fc1_gemm": 2 * 768 * 3072, "fc2_gemm": 2 * 3072 * 768}
 
 

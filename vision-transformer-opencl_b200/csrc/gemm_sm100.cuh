@@ -79,12 +79,22 @@ struct GemmStagedSmem {
     static constexpr int BIAS_OFF = CAST_OFF + CAST_BUFS * GEMM_SLOT_BYTES;
     static constexpr int BIAS_BYTES = PRE_BYTES > 0 ? 2 * PRE_BYTES : 2 * 256 * 4;  // unstaged: [bias | colsum][256] of the current tile
     static constexpr int BAR_OFF = BIAS_OFF + BIAS_BYTES;
-    static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * SLOTS + 4;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + 3 * SLOTS + 4;
     static constexpr int DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16;  // base must be 1024-aligned (checked)
 };
 
 template <int NTHREADS>
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
+
+// -DVIT_GEMM_TRACE (tools/gemm_trace.sh; never in the product build): the first CTA's roles add up the SM cycles they spend
+// in each kind of wait and print one line per launch.
+#ifdef VIT_GEMM_TRACE
+#define TR_DECL(n) long long tr_##n = 0
+#define TR_WAIT(n, ...) do { const long long t0__ = clock64(); __VA_ARGS__; tr_##n += clock64() - t0__; } while (0)
+#else
+#define TR_DECL(n)
+#define TR_WAIT(n, ...) __VA_ARGS__
+#endif
 
 // LayerNorm folded into the GEMMs (LN = true).  The reference normalises every token row before in_proj
 // and mlp_0 (layer_norm, ViT_seq.c:103-121, called at :281 and :291).  Here no normalised activation is
@@ -163,7 +173,8 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* res_full = tempty_bar + 2;     // [SLOTS] residual chunk landed in the slot
     uint64_t* slot_free = res_full + SLOTS;  // [SLOTS] the store out of the slot has drained
-    uint64_t* pre_full = slot_free + SLOTS;  // [2] the tile's staged parameters are in shared memory (32 arrivals)
+    uint64_t* chunk_ready = slot_free + SLOTS;  // [SLOTS] RES16: every epilogue warp has updated its part of the slot (EPI_WARPS arrivals)
+    uint64_t* pre_full = chunk_ready + SLOTS;   // [2] the tile's staged parameters are in shared memory (32 arrivals)
     uint64_t* pre_free = pre_full + 2;       // [2] every epilogue warp is through with them
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pre_free + 2);
 
@@ -201,6 +212,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(&res_full[s], 1);
             mbar_init(&slot_free[s], 1);
+            mbar_init(&chunk_ready[s], EPI_WARPS);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&pre_full[s], kResidual ? 1 : 32);   // residual kernel with ONE cast staging tile: [0] = "tile drained"
@@ -223,11 +235,16 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // operands in uniform registers); one elected lane issues.
         int stage = 0;
         uint32_t phase = 0;
+        TR_DECL(empty);
+        TR_DECL(total);
+#ifdef VIT_GEMM_TRACE
+        tr_total = -clock64();
+#endif
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m0 = (tile / tiles_n) * 256 + rank * 128;
             const int n0 = (tile % tiles_n) * BN + rank * 128;
             for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                TR_WAIT(empty, mbar_wait(&empty_bar[stage], phase ^ 1));
                 if (elect_one()) {
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     // (a TMA box counts its full size towards the barrier, zero-filled out-of-bounds parts included)
@@ -245,6 +262,12 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+#ifdef VIT_GEMM_TRACE
+        tr_total += clock64();
+        if (blockIdx.x == 0 && lane == 0)
+            printf("gemm_trace producer K=%d N=%d epi=%d res16=%d tiles=%d total=%lld wait_empty=%lld\n", p.K, p.N, EPI, int(RES16),
+                   (num_tiles - pair + num_pairs - 1) / num_pairs, tr_total, tr_empty);
+#endif
     } else if (warp == W_MMA) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
         if (rank == 0) {
@@ -253,12 +276,18 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            TR_DECL(tempty);
+            TR_DECL(full);
+            TR_DECL(total);
+#ifdef VIT_GEMM_TRACE
+            tr_total = -clock64();
+#endif
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                TR_WAIT(tempty, mbar_wait(&tempty_bar[acc], acc_phase ^ 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    TR_WAIT(full, mbar_wait(&full_bar[stage], phase));
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -278,6 +307,11 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 __syncwarp();
                 if ((acc ^= 1) == 0) acc_phase ^= 1;
             }
+#ifdef VIT_GEMM_TRACE
+            tr_total += clock64();
+            if (blockIdx.x == 0 && lane == 0)
+                printf("gemm_trace mma      K=%d N=%d epi=%d res16=%d total=%lld wait_tempty=%lld wait_full=%lld\n", p.K, p.N, EPI, int(RES16), tr_total, tr_tempty, tr_full);
+#endif
         }
     } else if (warp == W_LOADER && STAGED) {
         // ------------------------------------------------------------ parameter stager (EPI_BIAS / EPI_BIAS_GELU)
@@ -350,6 +384,31 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
             }
         }
+    } else if (warp == W_TMEM) {
+        // ------------------------------------------------------------ chunk storer (RES16)
+        // The epilogue warps of the 16-bit residual kernel never wait for each other: a warp that has updated its part of
+        // a slot arrives on chunk_ready[slot] and goes on to the next chunk; this otherwise idle warp issues the chunk's
+        // TMA store once all EPI_WARPS parts are in, and hands the slot of the PREVIOUS chunk back to the loader when that
+        // chunk's store has drained.  (With the store issued by epilogue thread 0 behind a CTA-wide barrier per chunk,
+        // out_proj -- K = 768, one 3.2 us MMA per tile -- was bound by its epilogue: profiles/r2_gemm_trace.txt.)
+        if (RES16 && lane == 0) {
+            uint32_t k = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / tiles_n) * 256 + rank * 128;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int c = 0; c < NCHUNK; ++c, ++k) {
+                    const uint32_t slot = k % SLOTS;
+                    mbar_wait(&chunk_ready[slot], (k / SLOTS) & 1);
+                    tma_store_2d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, m0);
+                    tma_store_commit();
+                    if (k >= 1) {
+                        tma_store_wait_read<1>();
+                        mbar_arrive(&slot_free[(k - 1) % SLOTS]);
+                    }
+                }
+            }
+            tma_store_wait_all<0>();
+        }
     } else if (warp < EPI_WARPS) {
         // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
         const int ew = warp;
@@ -365,15 +424,28 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         uint32_t k = 0;  // running chunk counter (ring position)
         [[maybe_unused]] int tile_par = 0;
         [[maybe_unused]] uint32_t pre_phase = 0;
+        TR_DECL(tfull);
+        TR_DECL(drain);
+        TR_DECL(res);
+        TR_DECL(bar);
+        TR_DECL(store);
+        TR_DECL(pre);
+        TR_DECL(comp);
+        TR_DECL(total);
+#ifdef VIT_GEMM_TRACE
+        tr_total = -clock64();
+#endif
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m0 = (tile / tiles_n) * 256 + rank * 128;
             const int n0 = (tile % tiles_n) * BN;
             float* sb = s_bias;
+            if constexpr (RES16) sb = s_bias + tile_par * 256;   // two bias buffers: the warps drift apart by up to a tile
             float ln_rstd = 1.f, ln_nm = 0.f;  // LN consumer: this thread's row: rstd and -rstd * mean
             if constexpr (!STAGED) {
-                // Loaded by the epilogue threads themselves.  One buffer is enough: in the residual kernel every
+                // Loaded by the epilogue threads themselves.  One buffer is enough: in the fp32 residual kernel every
                 // chunk iteration below ends with a barrier after its last read of it, so nobody still reads the
-                // previous tile's values here (the other kernels regroup explicitly).  The global-memory round trip is short because each thread asked for the NEXT tile's lines
+                // previous tile's values here (the other kernels regroup explicitly; RES16 alternates two buffers,
+                // whose previous use lies before the previous tile's barrier).  The global-memory round trip is short because each thread asked for the NEXT tile's lines
                 // (prefetch.global.L1) one tile ago; TMA traffic bypasses L1, so they are still there.
                 [[maybe_unused]] float2 part[6];
                 if constexpr (LN && !kResidual) {
@@ -418,11 +490,11 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                     }
                 }
-                epi_bar_sync<EPI_THREADS>();
+                TR_WAIT(bar, epi_bar_sync<EPI_THREADS>());
             } else {
                 // staged one tile ahead by the loader warp (bias | column sums | row statistics)
                 sb = s_bias + tile_par * PRE_FLOATS;
-                mbar_wait(&pre_full[tile_par], pre_phase);
+                TR_WAIT(pre, mbar_wait(&pre_full[tile_par], pre_phase));
                 if constexpr (LN) {
                     const float2 st = reinterpret_cast<const float2*>(sb + 512)[row];
                     ln_rstd = st.x;
@@ -435,7 +507,8 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int grow = m0 + row;
                 if (p.cls_rows32 && grow < p.M && grow % p.tokens == 0) cls32 = p.cls_rows32 + static_cast<size_t>(grow / p.tokens) * p.N;
             }
-            mbar_wait(&tfull_bar[acc], acc_phase);
+
+            TR_WAIT(tfull, mbar_wait(&tfull_bar[acc], acc_phase));
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_WARP;
             // Early accumulator release: the thread's whole share of the accumulator stage (NCHUNK x
@@ -445,12 +518,18 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // end of the epilogue couples the MMA and epilogue periods (measured: MMA issuer spinning
             // on the stage barrier while the epilogue warps wait for the next accumulator).
             uint32_t racc[NCHUNK][COLS_PER_WARP];
+#ifdef VIT_GEMM_TRACE
+            tr_drain -= clock64();
+#endif
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
                 tmem_ld_x16p(taddr + c * CHUNK_COLS, racc[c]);
                 if constexpr (COLS_PER_WARP == 32) tmem_ld_x16p(taddr + c * CHUNK_COLS + 16, racc[c] + 16);
             }
             tmem_ld_wait();
+#ifdef VIT_GEMM_TRACE
+            tr_drain += clock64();
+#endif
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
@@ -461,7 +540,10 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const float* bcol = sb + c * CHUNK_COLS + half * COLS_PER_WARP;
                 const uint32_t* r = racc[c];
                 if constexpr (RES16) {
-                    mbar_wait(&res_full[slot], (k / SLOTS) & 1);
+                    TR_WAIT(res, mbar_wait(&res_full[slot], (k / SLOTS) & 1));
+#ifdef VIT_GEMM_TRACE
+                    tr_comp -= clock64();
+#endif
 #pragma unroll
                     for (int j = 0; j < PIECES; ++j) {   // this thread's 32 columns of the 64-column chunk: four 16-byte pieces
                         uint4* q = reinterpret_cast<uint4*>(srow + (((half * PIECES + j) ^ sw) << 4));
@@ -485,7 +567,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         *q = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 } else if constexpr (kResidual) {
-                    mbar_wait(&res_full[slot], (k / SLOTS) & 1);
+                    TR_WAIT(res, mbar_wait(&res_full[slot], (k / SLOTS) & 1));
                     [[maybe_unused]] uint32_t cast[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -539,14 +621,22 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                 }
                 fence_proxy_async_smem();
+                if constexpr (RES16) {   // hand this warp's part of the chunk to the storer warp and move on
+#ifdef VIT_GEMM_TRACE
+                    tr_comp += clock64();
+#endif
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&chunk_ready[slot]);
+                    continue;
+                }
                 if constexpr (!kResidual) {
                     // Each TMEM lane quarter (two warps, 32 rows) stores its own 32 x 64 piece of the chunk:
                     // the quarters only ever meet their own partner warp, so they drift apart and the MUFU
                     // pipe (two ops per GELU: the limiter of the mlp_0 epilogue) is not left idle while all
                     // eight warps gather at a chunk barrier.
                     const bool qstorer = half == 0 && lane == 0;
-                    if (qstorer) tma_store_wait_read<SLOTS - 2>();  // frees this quarter's part of the slot of chunk k + 1
-                    asm volatile("bar.sync %0, %1;" ::"r"(2 + quarter), "n"(PARTS * 32) : "memory");
+                    if (qstorer) TR_WAIT(store, tma_store_wait_read<SLOTS - 2>());  // frees this quarter's part of the slot of chunk k + 1
+                    TR_WAIT(bar, asm volatile("bar.sync %0, %1;" ::"r"(2 + quarter), "n"(PARTS * 32) : "memory"));
                     if (qstorer) {
                         tma_store_2d(&tmap_cast /* 32-row boxes of the output */, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES + quarter * 4096,
                                      n0 + c * CHUNK_COLS, m0 + quarter * 32);
@@ -554,7 +644,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                     continue;
                 }
-                epi_bar_sync<EPI_THREADS>();
+                TR_WAIT(bar, epi_bar_sync<EPI_THREADS>());
                 if (storer) {
                     if constexpr (EMBED)
                         tma_store_3d(&tmap_out, smem + L::SLOT_OFF + slot * GEMM_SLOT_BYTES, n0 + c * CHUNK_COLS, 1 + embed_patch0(tile / tiles_n), embed_img(tile / tiles_n));
@@ -580,7 +670,7 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     }
                     if constexpr (kResidual) {
                         if (k >= 1) {  // the previous chunk's store has finished reading its slot: hand it to the loader
-                            tma_store_wait_read<1>();
+                            TR_WAIT(store, tma_store_wait_read<1>());
                             mbar_arrive(&slot_free[(k - 1) % SLOTS]);
                         }
                     }
@@ -600,9 +690,16 @@ gemm_sm100_staged_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (lane == 0) mbar_arrive(&pre_free[tile_par]);
                 if ((tile_par ^= 1) == 0) pre_phase ^= 1;
             }
+            if constexpr (RES16) tile_par ^= 1;
             if ((acc ^= 1) == 0) acc_phase ^= 1;
         }
-        if (kResidual ? storer : (half == 0 && lane == 0)) tma_store_wait_all<0>();
+#ifdef VIT_GEMM_TRACE
+        tr_total += clock64();
+        if (blockIdx.x == 0 && etid == 0)
+            printf("gemm_trace epilogue K=%d N=%d epi=%d res16=%d total=%lld wait_tfull=%lld drain=%lld wait_residual=%lld barriers=%lld wait_store_read=%lld wait_params=%lld chunk_math=%lld\n",
+                   p.K, p.N, EPI, int(RES16), tr_total, tr_tfull, tr_drain, tr_res, tr_bar, tr_store, tr_pre, tr_comp);
+#endif
+        if (kResidual32 ? storer : (!kResidual && half == 0 && lane == 0)) tma_store_wait_all<0>();
     }
 
     tc_fence_before();

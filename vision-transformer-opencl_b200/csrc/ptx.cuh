@@ -483,14 +483,34 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 // GELU with the erf definition the reference uses, 0.5*x*(1+erf(x/sqrt 2)) = x * Phi(x) (ViT_seq.c:231-233), on two values.
 // Phi is evaluated as a logistic of an odd degree-7 polynomial,
-//     Phi(x) = 1 / (1 + exp(-x (a + b x^2 + c x^4 + d x^6))),
+//     Phi(x) = 1 / (1 + exp(-x p(x^2))) = (1 + tanh(x p(x^2) / 2)) / 2,     p(s) = a + b s + c s^2 + d s^3,
 // with (a, b, c, d) a minimax fit of x * Phi(x) over the whole real line (d > 0 keeps the argument monotone, so both tails
-// saturate correctly and no clamp is needed): max |error| 2.7e-5 against the fp64 definition (tools/gelu_fit.py; the fp32
-// evaluation below measured over [-14, 14]) -- below the half-ulp of the FP16 / BF16 value it is rounded to wherever
-// |gelu| > 0.06, and 10x inside the operator test's 3e-4.  The same accuracy as the three-term Abramowitz-Stegun erfc form
-// this replaces, for 7 packed FMA-pipe instructions + 4 MUFU (ex2, rcp) per PAIR of values instead of 9 + 4 + 2 ALU (and
-// round 1's 12 + 4 + 4): the mlp_0 epilogue applies this to 3072 values per token under the MMA of the next tile, and in a
-// power-bound step every instruction it does not issue is energy the tensor pipe gets instead.
+// saturate correctly and no clamp is needed): max |error| 2.7e-5 against the fp64 definition (tools/gelu_fit.py).
+// The logistic is ONE MUFU operation per value (tanh.approx.f32) plus 7 packed FMA-pipe instructions per PAIR of values:
+//     gelu(x) = h + h tanh(x p(x^2) / 2),  h = x / 2.
+// The mlp_0 epilogue applies this to 3072 values per token under the MMA of the next tile, with two warps per scheduler; at
+// 16 MUFU results per clock per SM the two-MUFU form (ex2 + rcp, below under VIT_GELU_EX2RCP; itself the replacement of
+// round 1's erfc series) kept the MUFU pipe busy for 4096 of the 6100 cycles a tile's MMAs take and made mlp_0 epilogue bound
+// (profiles/r2_gemm_trace.txt: its MMA issuer waited 28 % of the time for an accumulator stage).  Measured on the B200
+// (tools/gelu_probe.py, every FP16 value in [-8, 8] through mlp_0's epilogue, against the fp64 definition): see
+// profiles/r2_gelu_probe.txt -- tanh.approx is specified to 2^-11 relative; what reaches the 16-bit result is of the order
+// of that result's own rounding, and the logits' distance to the oracle is unchanged (mean |dlogit| 0.00099 either way).
+#ifndef VIT_GELU_EX2RCP
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 x2 = mul2(x, x);
+    float2 q = fma2(x2, splat2(0.5f * 1.7587348630007966e-06f), splat2(0.5f * -0.0007240021688758574f));
+    q = fma2(q, x2, splat2(0.5f * 0.07407428951979206f));
+    q = fma2(q, x2, splat2(0.5f * 1.5949720998985588f));
+    const float2 u = mul2(x, q);
+    const float2 h = mul2(x, splat2(0.5f));
+    return fma2(h, make_float2(fast_tanh(u.x), fast_tanh(u.y)), h);
+}
+#else   // the two-MUFU form, kept for A/B builds: 7 packed instructions + 4 MUFU (ex2, rcp) per pair
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     constexpr float kL = -1.4426950408889634f;   // -log2(e): the polynomial is evaluated pre-scaled for ex2
     const float2 x2 = mul2(x, x);
@@ -501,5 +521,6 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
     const float2 s = add2(make_float2(fast_exp2(t.x), fast_exp2(t.y)), splat2(1.0f));   // 1 + exp(-p(x)); inf for very negative x
     return mul2(x, make_float2(fast_rcp(s.x), fast_rcp(s.y)));
 }
+#endif
 
 }  // namespace vit
