@@ -55,6 +55,31 @@ def test_linear_bias_gelu(vit, oracle, prec):
     _close(got, ref, OUT_RTOL[prec], 3e-4, "linear+bias+gelu")
 
 
+def test_gelu_on_every_fp16_input(vit, oracle):
+    """The GELU of mlp_0's epilogue (gelu, ViT_seq.c:231-233: 0.5 x (1 + erf(x / sqrt 2))) on EVERY FP16 value in [-8, 8]: the
+    values pass through vit_cuda_op_linear with identity weights and zero bias, so what comes back is the epilogue's GELU
+    rounded to FP16.  It is evaluated through one MUFU.TANH per value, which the ISA only specifies to 2^-11 relative: this test
+    is the accuracy statement -- the result's own FP16 rounding (half an ulp = 2^-11 |gelu|) plus 1e-4, against the oracle's
+    restatement of the reference function (measured on a B200: 8.7e-5 beyond the rounding nowhere, profiles/r2_gelu_probe.txt)."""
+    vals = np.arange(0, 1 << 16, dtype=np.uint16).view(np.float16).astype(np.float32)
+    vals = vals[np.isfinite(vals) & (np.abs(vals) <= 8.0)]
+    k = 768
+    rows = (vals.size + k - 1) // k
+    x = np.zeros(rows * k, np.float32)
+    x[:vals.size] = vals
+    x = np.ascontiguousarray(x.reshape(rows, k))
+    got = vit.op_linear(x, np.ascontiguousarray(np.eye(k, dtype=np.float32)), np.zeros(k, np.float32),
+                        epilogue=vit.EPI_BIAS_GELU, precision=vit.PREC_FP16)
+    ref = oracle.gelu(x)
+    assert np.isfinite(got).all()
+    _close(got, ref, 2.0 ** -11, 1e-4, "gelu on every fp16 input in [-8, 8]")
+    # the tails: exactly x for large x, zero (to 2e-6) for very negative x -- no clamp, no NaN from the saturated logistic
+    big = np.ascontiguousarray(np.tile(np.array([60000.0, -60000.0, 30.0, -30.0, 12.0, -12.0, 0.0, -0.0], np.float32), (128, k // 8)))
+    got = vit.op_linear(big, np.ascontiguousarray(np.eye(k, dtype=np.float32)), np.zeros(k, np.float32), epilogue=vit.EPI_BIAS_GELU, precision=vit.PREC_FP16)
+    assert np.array_equal(got[big > 0], big[big > 0])
+    assert np.all(np.abs(got[big <= 0]) <= 2e-6)
+
+
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("m,n,k", [(197, 768, 768), (197, 768, 3072), (2 * 197, 768, 3072)])
 def test_linear_bias_residual(vit, oracle, prec, m, n, k):
