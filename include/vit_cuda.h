@@ -113,6 +113,25 @@ int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* firs
  * several GPUs pull from the same host memory at once -- a pass whose copy is slower than the previous pass's kernels would
  * otherwise wait for it (measured at 8 GPUs in one process: 47.8 ms per 8192 images with the fixed factor 3). */
 int vit_cuda_pass_schedule_growth(int n_images, int max_batch, int staged, int growth_percent, int* first, int* count, int cap);
+/* The schedule vit_cuda_forward uses for pinned input (VIT_OPT_WAVE_PASSES, default on), from a cost model of the pipeline: the
+ * kernels of a pass of n images take fixed_us_per_pass + kernel_us_per_image * n (measured on a B200: ~0.7 ms + 33 us * n at
+ * 224x224 -- some sixty kernels, each with its own fill and drain), its host-to-device copy copy_us_per_image * n (11 us at
+ * 55 GB/s), the copies run back to back.  Pass i + 1 is the largest whose copy still hides under pass i's kernels (10 % reserve);
+ * among the pass counts P the one with the smallest exposed cost -- the first pass's copy + P fixed costs -- is taken, with the
+ * smallest first pass that reaches n_images in P passes.  (1024, 1024, 10.9, 33, 700) -> 68 + 243 + 713: three passes instead of
+ * the geometric schedule's four.  vit_cuda_forward fits the three numbers per GPU to the pass times of its previous calls. */
+int vit_cuda_pass_schedule_model(int n_images, int max_batch, double copy_us_per_image, double kernel_us_per_image, double fixed_us_per_pass,
+                                 int* first, int* count, int cap);
+/* ... and every schedule is then re-cut at wave-efficient sizes (VIT_OPT_WAVE_PASSES; shown here for the geometric one).
+ * The GEMMs are persistent over sm_count / 2 CTA pairs with 256-row tiles, so a pass costs whole waves of tiles: 32 images of
+ * 197 tokens are 25 row tiles = 75 out_proj / mlp_3 tiles = TWO waves on a 148-SM part, 31 images are one; 128 images need
+ * 5 / 13 / 17 waves (N = 768 / 2304 / 3072), 127 need 4 / 12 / 16.  Every pass but the last becomes the size in
+ * [0.8, 1.0] x its scheduled size ([0.8, 1.08] below 128 images) with the fewest tile waves per image; what that leaves over
+ * moves to the later passes.
+ * tokens = (img_size / 16)^2 + 1.  Pure host arithmetic, like the functions above: (1024, 1024, pinned, 300 %, 197, 148) ->
+ * 31 + 96 + 288 + 609. */
+int vit_cuda_pass_schedule_waves(int n_images, int max_batch, int staged, int growth_percent, int tokens, int sm_count,
+                                 int* first, int* count, int cap);
 
 /* Device-resident variant for one GPU slot (0 <= gpu_slot < n_gpus): d_images and d_logits
  * are device pointers on that GPU, n <= max_batch_per_gpu.  Work is enqueued on the
@@ -163,7 +182,7 @@ int vit_cuda_set_attention_exact(int on);
 int vit_cuda_set_class_row_pruning(int on);
 
 /* Run-time switches (all also readable).  Each has an environment variable of the same meaning that is read ONCE,
- * at vit_cuda_init*: VIT_ATTN_EXACT, VIT_PRUNE_LAST, VIT_LN_FUSED, VIT_PDL, VIT_GRAPHS, VIT_HOST_THREADS, VIT_RESIDUAL16. */
+ * at vit_cuda_init*: VIT_ATTN_EXACT, VIT_PRUNE_LAST, VIT_LN_FUSED, VIT_PDL, VIT_GRAPHS, VIT_HOST_THREADS, VIT_RESIDUAL16, VIT_WAVE_PASSES. */
 enum {
     VIT_OPT_ATTENTION_EXACT   = 0,  /* 1: always the exact two-pass softmax (default 0, see vit_cuda_set_attention_exact) */
     VIT_OPT_CLASS_ROW_PRUNING = 1,  /* default 1, see vit_cuda_set_class_row_pruning */
@@ -172,12 +191,15 @@ enum {
     VIT_OPT_GRAPHS            = 4,  /* default 1: passes of <= 8 images replay a captured CUDA graph */
     VIT_OPT_HOST_THREADS      = 5,  /* default 1: vit_cuda_forward feeds every GPU from its own host thread (n_gpus > 1);
                                        0: one thread issues for all GPUs in turn */
-    VIT_OPT_RESIDUAL16        = 6   /* default 1: with FP16 operands and folded LayerNorm the patch rows' residual stream is kept in
+    VIT_OPT_RESIDUAL16        = 6,  /* default 1: with FP16 operands and folded LayerNorm the patch rows' residual stream is kept in
                                        FP16 (the rows out_proj / mlp_3 update ARE the next GEMM's operand; no fp32 row beside
                                        them: -21 % HBM traffic per step), while each image's class-token row -- the one row the
                                        head reads -- keeps an fp32 master copy that the same epilogues update.  Measured against
                                        ViT_seq this is as close as the fp32 stream (max |dlogit| 0.0053 vs 0.0060 on the bench's
                                        parity block).  Ignored for BF16 operands.  0: fp32 residual stream for every row. */
+    VIT_OPT_WAVE_PASSES       = 7   /* default 1: vit_cuda_forward sizes its passes by the measured cost model
+                                       (vit_cuda_pass_schedule_model) and cuts them at wave-efficient sizes
+                                       (vit_cuda_pass_schedule_waves); 0: the plain geometric schedule */
 };
 int vit_cuda_set_option(int option, int value);
 int vit_cuda_get_option(int option, int* value);

@@ -360,7 +360,7 @@ def test_engine_options_unfused_layernorm_pdl_graphs(vit, weights224, ref16):
         base, top1 = eng.forward(imgs8, want_top1=True)
         small = [eng.forward(np.ascontiguousarray(imgs[3:5])) for _ in range(3)]     # plain launches, capture, replay
         assert np.array_equal(small[0], small[1]) and np.array_equal(small[0], small[2]) and np.array_equal(small[0], base[3:5])
-        for opt in (vit.OPT_PDL, vit.OPT_GRAPHS):
+        for opt in (vit.OPT_PDL, vit.OPT_GRAPHS, vit.OPT_WAVE_PASSES):
             assert eng.get_option(opt) == 1
             eng.set_option(opt, 0)
             assert np.array_equal(eng.forward(imgs8), base), f"option {opt} changed the result"

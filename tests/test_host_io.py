@@ -143,6 +143,67 @@ def test_pass_schedule_covers_the_shard_with_a_small_first_pass(vit):
         vit.pass_schedule(100000, 1)   # more than 64 passes
 
 
+def _wave_cost(nb, tokens=197, pairs=74):
+    """Tile waves of one pass on `pairs` CTA pairs, in units of one K = 768 wave: out_proj + mlp_3 (3 column tiles of 256,
+    K = 768 + 3072), in_proj (9), mlp_0 (12) -- the model vit_cuda_pass_schedule_waves optimises."""
+    tm = -(-nb * tokens // 256)
+    w = lambda tiles_n: -(-tm * tiles_n // pairs)
+    return 5 * w(3) + w(9) + w(12)
+
+
+def test_wave_efficient_pass_schedule(vit):
+    """vit_cuda_pass_schedule_waves, the schedule vit_cuda_forward runs: the geometric schedule re-cut at sizes that fill whole
+    waves of GEMM tiles.  Complete and contiguous, within the workspace, every pass within [0.8, 1.08] of a geometric ramp's
+    step (so its copy still hides), no stub pass at the end, and never more tile waves than the plain schedule."""
+    assert vit.pass_schedule_waves(1024, 1024) == [(0, 31), (31, 96), (127, 288), (415, 609)]     # from 32 + 96 + 288 + 608
+    assert [c for _, c in vit.pass_schedule_waves(1024, 1024, staged=True)] == [63] + [127] * 7 + [72]
+    assert _wave_cost(31) < _wave_cost(32) and _wave_cost(127) < _wave_cost(128)     # the boundaries the header quotes
+    for tokens, sm in [(197, 148), (577, 148), (197, 132), (5, 148)]:
+        for staged in (False, True):
+            for growth in (300, 250, 160, 100):
+                for n, mb in [(0, 8), (1, 1), (5, 1024), (33, 1024), (100, 16), (100, 1024), (1024, 1024), (1024, 256), (8192, 1024), (5000, 999)]:
+                    if (n / min(mb, 32) > 40 and growth == 100) or (staged and n / min(mb, 128) > 60):   # beyond the wrappers' pass arrays
+                        continue
+                    sched = vit.pass_schedule_waves(n, mb, tokens=tokens, sm_count=sm, staged=staged, growth_percent=growth)
+                    plain = vit.pass_schedule(n, mb, staged=staged, growth_percent=growth)
+                    assert sum(c for _, c in sched) == n
+                    assert [f for f, _ in sched] == [int(v) for v in np.cumsum([0] + [c for _, c in sched[:-1]])][:len(sched)]
+                    assert all(0 < c <= mb for _, c in sched)
+                    if n:
+                        assert sched[0][1] <= max(plain[0][1] + plain[0][1] // 12, min(n, mb) if n - plain[0][1] < 16 else 0)
+                    if len(sched) > 1 and sched[-2][1] + sched[-1][1] <= mb:
+                        assert sched[-1][1] >= min(16, sched[-2][1] // 4)                # no stub at the end
+                    pairs = sm // 2
+                    cost = sum(_wave_cost(c, tokens, pairs) for _, c in sched)
+                    assert cost <= sum(_wave_cost(c, tokens, pairs) for _, c in plain) + 7 * max(0, len(sched) - len(plain))
+    with pytest.raises(vit.VitCudaError):
+        vit.pass_schedule_waves(1024, 1024, tokens=0)
+
+
+def test_cost_model_pass_schedule(vit):
+    """vit_cuda_pass_schedule_model: pass sizes from (copy us / image, kernel us / image, fixed us / pass).  Complete, contiguous,
+    within the workspace; every pass's copy hides under the kernels of the pass before it (10 % reserve) unless the copies are
+    the slower side (then equal passes); the pass count weighs the exposed first copy against the fixed cost per pass."""
+    assert [c for _, c in vit.pass_schedule_model(1024, 1024, 10.9, 33.0, 700.0)] == [68, 243, 713]
+    assert vit.pass_schedule_model(1024, 1024, 10.9, 33.0, 1e7) == [(0, 1024)]                   # passes cost too much: one
+    assert vit.pass_schedule_model(1024, 1024, 10.9, 33.0, 0.0)[0] == (0, 1)                      # passes are free: start at once
+    assert [c for _, c in vit.pass_schedule_model(1024, 1024, 40.0, 33.0, 700.0)] == [128] * 8   # copy bound: equal passes
+    assert vit.pass_schedule_model(0, 8, 10.9, 33.0, 700.0) == []
+    for h, k, fx in [(10.9, 33.0, 700.0), (21.5, 33.0, 700.0), (32.0, 112.0, 900.0), (40.0, 33.0, 700.0), (5.0, 50.0, 0.0), (10.9, 33.0, 5000.0)]:
+        for n, mb in [(1, 1), (5, 1024), (33, 1024), (100, 16), (1024, 1024), (1024, 256), (8192, 1024), (5000, 999)]:
+            sched = vit.pass_schedule_model(n, mb, h, k, fx)
+            assert sum(c for _, c in sched) == n and all(0 < c <= mb for _, c in sched)
+            assert [f for f, _ in sched] == [int(v) for v in np.cumsum([0] + [c for _, c in sched[:-1]])]
+            for (_, a), (_, b) in zip(sched, sched[1:]):
+                assert b <= max(a, 0.9 * (fx + k * a) / h) + 1
+            # not worse than one pass, and not worse than starting with 32 images and tripling (the plain schedule's shape)
+            exposed = h * sched[0][1] + fx * len(sched)
+            assert exposed <= h * min(n, mb) + fx * -(-n // mb) + 1e-6
+    for bad in [(1024, 1024, 0.0, 33.0, 700.0), (1024, 1024, 10.9, -1.0, 700.0), (1024, 0, 10.9, 33.0, 700.0)]:
+        with pytest.raises(vit.VitCudaError):
+            vit.pass_schedule_model(*bad)
+
+
 def test_weight_cache_blob_round_trip_and_damage_detection(vit, tmp_path):
     """The single-file weight cache: bit-exact round trip of all 152 tensors, and a flipped byte, a
     truncated file or a foreign file are refused."""

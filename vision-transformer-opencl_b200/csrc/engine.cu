@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -136,9 +137,10 @@ int embed_tiles_per_image(int S) {
 
 // ------------------------------------------------------------------------------------ run-time switches
 struct Options {
-    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1}, residual16{1};
+    std::atomic<int> attn_exact{0}, prune_last{1}, ln_fused{1}, pdl{1}, graphs{1}, host_threads{1}, residual16{1}, wave_passes{1};
 };
 Options g_opt;
+int snap_schedule(std::vector<int>& first, std::vector<int>& count, int n_pass, int n_images, int max_batch, int tokens, int pairs);
 
 int env_flag(const char* name, int dflt) {
     const char* s = getenv(name);
@@ -490,6 +492,8 @@ struct DeviceCtx {
     // timing events around every pass's H2D copy and kernels, read after the call; exponential averages in ms per image
     std::vector<cudaEvent_t> tm_events;      // 4 per pass: copy start / stop, kernels start / stop
     double h2d_ms_per_image = 0, kernel_ms_per_image = 0;
+    double pass_fixed_ms = 0, pass_ms_per_image = 0;
+    cudaEvent_t img_release = nullptr;   // set by run_shard: recorded right behind conv_proj, the only kernel that reads the image buffer   // kernels of a pass ~ pass_fixed_ms + pass_ms_per_image * images (fit over a call's passes)
     char err[512] = "";   // failure text of this slot's feeding thread
     // optional per-kernel-category timing (vit_cuda_profile_*): event pairs around launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[VIT_PROF_NCAT];
@@ -970,6 +974,10 @@ int enqueue_forward_kernels(DeviceCtx& c, const Engine& e, const PassMode& m, co
             p.stats_rows = stats_rows;
         }
         VIT_TRY(launch_gemm_embed(prec, fused, *tm_img, c.tm_conv_w, c.tm_x3, c.tm_xn3, c.tm_pos, p, c.sm_count, st));
+        if (c.img_release) {   // the image buffer is free for the copy of the pass after next (never set while capturing a graph)
+            CU_TRY(cudaEventRecord(c.img_release, st));
+            c.img_release = nullptr;
+        }
     }
     bool pruned_tail = false;
     for (int l = 0; l < kDepth; ++l) {
@@ -1086,6 +1094,7 @@ void read_env_options() {
     g_opt.graphs = env_flag("VIT_GRAPHS", 1);
     g_opt.host_threads = env_flag("VIT_HOST_THREADS", 1);
     g_opt.residual16 = env_flag("VIT_RESIDUAL16", 1);
+    g_opt.wave_passes = env_flag("VIT_WAVE_PASSES", 1);
 }
 
 int configure_engine(Engine& e, int img_size, int max_batch_per_gpu, int n_gpus, const int* device_ids, int precision) {
@@ -1269,6 +1278,7 @@ int vit_cuda_set_option(int option, int value) {
         case VIT_OPT_GRAPHS: g_opt.graphs = v; break;
         case VIT_OPT_HOST_THREADS: g_opt.host_threads = v; break;
         case VIT_OPT_RESIDUAL16: g_opt.residual16 = v; break;
+        case VIT_OPT_WAVE_PASSES: g_opt.wave_passes = v; break;
         default: return set_err(VIT_E_ARG, "unknown option %d", option);
     }
     return 0;
@@ -1283,6 +1293,7 @@ int vit_cuda_get_option(int option, int* value) {
         case VIT_OPT_GRAPHS: *value = g_opt.graphs; break;
         case VIT_OPT_HOST_THREADS: *value = g_opt.host_threads; break;
         case VIT_OPT_RESIDUAL16: *value = g_opt.residual16; break;
+        case VIT_OPT_WAVE_PASSES: *value = g_opt.wave_passes; break;
         default: return set_err(VIT_E_ARG, "unknown option %d", option);
     }
     return 0;
@@ -1372,6 +1383,63 @@ int vit_cuda_pass_schedule_growth(int n_images, int max_batch, int staged, int g
     return n;
 }
 
+int vit_cuda_pass_schedule_model(int n_images, int max_batch, double copy_us_per_image, double kernel_us_per_image, double fixed_us_per_pass,
+                                 int* first, int* count, int cap) {
+    if (n_images < 0 || max_batch <= 0 || !first || !count || cap <= 0 || !(copy_us_per_image > 0) || !(kernel_us_per_image > 0) || !(fixed_us_per_pass >= 0))
+        return set_err(VIT_E_ARG, "bad schedule arguments");
+    if (n_images == 0) return 0;
+    // the largest pass whose copy hides under a pass of `prev` images (10 % reserve), never smaller than that pass
+    auto next_size = [&](int prev) {
+        const double fit = 0.9 * (fixed_us_per_pass + kernel_us_per_image * prev) / copy_us_per_image;
+        return static_cast<int>(std::min<double>(max_batch, std::max<double>(prev, fit)));
+    };
+    auto covered = [&](int n0, int passes) {
+        long long sum = 0;
+        for (int i = 0, sz = n0; i < passes && sum < n_images; ++i, sz = next_size(sz)) sum += sz;
+        return sum;
+    };
+    int best_p = 0, best_n0 = 0;
+    double best_cost = 0;
+    const int n0_max = std::min(n_images, max_batch);
+    for (int p = 1; p <= cap; ++p) {
+        if (covered(n0_max, p) < n_images) continue;
+        int lo = 1, hi = n0_max;   // the smallest first pass with which p passes reach n_images
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (covered(mid, p) >= n_images) hi = mid;
+            else lo = mid + 1;
+        }
+        const double cost = copy_us_per_image * lo + fixed_us_per_pass * p;   // what the pipeline does not hide
+        if (best_p == 0 || cost < best_cost) {
+            best_p = p;
+            best_n0 = lo;
+            best_cost = cost;
+        }
+        if (lo == 1) break;   // more passes cannot make the first one smaller
+    }
+    if (best_p == 0) return set_err(VIT_E_ARG, "pass schedule of %d images with max_batch %d needs more than %d passes", n_images, max_batch, cap);
+    int n = 0;
+    for (int done = 0, sz = best_n0; done < n_images; sz = next_size(sz), ++n) {
+        first[n] = done;
+        count[n] = std::min(sz, n_images - done);
+        done += count[n];
+    }
+    return n;
+}
+
+int vit_cuda_pass_schedule_waves(int n_images, int max_batch, int staged, int growth_percent, int tokens, int sm_count, int* first, int* count, int cap) {
+    if (tokens <= 0 || sm_count < 2) return set_err(VIT_E_ARG, "bad schedule arguments");
+    const int worst = std::max(cap, n_images / std::min(std::max(max_batch, 1), 32) + 40);
+    std::vector<int> f(worst), c(worst);
+    int n = vit_cuda_pass_schedule_growth(n_images, max_batch, staged, growth_percent, f.data(), c.data(), worst);
+    if (n < 0) return n;
+    n = snap_schedule(f, c, n, n_images, max_batch, tokens, sm_count / 2);
+    if (n > cap) return set_err(VIT_E_ARG, "pass schedule of %d images with max_batch %d needs more than %d passes", n_images, max_batch, cap);
+    std::copy(f.begin(), f.begin() + n, first);
+    std::copy(c.begin(), c.begin() + n, count);
+    return n;
+}
+
 int vit_cuda_pass_schedule_ex(int n_images, int max_batch, int staged, int* first, int* count, int cap) {
     return vit_cuda_pass_schedule_growth(n_images, max_batch, staged, 300, first, count, cap);
 }
@@ -1422,6 +1490,50 @@ int schedule_growth(const DeviceCtx& c) {
 
 // One slot's shard of a host call: its passes, H2D copies on the copy stream into alternating image buffers under the
 // kernels of the previous pass, logits back per pass; ends with the slot's stream synchronised and its status flags read.
+// Wave-aware pass sizes.  The GEMMs are persistent over sm_count / 2 CTA pairs with 256-row tiles, so a pass costs whole waves:
+// 32 images are 25 row tiles = 75 out_proj / mlp_3 tiles = TWO waves on 74 pairs, 31 images are 24 row tiles = one; 128 images
+// need 5 / 13 / 17 waves (N = 768 / 2304 / 3072) where 127 need 4 / 12 / 16.  Cost of a pass in units of one K = 768 tile wave:
+// out_proj + mlp_3 (K = 768 + 3072, 3 column tiles), in_proj (9), mlp_0 (12).
+long long pass_wave_cost(int nb, int tokens, int pairs) {
+    const long long tm = (static_cast<long long>(nb) * tokens + 255) / 256;
+    auto waves = [&](int tiles_n) { return (tm * tiles_n + pairs - 1) / pairs; };
+    return 5 * waves(3) + waves(9) + waves(12);
+}
+// The most wave-efficient size in [0.8, 1.0] x target ([0.8, 1.08] below 128 images; not above limit); ties go to the larger pass.
+int snap_pass_count(int target, int limit, int tokens, int pairs) {
+    if (target >= limit) return limit;   // the shard's last pass takes what is left
+    int best = target;
+    double best_eff = static_cast<double>(target) / pass_wave_cost(target, tokens, pairs);
+    // (upwards only for small passes, where 8 % are a few images: a larger pass's copy must still hide under the pass before it)
+    for (int nb = std::max(1, target * 4 / 5); nb <= std::min(limit, target < 128 ? target + target / 12 : target); ++nb) {
+        const double eff = static_cast<double>(nb) / pass_wave_cost(nb, tokens, pairs);
+        if (eff > best_eff * (1 + 1e-9) || (eff > best_eff * (1 - 1e-9) && nb > best)) {
+            best = nb;
+            best_eff = eff;
+        }
+    }
+    return best;
+}
+// Re-cut a shard's schedule (vit_cuda_pass_schedule_growth: sizes from the copy / kernel rates) at wave-efficient sizes.
+int snap_schedule(std::vector<int>& first, std::vector<int>& count, int n_pass, int n_images, int max_batch, int tokens, int pairs) {
+    std::vector<int> target(count.begin(), count.begin() + n_pass);
+    int n = 0;
+    for (int done = 0; done < n_images; ++n) {
+        if (n == static_cast<int>(first.size())) {
+            first.push_back(0);
+            count.push_back(0);
+        }
+        const int left = n_images - done;
+        const int want = n < n_pass ? target[n] : std::min(max_batch, left);
+        first[n] = done;
+        count[n] = snap_pass_count(std::min(want, left), std::min(max_batch, left), tokens, pairs);
+        const int rest = left - count[n];   // no stub of a pass at the end: a pass has a fixed cost of ~60 launches
+        if (rest > 0 && rest < std::max(16, count[n] / 4) && left <= max_batch) count[n] = left;
+        done += count[n];
+    }
+    return n;
+}
+
 // Runs on the slot's own host thread when the engine has several GPUs: a gather of pass i + 1 for one GPU
 // must not hold up the enqueueing for another.
 int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
@@ -1441,8 +1553,21 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
     // ~25 GB/s each: the 608-image pass then waits 10 ms for its copy), so the factor follows the measured rates.
     const int worst = job.per_gpu / std::min(e.max_batch, 32) + 40;
     std::vector<int> pass_first(worst), pass_count(worst);
-    const int n_pass = vit_cuda_pass_schedule_growth(job.per_gpu, e.max_batch, staged ? 1 : 0, schedule_growth(c), pass_first.data(), pass_count.data(), worst);
+    const bool tuned = g_opt.wave_passes.load() != 0;
+    int n_pass;
+    if (tuned && !staged) {
+        // pinned input: sizes from the cost model of this GPU's pipeline (measured in the previous calls; before that, what a
+        // lone B200 on PCIe Gen5 shows: 55 GB/s of copies, 34 us of kernels per 197-token image, 0.7 ms per pass)
+        const double img_bytes = static_cast<double>(img_elems) * sizeof(float);
+        const double copy_us = c.h2d_ms_per_image > 0 ? 1e3 * c.h2d_ms_per_image : img_bytes / 55e3;
+        const double kern_us = c.pass_ms_per_image > 0 ? 1e3 * c.pass_ms_per_image : 34.3 * std::pow(e.tokens / 197.0, 1.1);
+        const double fixed_us = c.pass_ms_per_image > 0 ? 1e3 * c.pass_fixed_ms : 700.0;
+        n_pass = vit_cuda_pass_schedule_model(std::min(job.per_gpu, hi - lo), e.max_batch, copy_us, kern_us, fixed_us, pass_first.data(), pass_count.data(), worst);
+    } else {
+        n_pass = vit_cuda_pass_schedule_growth(job.per_gpu, e.max_batch, staged ? 1 : 0, schedule_growth(c), pass_first.data(), pass_count.data(), worst);
+    }
     if (n_pass < 0) return n_pass;
+    if (tuned) n_pass = snap_schedule(pass_first, pass_count, n_pass, std::min(job.per_gpu, hi - lo), e.max_batch, e.tokens, c.sm_count / 2);
     const bool timing = !staged && !e.profiling;
     if (timing)
         while (c.tm_events.size() < static_cast<size_t>(4 * n_pass)) {
@@ -1496,10 +1621,15 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
         CU_TRY(cudaEventRecord(c.ev_h2d[buf], c.copy_stream));
         CU_TRY(cudaStreamWaitEvent(c.stream, c.ev_h2d[buf], 0));
         if (timing) CU_TRY(cudaEventRecord(c.tm_events[4 * pass + 2], c.stream));
-        VIT_TRY(enqueue_forward(c, e, job.mode, c.images[buf], nb, c.logits));
+        c.img_release = c.ev_done[buf];
+        const int frc = enqueue_forward(c, e, job.mode, c.images[buf], nb, c.logits);
+        if (c.img_release) {   // not taken (graph replay of a small pass, or an error): the buffer is free when the pass is through
+            c.img_release = nullptr;
+            if (!frc) CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
+        }
+        VIT_TRY(frc);
         if (timing) CU_TRY(cudaEventRecord(c.tm_events[4 * pass + 3], c.stream));
         n_timed = pass + 1;
-        CU_TRY(cudaEventRecord(c.ev_done[buf], c.stream));
         if (job.logits_pinned) {
             CU_TRY(cudaMemcpyAsync(job.logits_out + static_cast<size_t>(first) * kClasses, c.logits,
                                    static_cast<size_t>(nb) * kClasses * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
@@ -1537,6 +1667,39 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
             h2d_ms += a;
             k_ms += b;
             imgs += nb;
+        }
+        static const int pass_trace = env_flag("VIT_PASS_TRACE", 0);   // diagnosis: the call's timeline on stderr
+        if (pass_trace) {
+            for (int pass = 0; pass < n_timed; ++pass) {
+                float t[4] = {0, 0, 0, 0};
+                for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c.tm_events[0], c.tm_events[4 * pass + i]);
+                fprintf(stderr, "pass_trace gpu %d pass %d images %d: copy %.3f..%.3f ms, kernels %.3f..%.3f ms\n", g, pass, pass_count[pass], t[0], t[1], t[2], t[3]);
+            }
+            cudaGetLastError();
+        }
+        // kernels of a pass = fixed + per-image * images: least squares over this call's passes (needs two different sizes)
+        {
+            double sn = 0, st = 0, snn = 0, snt = 0;
+            int m = 0;
+            for (int pass = 0; pass < n_timed; ++pass) {
+                float b = 0;
+                if (cudaEventElapsedTime(&b, c.tm_events[4 * pass + 2], c.tm_events[4 * pass + 3]) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                const double nb = pass_count[pass];
+                sn += nb, st += b, snn += nb * nb, snt += nb * b;
+                ++m;
+            }
+            const double det = m * snn - sn * sn;
+            if (m >= 2 && det > 0) {
+                const double slope = (m * snt - sn * st) / det, icpt = (st - slope * sn) / m;
+                if (slope > 0 && icpt >= 0 && icpt < 5.0) {
+                    const double w = c.pass_ms_per_image > 0 ? 0.5 : 1.0;
+                    c.pass_ms_per_image = (1 - w) * c.pass_ms_per_image + w * slope;
+                    c.pass_fixed_ms = (1 - w) * c.pass_fixed_ms + w * icpt;
+                }
+            }
         }
         if (imgs > 0 && h2d_ms > 0 && k_ms > 0) {
             const double w = c.h2d_ms_per_image > 0 ? 0.5 : 1.0;

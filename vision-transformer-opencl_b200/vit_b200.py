@@ -18,7 +18,7 @@ NUM_TENSORS = 152
 NUM_CLASSES = 1000
 PREC_BF16, PREC_FP16, PREC_AUTO = 0, 1, 2
 PREC_NAMES = {0: "bf16", 1: "fp16", 2: "auto"}
-OPT_ATTENTION_EXACT, OPT_CLASS_ROW_PRUNING, OPT_LN_FUSED, OPT_PDL, OPT_GRAPHS, OPT_HOST_THREADS, OPT_RESIDUAL16 = range(7)
+OPT_ATTENTION_EXACT, OPT_CLASS_ROW_PRUNING, OPT_LN_FUSED, OPT_PDL, OPT_GRAPHS, OPT_HOST_THREADS, OPT_RESIDUAL16, OPT_WAVE_PASSES = range(8)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PROF_CATEGORIES = ["class_rows", "embed_gemm", "layernorm", "qkv_gemm", "attention", "out_gemm", "fc1_gemm", "fc2_gemm", "head"]
 
@@ -62,6 +62,8 @@ _sig("vit_cuda_forward_scattered", C.c_int, C.POINTER(_f32p), C.c_int, C.c_void_
 _sig("vit_cuda_pass_schedule", C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_pass_schedule_ex", C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_pass_schedule_growth", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
+_sig("vit_cuda_pass_schedule_model", C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _i32p, _i32p, C.c_int)
+_sig("vit_cuda_pass_schedule_waves", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int)
 _sig("vit_cuda_forward_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_enqueue_device", C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 _sig("vit_cuda_sync", C.c_int, C.c_int)
@@ -294,6 +296,25 @@ def shard_range(n: int, n_gpus: int, g: int) -> tuple[int, int]:
 def pass_schedule(n_images: int, max_batch: int, staged: bool = False, growth_percent: int = 300) -> list[tuple[int, int]]:
     first, count = (C.c_int * 64)(), (C.c_int * 64)()
     n = lib.vit_cuda_pass_schedule_growth(n_images, max_batch, 1 if staged else 0, growth_percent, first, count, 64)
+    if n < 0:
+        _check(n)
+    return [(first[i], count[i]) for i in range(n)]
+
+
+def pass_schedule_waves(n_images: int, max_batch: int, tokens: int = 197, sm_count: int = 148, staged: bool = False,
+                        growth_percent: int = 300) -> list[tuple[int, int]]:
+    """The wave-efficient schedule vit_cuda_forward runs (vit_cuda_pass_schedule_waves)."""
+    first, count = (C.c_int * 256)(), (C.c_int * 256)()
+    n = lib.vit_cuda_pass_schedule_waves(n_images, max_batch, 1 if staged else 0, growth_percent, tokens, sm_count, first, count, 256)
+    if n < 0:
+        _check(n)
+    return [(first[i], count[i]) for i in range(n)]
+
+
+def pass_schedule_model(n_images: int, max_batch: int, copy_us: float, kernel_us: float, fixed_us: float) -> list[tuple[int, int]]:
+    """vit_cuda_pass_schedule_model: pass sizes from the pipeline's cost model (before the wave-efficient re-cut)."""
+    first, count = (C.c_int * 256)(), (C.c_int * 256)()
+    n = lib.vit_cuda_pass_schedule_model(n_images, max_batch, copy_us, kernel_us, fixed_us, first, count, 256)
     if n < 0:
         _check(n)
     return [(first[i], count[i]) for i in range(n)]
