@@ -237,7 +237,8 @@ def abi_inproc(V, weights, S, B, G, steps, prec, per_process_e2e):
         info = eng.info()
         res["pinned"] = {"value": n * steps / dt, "unit": "images/s", "ms_per_call": dt / steps * 1e3,
                          "vs_one_process_per_gpu_e2e": n * steps / dt / per_process_e2e,
-                         "pass_growth_percent_slot0": info["pass_growth_percent"], "h2d_mb_per_s_slot0": info["h2d_mb_per_s"]}
+                         "pass_growth_percent_slot0": info["pass_growth_percent"], "h2d_mb_per_s_slot0": info["h2d_mb_per_s"],
+                         "pass_fixed_us_slot0": info["pass_fixed_us"], "pass_ns_per_image_slot0": info["pass_ns_per_image"]}
         checksum = int(h_log.argmax(1).sum())
         eng.set_option(V.OPT_HOST_THREADS, 0)
         eng.forward_raw(ip, n, lp)
@@ -587,6 +588,7 @@ def run_ours(args):
             "step_breakdown_ms": step_ms_by_cat, "ms_per_step_with_launch_events": ms_profiled,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h_imgs.nbytes), "d2h_bytes_per_step": int(h_logits.nbytes),
                     "ms_per_step": e2e_s / args.steps * 1e3, "pass_growth_percent": e2e_info["pass_growth_percent"],
+                    "pass_cost_model": {"fixed_us_per_pass": e2e_info["pass_fixed_us"], "kernel_ns_per_image": e2e_info["pass_ns_per_image"]},
                     "h2d_mb_per_s": e2e_info["h2d_mb_per_s"], "reference_signature_form": scattered},
             "gpu_launches": int(launches), "clocks": clocks, "engine": eng.info(), "top1_checksum": int(top1.sum()),
         }

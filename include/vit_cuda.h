@@ -208,7 +208,8 @@ int vit_cuda_get_option(int option, int* value);
  * {sm_count, cc_major, cc_minor, max_batch, tokens, active operand precision (VIT_PREC_BF16 / FP16), n_gpus,
  *  ws_bytes>>20, attention_exact, attention_fallbacks, class_row_pruning, precision policy (VIT_PREC_*),
  *  precision_fallbacks, weight_bytes>>20, pass-schedule growth percent of slot 0 (see vit_cuda_pass_schedule_growth),
- *  measured H2D copy rate of slot 0 in MB/s (0 until measured)}. */
+ *  measured H2D copy rate of slot 0 in MB/s (0 until measured), fitted fixed cost of a pass on slot 0 in microseconds and
+ *  kernel time per image in nanoseconds (vit_cuda_pass_schedule_model; 0 until a call with two passes has been timed)}. */
 int vit_cuda_info(long long* out, int n);
 
 /* CUDA-event stopwatch on a slot's stream: start records an event, stop records a second one,

@@ -1677,9 +1677,11 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
             }
             cudaGetLastError();
         }
-        // kernels of a pass = fixed + per-image * images: least squares over this call's passes (needs two different sizes)
+        // kernels of a pass = fixed + per-image * images: least squares of the RELATIVE error over this call's passes (weights
+        // 1 / images^2: the per-image rate falls a little with the size of a pass, and it is the small passes whose duration
+        // the schedule has to predict -- the next pass's copy must hide under them); needs two different sizes
         {
-            double sn = 0, st = 0, snn = 0, snt = 0;
+            double sw = 0, sn = 0, st = 0, snn = 0, snt = 0;
             int m = 0;
             for (int pass = 0; pass < n_timed; ++pass) {
                 float b = 0;
@@ -1687,13 +1689,13 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
                     cudaGetLastError();
                     continue;
                 }
-                const double nb = pass_count[pass];
-                sn += nb, st += b, snn += nb * nb, snt += nb * b;
+                const double nb = pass_count[pass], w = 1.0 / (nb * nb);
+                sw += w, sn += w * nb, st += w * b, snn += w * nb * nb, snt += w * nb * b;
                 ++m;
             }
-            const double det = m * snn - sn * sn;
-            if (m >= 2 && det > 0) {
-                const double slope = (m * snt - sn * st) / det, icpt = (st - slope * sn) / m;
+            const double det = sw * snn - sn * sn;
+            if (m >= 2 && det > 1e-12 * sw * snn) {
+                const double slope = (sw * snt - sn * st) / det, icpt = (st - slope * sn) / sw;
                 if (slope > 0 && icpt >= 0 && icpt < 5.0) {
                     const double w = c.pass_ms_per_image > 0 ? 0.5 : 1.0;
                     c.pass_ms_per_image = (1 - w) * c.pass_ms_per_image + w * slope;
@@ -1834,12 +1836,13 @@ int vit_cuda_info(long long* out, int n) {
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, c.device));
     const double img_mb = 3.0 * g_eng.img * g_eng.img * 4 / 1e6;
-    const long long v[16] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
+    const long long v[18] = {c.sm_count, prop.major, prop.minor, g_eng.max_batch, g_eng.tokens, g_eng.prec,
                              (long long)g_eng.ctx.size(), (long long)(c.ws_bytes >> 20), g_opt.attn_exact.load() ? 1 : 0,
                              g_eng.attn_fallbacks, g_opt.prune_last.load() ? 1 : 0, g_eng.policy, g_eng.prec_fallbacks,
                              (long long)(c.arena_bytes >> 20), schedule_growth(c),
-                             c.h2d_ms_per_image > 0 ? (long long)(img_mb / c.h2d_ms_per_image * 1e3) : 0};
-    for (int i = 0; i < n && i < 16; ++i) out[i] = v[i];
+                             c.h2d_ms_per_image > 0 ? (long long)(img_mb / c.h2d_ms_per_image * 1e3) : 0,
+                             (long long)(1e3 * c.pass_fixed_ms + 0.5), (long long)(1e6 * c.pass_ms_per_image + 0.5)};
+    for (int i = 0; i < n && i < 18; ++i) out[i] = v[i];
     return 0;
 }
 

@@ -257,11 +257,11 @@ class Engine:
         return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(PROF_CATEGORIES)}
 
     def info(self) -> dict:
-        v = (C.c_longlong * 16)()
-        _check(lib.vit_cuda_info(v, 16))
+        v = (C.c_longlong * 18)()
+        _check(lib.vit_cuda_info(v, 18))
         keys = ["sm_count", "cc_major", "cc_minor", "max_batch", "tokens", "precision", "n_gpus", "workspace_mib",
                 "attention_exact", "attention_fallbacks", "class_row_pruning", "precision_policy", "precision_fallbacks", "weights_mib",
-                "pass_growth_percent", "h2d_mb_per_s"]
+                "pass_growth_percent", "h2d_mb_per_s", "pass_fixed_us", "pass_ns_per_image"]
         d = dict(zip(keys, [int(x) for x in v]))
         d["precision"] = PREC_NAMES[d["precision"]]            # the operand type the next pass runs in
         d["precision_policy"] = PREC_NAMES[d["precision_policy"]]
