@@ -1561,7 +1561,8 @@ int run_shard(Engine& e, int g, const HostJob& job, unsigned int* flags_out) {
         const double img_bytes = static_cast<double>(img_elems) * sizeof(float);
         const double copy_us = c.h2d_ms_per_image > 0 ? 1e3 * c.h2d_ms_per_image : img_bytes / 55e3;
         const double kern_us = c.pass_ms_per_image > 0 ? 1e3 * c.pass_ms_per_image : 34.3 * std::pow(e.tokens / 197.0, 1.1);
-        const double fixed_us = c.pass_ms_per_image > 0 ? 1e3 * c.pass_fixed_ms : 700.0;
+        const double fixed_us = c.pass_ms_per_image > 0 ? std::max(200.0, 1e3 * c.pass_fixed_ms) : 700.0;   // (a fit that lost the fixed cost
+                                                                                                             // would ask for a string of tiny passes)
         n_pass = vit_cuda_pass_schedule_model(std::min(job.per_gpu, hi - lo), e.max_batch, copy_us, kern_us, fixed_us, pass_first.data(), pass_count.data(), worst);
     } else {
         n_pass = vit_cuda_pass_schedule_growth(job.per_gpu, e.max_batch, staged ? 1 : 0, schedule_growth(c), pass_first.data(), pass_count.data(), worst);
